@@ -1,0 +1,202 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU (numpy) restatement of the reference's GPU rulebook builders.
+
+Nothing under occuseg_b200/ may import this module; only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs do, and only as the checker.
+
+The reference builds its rulebooks with CUDA + the vendored cudpp cuckoo hash (GPU_GRID is
+hard-defined, Metadata/Metadata.h:42), which cannot be built or run here,
+and it ships no golden vectors for them.  PARITY FOR THE RULEBOOKS IS
+THEREFORE PINNED BY THIS RESTATEMENT ONLY ("parity unpinned" by any reference-side fixture);
+the floating-point arithmetic, by contrast, is pinned by the reference's own CPU code compiled
+unmodified (oracle/ref_shim.cpp).
+
+Each function cites the reference lines it restates.  All paths relative to
+/root/reference/sparseconvnet/SCN/ unless noted.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+NOT_FOUND = -1
+
+
+def key31(x, y, z):
+    """31-bit coordinate key, z most significant: CUDA/CUDPPWrapper.cu:80-81, :112-113;
+    neighbour queries use the same packing (CUDA/SubmanifoldRules_cuda.cu:68-69).
+    Arithmetic is done on 32-bit two's-complement words exactly as the device code does, so
+    out-of-range coordinates alias the same way (x: bits 0-9, y: 10-20, z: 21-30)."""
+    x = np.asarray(x).astype(np.int64).astype(np.uint32)      # wrap like a C cast of Int/long -> uint32
+    y = np.asarray(y).astype(np.int64).astype(np.uint32)
+    z = np.asarray(z).astype(np.int64).astype(np.uint32)
+    return ((z << np.uint32(21)) | (y << np.uint32(10)) | x) & np.uint32(0x7FFFFFFF)
+
+
+def _sample_bounds(batch_col, batch_size):
+    """Per-sample [start,end) in a batch-sorted coordinate list: CUDPPWrapper.cu:84-87 +
+    CUDPPWrapper.hpp:676-677 (start[0]=0, start[B]=P)."""
+    b = np.asarray(batch_col)
+    assert np.all(b[1:] >= b[:-1]), "reference requires the batch column to be sorted ascending"
+    starts = np.searchsorted(b, np.arange(batch_size), side="left")
+    return np.concatenate([starts, [len(b)]]).astype(np.int64)
+
+
+def voxelize(coords, batch_size=None):
+    """InputLayer rules (modes 3/4): Metadata/IOLayersRules.h:136-202.
+
+    Per sample: stable radix sort of (key, pointIndex) (cudpp_hash/hash_multivalue.cpp:45-56), unique keys,
+    voxel id = rank of the key among the sample's unique sorted keys (hash_multivalue.cpp:59-110,
+    CUDPPWrapper.cu:210-229) + ctr of the previous samples (IOLayersRules.h:164-169).
+
+    Returns dict with
+      locs    int64 [N,4]  (x,y,z,b) of every active row in row order  (Metadata.cpp:724-748)
+      row_of_point int32 [P]
+      rule_ptr int64 [N+1], rule_pts int32 [P]   CSR form of the reference's [N][1+maxRepeat] table
+                                                  (CUDPPWrapper.cu:53-64): points of row v in rule order
+      max_repeat, sample_ctr int64 [B+1]
+    """
+    coords = np.asarray(coords, dtype=np.int64)
+    P = coords.shape[0]
+    if batch_size is None:
+        batch_size = int(coords[:, 3].max()) + 1 if P else 0
+    bounds = _sample_bounds(coords[:, 3], batch_size)
+    locs, row_of_point = [], np.empty(P, np.int32)
+    rule_ptr, rule_pts = [np.zeros(1, np.int64)], []
+    ctr = [0]
+    max_repeat = 0
+    for b in range(batch_size):
+        s, e = bounds[b], bounds[b + 1]
+        k = key31(coords[s:e, 0], coords[s:e, 1], coords[s:e, 2])
+        order = np.argsort(k, kind="stable")                       # radix sort is stable
+        ks = k[order]
+        head = np.ones(e - s, bool)
+        head[1:] = ks[1:] != ks[:-1]                               # check_if_unique, hash_multivalue.cu:53-63
+        rank = np.cumsum(head) - 1
+        n = int(head.sum())
+        first = order[head]                                        # first point of each key group
+        locs.append(np.concatenate([coords[s:e][first, :3], np.full((n, 1), b, np.int64)], 1))
+        row_of_point[s + order] = rank + ctr[-1]
+        starts = np.flatnonzero(head)
+        counts = np.diff(np.concatenate([starts, [e - s]]))
+        if n:
+            max_repeat = max(max_repeat, int(counts.max()))
+        rule_ptr.append(rule_ptr[-1][-1] + np.cumsum(counts))
+        rule_pts.append((order + s).astype(np.int32))              # d_index[tid] = tid is global (CUDPPWrapper.cu:82)
+        ctr.append(ctr[-1] + n)
+    return dict(
+        locs=np.concatenate(locs, 0) if locs else np.zeros((0, 4), np.int64),
+        row_of_point=row_of_point,
+        rule_ptr=np.concatenate(rule_ptr),
+        rule_pts=np.concatenate(rule_pts) if rule_pts else np.zeros(0, np.int32),
+        max_repeat=max_repeat,
+        sample_ctr=np.asarray(ctr, np.int64),
+    )
+
+
+def _ctr_from_locs(locs, batch_size):
+    return _sample_bounds(locs[:, 3], batch_size)
+
+
+def submanifold_rules(locs, batch_size=None):
+    """27 rule lists for a 3x3x3 submanifold convolution:
+    Metadata/SubmanifoldConvolutionRules.h:435-468 (per-sample loop, lists appended) ->
+    CUDA/SubmanifoldRules_cuda.cpp:97-202.  Offset index k enumerates dx outermost, dz innermost
+    (SubmanifoldRules_cuda.cu:63-73): k = (dx+1)*9 + (dy+1)*3 + (dz+1).  For each voxel `self`
+    whose neighbour key is present in the SAME sample the pair (hit+ctr, self+ctr) is emitted
+    (SubmanifoldRules_cuda.cu:102-107); stream compaction keeps `self` ascending (:167-187).
+
+    Returns list of 27 int32 arrays [n_k, 2] = (inputRow, outputRow).
+    """
+    locs = np.asarray(locs, np.int64)
+    if batch_size is None:
+        batch_size = int(locs[:, 3].max()) + 1 if len(locs) else 0
+    ctr = _ctr_from_locs(locs, batch_size)
+    out = [[] for _ in range(27)]
+    for b in range(batch_size):
+        s, e = ctr[b], ctr[b + 1]
+        x, y, z = locs[s:e, 0], locs[s:e, 1], locs[s:e, 2]
+        keys = key31(x, y, z)                                       # sorted ascending == row order
+        assert np.all(keys[1:] > keys[:-1]), "rows must be in sorted-key order"
+        self_rows = np.arange(s, e, dtype=np.int32)
+        k = 0
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    q = key31(x + dx, y + dy, z + dz)
+                    pos = np.searchsorted(keys, q)
+                    pos_c = np.minimum(pos, max(e - s - 1, 0))
+                    hit = (keys[pos_c] == q) if e > s else np.zeros(0, bool)
+                    pairs = np.stack([(pos_c[hit] + s).astype(np.int32), self_rows[hit]], 1)
+                    out[k].append(pairs)
+                    k += 1
+    return [np.concatenate(l, 0) if l else np.zeros((0, 2), np.int32) for l in out]
+
+
+def strided_rules(locs, batch_size=None):
+    """Size-2 / stride-2 Convolution rules + the coarse grid they create:
+    Metadata/ConvolutionRules.h:344-378 (FastDownSampleMode, the path taken when no normals are
+    given, :774-785).  out = in/2 per axis; coarse row id = rank of key31(out) among the sample's
+    unique sorted coarse keys (Multival hash insert/retrieve) + coarse ctr; offset index
+    ((x&1)*2 + (y&1))*2 + (z&1) (SubmanifoldRules_cuda.cu:549-554); pair = (fineRow, coarseRow)
+    (:563-564), compaction keeps fineRow ascending.
+
+    Returns (coarse_locs int64 [Nc,4], list of 8 int32 arrays [n_k,2]).
+    Deconvolution uses the same lists with the columns' roles swapped (CUDA/Deconvolution.cpp:28-29).
+    """
+    locs = np.asarray(locs, np.int64)
+    if batch_size is None:
+        batch_size = int(locs[:, 3].max()) + 1 if len(locs) else 0
+    ctr = _ctr_from_locs(locs, batch_size)
+    lists = [[] for _ in range(8)]
+    coarse = []
+    octr = 0
+    for b in range(batch_size):
+        s, e = ctr[b], ctr[b + 1]
+        fine = locs[s:e, :3]
+        c = fine // 2
+        ck = key31(c[:, 0], c[:, 1], c[:, 2])
+        uk, first, inv = np.unique(ck, return_index=True, return_inverse=True)
+        coarse.append(np.concatenate([c[first], np.full((len(uk), 1), b, np.int64)], 1))
+        off = ((fine[:, 0] - 2 * c[:, 0]) * 2 + (fine[:, 1] - 2 * c[:, 1])) * 2 + (fine[:, 2] - 2 * c[:, 2])
+        rows = np.arange(s, e, dtype=np.int32)
+        for k in range(8):
+            m = off == k
+            lists[k].append(np.stack([rows[m], (inv[m] + octr).astype(np.int32)], 1))
+        octr += len(uk)
+    coarse_locs = np.concatenate(coarse, 0) if coarse else np.zeros((0, 4), np.int64)
+    return coarse_locs, [np.concatenate(l, 0) if l else np.zeros((0, 2), np.int32) for l in lists]
+
+
+def canonical(rule_lists):
+    """Canonical form used for bit-exact comparison: every list sorted by (out, in)."""
+    out = []
+    for r in rule_lists:
+        r = np.asarray(r, np.int32).reshape(-1, 2)
+        order = np.lexsort((r[:, 0], r[:, 1]))
+        out.append(r[order])
+    return out
+
+
+def rules_from_neighbour_table(nbr):
+    """Turn an output-stationary table nbr[V][N] (input row or -1) into the reference's rule lists."""
+    nbr = np.asarray(nbr)
+    lists = []
+    for k in range(nbr.shape[0]):
+        o = np.flatnonzero(nbr[k] >= 0).astype(np.int32)
+        lists.append(np.stack([nbr[k][o].astype(np.int32), o], 1))
+    return lists
+
+
+def input_layer_mean(feats, vox, average=True):
+    """InputLayer forward, modes 3/4: CUDA/IOLayers.cu:16-31 -- out[row] += (1/n) * in[p] in rule order,
+    accumulated in fp32."""
+    feats = np.asarray(feats, np.float32)
+    N = len(vox["rule_ptr"]) - 1
+    out = np.zeros((N, feats.shape[1]), np.float32)
+    ptr, pts = vox["rule_ptr"], vox["rule_pts"]
+    cnt = np.diff(ptr)
+    mult = np.where(cnt > 0, np.float32(1) / cnt.astype(np.float32), np.float32(1)).astype(np.float32) if average \
+        else np.ones(N, np.float32)
+    for j in range(int(cnt.max()) if N else 0):
+        m = cnt > j
+        out[m] += mult[m, None] * feats[pts[ptr[:-1][m] + j]]
+    return out
