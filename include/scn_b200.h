@@ -1,0 +1,124 @@
+/*
+ * scn_b200.h -- C ABI of libscn_b200.so: the B200 (sm_100a) replacement for the hot path behind
+ * OccuSeg's pybind11 module `sparseconvnet.SCN` (reference: sparseconvnet/SCN/pybind.cpp:11-239,
+ * sparseconvnet/SCN/sparseconvnet.h:9-239).  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *  - every feature matrix is dense row-major fp32 [rows, channels] in DEVICE memory, one row per
+ *    active voxel, samples concatenated (reference layout, SURVEY.md "Vocabulary");
+ *  - weights are the reference's [V, Cin, Cout] fp32 (V=27 submanifold, k=(dx+1)*9+(dy+1)*3+(dz+1),
+ *    CUDA/SubmanifoldRules_cuda.cu:63-73; V=8 strided, k=(x&1)*4+(y&1)*2+(z&1), :549-554);
+ *  - a spatial size is the int64[3] the Python layer carries (cubes in practice); it names a scale
+ *    inside a handle exactly as Metadata's maps are keyed (Metadata/Metadata.h:238-248);
+ *  - all work is enqueued on the caller's CUDA stream (`stream` is a cudaStream_t passed as void*);
+ *    the only host synchronisations are the ones that return a row count to the caller;
+ *  - every entry returns 0 on success, non-zero on failure, message via scn_last_error().  The
+ *    library never calls exit()/abort() (the reference does: CUDPPWrapper.hpp:15-25,
+ *    Convolution.cu:14-24);
+ *  - the library never allocates caller-visible memory: the caller asks for row counts, allocates,
+ *    and passes pointers.  Outputs are OVERWRITTEN (d_weight too -- the Python wrapper hands in
+ *    zeros like the reference does, submanifoldConvolution.py:113-115, so both conventions agree).
+ *
+ * precision: SCN_FP32 = exact fp32 FMA path (rel 1e-5 vs the reference CPU arithmetic);
+ *            SCN_TF32 = tcgen05 kind::tf32 tiles, fp32 accumulate in TMEM (rel 2e-2), used only
+ *                       when Cin and Cout are multiples of 32 and >= 32, else falls to SCN_FP32.
+ */
+#ifndef SCN_B200_H
+#define SCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scn_meta scn_meta; /* opaque; replaces Metadata<3> (Metadata/Metadata.h:218-364) */
+
+enum { SCN_FP32 = 0, SCN_TF32 = 1 };
+
+/* ---- library --------------------------------------------------------------------------------- */
+int scn_version(void);
+const char *scn_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t scn_launch_count(void);
+
+/* ---- handle: replaces py `Metadata_3()` / ~Metadata (pybind.cpp:11-13) ------------------------ */
+scn_meta *scn_meta_create(int device);
+void scn_meta_destroy(scn_meta *m);
+
+/* ---- InputLayer: replaces InputLayer_updateOutput's Metadata::inputLayer -> inputLayerRulesSimple
+ * (CUDA/IOLayers.cpp:17-80, Metadata/Metadata.cpp:425-437, Metadata/IOLayersRules.h:136-202).
+ * coords: int64 [P,4] (x,y,z,batch), batch column ascending; host pointer unless coords_on_device.
+ * Builds the finest scale: voxel row = rank of (z,y,x) among the sample's unique voxels + rows of
+ * earlier samples.  *n_active receives the row count (one host sync). mode must be 3 (sum) or 4 (mean). */
+int scn_input_layer_build(scn_meta *m, const int64_t spatial_size[3], const int64_t *coords, int coords_on_device,
+                          int64_t n_points, int batch_size, int mode, void *stream, int64_t *n_active);
+/* feature part of InputLayer_updateOutput (CUDA/IOLayers.cu:16-43): out[N,C] = sum/mean of the points of each voxel */
+int scn_input_layer_fwd(scn_meta *m, const float *point_feats, int channels, float *out, void *stream);
+/* InputLayer_updateGradInput (CUDA/IOLayers.cpp:81-105): d_point[P,C] = (1/n) * d_out[row(p)] */
+int scn_input_layer_bwd(scn_meta *m, const float *d_out, int channels, float *d_point_feats, void *stream);
+/* OutputLayer_updateOutput (CUDA/IOLayers.cpp:107-130): out[P,C] = in[row(p)] */
+int scn_output_layer_fwd(scn_meta *m, const float *in, int channels, float *out_points, void *stream);
+/* OutputLayer_updateGradInput (CUDA/IOLayers.cpp:131-154): d_in[N,C] = sum over the voxel's points of d_out[p] */
+int scn_output_layer_bwd(scn_meta *m, const float *d_out_points, int channels, float *d_in, void *stream);
+int64_t scn_n_points(scn_meta *m);
+
+/* ---- scale queries: Metadata::getNActive / getSpatialLocations (Metadata.cpp:89-92, :724-748) -- */
+int64_t scn_nactive(scn_meta *m, const int64_t spatial_size[3]); /* -1 if the scale does not exist */
+/* locations int64 [N,4] (x,y,z,batch) in row order, written to HOST memory */
+int scn_spatial_locations(scn_meta *m, const int64_t spatial_size[3], int64_t *out_host);
+
+/* ---- rulebooks (built lazily and cached per scale like Metadata::getSubmanifoldRuleBook /
+ * getRuleBook, Metadata.cpp:503-529,597-625).  Exposed so parity tests can compare them bit-exactly
+ * with the reference's rule lists after canonical sorting. ------------------------------------- */
+/* ensure the 27-offset neighbour table of a scale exists; *n_rules = total rule count (centre included) */
+int scn_subm_rulebook(scn_meta *m, const int64_t spatial_size[3], void *stream, int64_t *n_rules);
+/* copy the table to HOST: int32 [27, N]; entry = input row feeding output row o at offset k, or -1 */
+int scn_subm_neighbour_table(scn_meta *m, const int64_t spatial_size[3], int32_t *out_host);
+/* build (if needed) the size-2/stride-2 link fine -> coarse and the coarse scale; *n_coarse = its rows */
+int scn_strided_rulebook(scn_meta *m, const int64_t fine_size[3], const int64_t coarse_size[3], void *stream,
+                         int64_t *n_coarse);
+/* copy to HOST: parent int32 [Nfine] (coarse row of each fine row) and offset uint8 [Nfine] (0..7) */
+int scn_strided_table(scn_meta *m, const int64_t fine_size[3], int32_t *parent_host, uint8_t *offset_host);
+
+/* ---- SubmanifoldConvolution_updateOutput / _backward (sparseconvnet.h:50-61; drivers
+ * CUDA/Convolution.cpp:104-210; kernels CUDA/Convolution.cu:447-534,695-753,1059-1152) ----------
+ * out[N,Cout] = sum_k in[nbr_k(o)] * W[k];  *macs = sum_k n_k*Cin*Cout (the reference's return value) */
+int scn_subm_fwd(scn_meta *m, const int64_t spatial_size[3], const float *in, const float *weight, const float *bias,
+                 float *out, int c_in, int c_out, int precision, void *stream, double *macs);
+/* d_in[N,Cin], d_weight[27,Cin,Cout], d_bias[Cout] (NULL when no bias) */
+int scn_subm_bwd(scn_meta *m, const int64_t spatial_size[3], const float *in, const float *d_out, const float *weight,
+                 float *d_in, float *d_weight, float *d_bias, int c_in, int c_out, int precision, void *stream);
+
+/* ---- Convolution (size 2, stride 2): sparseconvnet.h:89-102, CUDA/Convolution.cpp:36-102 ------- */
+int scn_conv_fwd(scn_meta *m, const int64_t in_size[3], const int64_t out_size[3], const float *in, const float *weight,
+                 const float *bias, float *out, int c_in, int c_out, int precision, void *stream, double *macs);
+int scn_conv_bwd(scn_meta *m, const int64_t in_size[3], const int64_t out_size[3], const float *in, const float *d_out,
+                 const float *weight, float *d_in, float *d_weight, float *d_bias, int c_in, int c_out, int precision,
+                 void *stream);
+
+/* ---- Deconvolution (size 2, stride 2), reuses the down-convolution's rulebook:
+ * sparseconvnet.h:103-116, CUDA/Deconvolution.cpp:19-84.  in_size is the COARSE scale. ----------- */
+int scn_deconv_fwd(scn_meta *m, const int64_t in_size[3], const int64_t out_size[3], const float *in,
+                   const float *weight, const float *bias, float *out, int c_in, int c_out, int precision, void *stream,
+                   double *macs);
+int scn_deconv_bwd(scn_meta *m, const int64_t in_size[3], const int64_t out_size[3], const float *in,
+                   const float *d_out, const float *weight, float *d_in, float *d_weight, float *d_bias, int c_in,
+                   int c_out, int precision, void *stream);
+
+/* ---- BatchNormalization_updateOutput / _backward with the fused (leaky) ReLU
+ * (sparseconvnet.h:21-33, CUDA/BatchNormalization.cpp:21-71, BatchNormalization.cu:14-199) --------
+ * train: batch statistics, running = momentum*running + (1-momentum)*batch (unbiased var);
+ * y = leaky(gamma*(x-mean)*invstd + beta); leakiness 0 = ReLU, 1 = identity.  gamma/beta may be NULL. */
+int scn_bn_fwd(const float *in, float *out, float *save_mean, float *save_invstd, float *running_mean,
+               float *running_var, const float *gamma, const float *beta, int64_t n_rows, int channels, float eps,
+               float momentum, int train, float leakiness, void *stream);
+/* d_out is NOT modified (the reference masks it in place, BatchNormalization.cu:151-153; no caller observes it) */
+int scn_bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
+               const float *gamma, float *d_in, float *d_gamma, float *d_beta, int64_t n_rows, int channels,
+               float leakiness, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCN_B200_H */

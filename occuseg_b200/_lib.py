@@ -1,0 +1,86 @@
+"""ctypes binding of libscn_b200.so (include/scn_b200.h).  There is no fallback: if the CUDA library is
+missing or an entry fails, the caller gets an exception -- never a CPU or PyTorch substitute."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libscn_b200.so")
+
+FP32, TF32 = 0, 1
+
+_i64p = C.POINTER(C.c_int64)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes); kept in one table so tests can check it against include/scn_b200.h
+PROTOTYPES = {
+    "scn_version": (C.c_int, []),
+    "scn_last_error": (C.c_char_p, []),
+    "scn_launch_count": (C.c_int64, []),
+    "scn_meta_create": (_vp, [C.c_int]),
+    "scn_meta_destroy": (None, [_vp]),
+    "scn_input_layer_build": (C.c_int, [_vp, _i64p, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _i64p]),
+    "scn_input_layer_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "scn_input_layer_bwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "scn_output_layer_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "scn_output_layer_bwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "scn_n_points": (C.c_int64, [_vp]),
+    "scn_nactive": (C.c_int64, [_vp, _i64p]),
+    "scn_spatial_locations": (C.c_int, [_vp, _i64p, _vp]),
+    "scn_subm_rulebook": (C.c_int, [_vp, _i64p, _vp, _i64p]),
+    "scn_subm_neighbour_table": (C.c_int, [_vp, _i64p, _vp]),
+    "scn_strided_rulebook": (C.c_int, [_vp, _i64p, _i64p, _vp, _i64p]),
+    "scn_strided_table": (C.c_int, [_vp, _i64p, _vp, _vp]),
+    "scn_subm_fwd": (C.c_int, [_vp, _i64p, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
+    "scn_subm_bwd": (C.c_int, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "scn_conv_fwd": (C.c_int, [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
+    "scn_conv_bwd": (C.c_int, [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "scn_deconv_fwd": (C.c_int, [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
+    "scn_deconv_bwd": (C.c_int, [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "scn_bn_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, _vp]),
+    "scn_bn_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, _vp]),
+}
+
+_lib = None
+
+
+class ScnError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the CDLL.  Raises if the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ScnError(
+                f"{LIB_PATH} not found: build it with `python occuseg_b200/csrc/build.py` "
+                "(there is no CPU fallback for this path)")
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise ScnError(lib().scn_last_error().decode("utf-8", "replace"))
+
+
+def size3(v):
+    """int / sequence / LongTensor -> ctypes int64[3]"""
+    if hasattr(v, "tolist"):
+        v = v.tolist()
+    if isinstance(v, (int,)):
+        v = [v, v, v]
+    v = [int(x) for x in v]
+    assert len(v) == 3, "only 3-D grids are on this path"
+    return (C.c_int64 * 3)(*v)
+
+
+def launch_count():
+    return int(lib().scn_launch_count())

@@ -1,0 +1,253 @@
+// BatchNorm + (leaky) ReLU, forward and backward.  Replaces BatchNormalization_f_train / f_test / _b
+// (CUDA/BatchNormalization.cu:14-199, dispatch :201-238; drivers CUDA/BatchNormalization.cpp:21-71).
+//
+// The reference walks all N rows with at most 16 CTAs (grid = min(16, C/NTX)) and accumulates the
+// statistics as fp32 running sums.  Here the reduction is spread over 2 CTAs per SM, partial sums are
+// short fp32 chains merged in fp64, and the normalise pass is a 128-bit streaming kernel.
+// HBM-bound: forward 3*N*C*4 bytes (read x twice, write y), backward 5*N*C*4.
+#include "common.cuh"
+
+namespace scn {
+
+constexpr int BX = 64, BY = 4;          // block = 64 column lanes x 4 row lanes
+constexpr int ROWS_PER_STEP = 256;      // rows a CTA folds in fp32 before flushing to fp64
+
+// column sums of u(x) and v(x):  MODE 0: (x, x*x)          (forward statistics)
+//                                MODE 1: (d', (x-mean)*d')  with d' = d * (y>0 ? 1 : leak)   (backward)
+template <int VEC, int MODE>
+__global__ void __launch_bounds__(BX *BY) k_bn_reduce(const float *__restrict__ x, const float *__restrict__ y,
+                                                       const float *__restrict__ d, const float *__restrict__ mean,
+                                                       long long n, int C, float leak, double *__restrict__ acc) {
+  const int cv = C / VEC;
+  __shared__ float red[2][BY][BX * VEC];
+  for (int cg0 = 0; cg0 < cv; cg0 += BX) {
+    const int cg = cg0 + threadIdx.x;
+    const bool live = cg < cv;
+    float m[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) m[j] = (MODE == 1 && live) ? __ldg(&mean[cg * VEC + j]) : 0.f;
+    for (long long rb = (long long)blockIdx.x * ROWS_PER_STEP; rb < n; rb += (long long)gridDim.x * ROWS_PER_STEP) {
+      float s0[VEC], s1[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) s0[j] = s1[j] = 0.f;
+      if (live) {
+        long long rend = rb + ROWS_PER_STEP < n ? rb + ROWS_PER_STEP : n;
+        for (long long r = rb + threadIdx.y; r < rend; r += BY) {
+          float xv[VEC], yv[VEC], dv[VEC];
+          if (VEC == 4) {
+            float4 t = __ldg(reinterpret_cast<const float4 *>(x + r * C) + cg);
+            xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+            if (MODE == 1) {
+              float4 u = __ldg(reinterpret_cast<const float4 *>(y + r * C) + cg);
+              float4 w = __ldg(reinterpret_cast<const float4 *>(d + r * C) + cg);
+              yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
+              dv[0] = w.x; dv[1] = w.y; dv[2] = w.z; dv[3] = w.w;
+            }
+          } else {
+            xv[0] = __ldg(x + r * C + cg);
+            if (MODE == 1) { yv[0] = __ldg(y + r * C + cg); dv[0] = __ldg(d + r * C + cg); }
+          }
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            if (MODE == 0) {
+              s0[j] += xv[j];
+              s1[j] = fmaf(xv[j], xv[j], s1[j]);
+            } else {
+              float dd = yv[j] > 0.f ? dv[j] : dv[j] * leak;
+              s0[j] += dd;
+              s1[j] = fmaf(xv[j] - m[j], dd, s1[j]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        red[0][threadIdx.y][threadIdx.x * VEC + j] = s0[j];
+        red[1][threadIdx.y][threadIdx.x * VEC + j] = s1[j];
+      }
+      __syncthreads();
+      // BY partials per column -> fp64 -> one atomic per column per step
+      for (int e = threadIdx.y * BX + threadIdx.x; e < 2 * BX * VEC; e += BX * BY) {
+        int which = e / (BX * VEC), col = e % (BX * VEC);
+        int c = cg0 * VEC + col;
+        if (c < C) {
+          double t = 0.0;
+#pragma unroll
+          for (int i = 0; i < BY; ++i) t += (double)red[which][i][col];
+          atomicAdd(&acc[which * C + c], t);
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// forward finalize: mean / invstd / running statistics.  Formulas follow BatchNormalization.cu:38-51
+// (biased variance for normalisation, unbiased for the running estimate), evaluated in fp64.
+__global__ void k_bn_finalize_fwd(const double *__restrict__ acc, long long n, int C, float eps, float momentum,
+                                  bool train, float *__restrict__ save_mean, float *__restrict__ save_invstd,
+                                  float *__restrict__ running_mean, float *__restrict__ running_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (train) {
+    double mean = acc[c] / (double)n;
+    double var_sum = acc[C + c] - mean * mean * (double)n;
+    if (var_sum < 0.0) var_sum = 0.0;
+    save_mean[c] = (float)mean;
+    save_invstd[c] = (float)(1.0 / sqrt(var_sum / (double)n + (double)eps));
+    running_mean[c] = momentum * running_mean[c] + (1.f - momentum) * (float)mean;
+    running_var[c] = momentum * running_var[c] + (1.f - momentum) * (float)(var_sum / (double)(n - 1));
+  } else {
+    save_mean[c] = running_mean[c];
+    save_invstd[c] = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_bn_apply_fwd(const float *__restrict__ x, float *__restrict__ y,
+                                                      const float *__restrict__ save_mean,
+                                                      const float *__restrict__ save_invstd,
+                                                      const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                      long long n, int C, float leak) {
+  extern __shared__ float wb[];   // [2][C]: w = invstd*gamma, b = beta - mean*w  (BatchNormalization.cu:56-60)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float w = save_invstd[c] * (gamma ? gamma[c] : 1.f);
+    wb[c] = w;
+    wb[C + c] = -save_mean[c] * w + (beta ? beta[c] : 0.f);
+  }
+  __syncthreads();
+  const int cv = C / VEC;
+  const long long total = n * cv;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int cg = (int)(e % cv);
+    if (VEC == 4) {
+      float4 t = __ldg(reinterpret_cast<const float4 *>(x) + e);
+      float4 w = *reinterpret_cast<const float4 *>(&wb[cg * 4]);
+      float4 b = *reinterpret_cast<const float4 *>(&wb[C + cg * 4]);
+      float4 o;
+      o.x = fmaf(w.x, t.x, b.x); o.y = fmaf(w.y, t.y, b.y); o.z = fmaf(w.z, t.z, b.z); o.w = fmaf(w.w, t.w, b.w);
+      o.x = o.x > 0.f ? o.x : o.x * leak; o.y = o.y > 0.f ? o.y : o.y * leak;
+      o.z = o.z > 0.f ? o.z : o.z * leak; o.w = o.w > 0.f ? o.w : o.w * leak;
+      reinterpret_cast<float4 *>(y)[e] = o;
+    } else {
+      float o = fmaf(wb[cg], __ldg(x + e), wb[C + cg]);
+      y[e] = o > 0.f ? o : o * leak;
+    }
+  }
+}
+
+// backward finalize: d_gamma = dotp*invstd, d_beta = sum d'; coef[0][c] = mean(d'), coef[1][c] = dotp*invstd^2/N
+// (BatchNormalization.cu:160-170)
+__global__ void k_bn_finalize_bwd(const double *__restrict__ acc, long long n, int C,
+                                  const float *__restrict__ save_invstd, float *__restrict__ d_gamma,
+                                  float *__restrict__ d_beta, float *__restrict__ coef) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double gsum = acc[c], dotp = acc[C + c], is = (double)save_invstd[c];
+  if (d_gamma) d_gamma[c] = (float)(dotp * is);
+  if (d_beta) d_beta[c] = (float)gsum;
+  coef[c] = (float)(gsum / (double)n);
+  coef[C + c] = (float)(dotp * is * is / (double)n);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ x, const float *__restrict__ y,
+                                                      const float *__restrict__ d, float *__restrict__ dx,
+                                                      const float *__restrict__ save_mean,
+                                                      const float *__restrict__ save_invstd,
+                                                      const float *__restrict__ gamma, const float *__restrict__ coef,
+                                                      long long n, int C, float leak) {
+  extern __shared__ float sm[];   // [4][C]: mean, gradMean, k, invstd*gamma
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sm[c] = save_mean[c];
+    sm[C + c] = coef[c];
+    sm[2 * C + c] = coef[C + c];
+    sm[3 * C + c] = save_invstd[c] * (gamma ? gamma[c] : 1.f);
+  }
+  __syncthreads();
+  const int cv = C / VEC;
+  const long long total = n * cv;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int c0 = (int)(e % cv) * VEC;
+    float xv[VEC], yv[VEC], dv[VEC], ov[VEC];
+    if (VEC == 4) {
+      float4 t = __ldg(reinterpret_cast<const float4 *>(x) + e);
+      float4 u = __ldg(reinterpret_cast<const float4 *>(y) + e);
+      float4 w = __ldg(reinterpret_cast<const float4 *>(d) + e);
+      xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+      yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
+      dv[0] = w.x; dv[1] = w.y; dv[2] = w.z; dv[3] = w.w;
+    } else {
+      xv[0] = __ldg(x + e); yv[0] = __ldg(y + e); dv[0] = __ldg(d + e);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      int c = c0 + j;
+      float dd = yv[j] > 0.f ? dv[j] : dv[j] * leak;
+      ov[j] = (dd - sm[C + c] - (xv[j] - sm[c]) * sm[2 * C + c]) * sm[3 * C + c];
+    }
+    if (VEC == 4) reinterpret_cast<float4 *>(dx)[e] = make_float4(ov[0], ov[1], ov[2], ov[3]);
+    else dx[e] = ov[0];
+  }
+}
+
+static int stream_grid(long long work_items, int block) {
+  long long g = (work_items + block - 1) / block;
+  long long cap = (long long)sm_count() * 8;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+void bn_fwd(const float *in, float *out, float *save_mean, float *save_invstd, float *running_mean, float *running_var,
+            const float *gamma, const float *beta, long long n, int C, float eps, float momentum, bool train,
+            float leakiness, cudaStream_t s) {
+  SCN_CHECK(C > 0 && C <= 4096, "BatchNorm: channel count out of range");
+  if (n == 0) return;
+  bool v4 = (C % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  DevBuf<double> acc;
+  acc.alloc(2 * (size_t)C, s);
+  if (train) {
+    SCN_CHECK(n > 1, "BatchNorm (train): needs at least two active rows");
+    SCN_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * 2 * C, s));
+    int grid = (int)std::min<long long>((n + ROWS_PER_STEP - 1) / ROWS_PER_STEP, (long long)sm_count() * 2);
+    if (v4) k_bn_reduce<4, 0><<<grid, dim3(BX, BY), 0, s>>>(in, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
+    else k_bn_reduce<1, 0><<<grid, dim3(BX, BY), 0, s>>>(in, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
+    SCN_LAUNCH_CHECK();
+  }
+  k_bn_finalize_fwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, eps, momentum, train, save_mean, save_invstd,
+                                                    running_mean, running_var);
+  SCN_LAUNCH_CHECK();
+  size_t smem = sizeof(float) * 2 * C;
+  if (v4) k_bn_apply_fwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, out, save_mean, save_invstd, gamma, beta, n, C, leakiness);
+  else k_bn_apply_fwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, out, save_mean, save_invstd, gamma, beta, n, C, leakiness);
+  SCN_LAUNCH_CHECK();
+  acc.release(s);
+}
+
+void bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
+            const float *gamma, float *d_in, float *d_gamma, float *d_beta, long long n, int C, float leakiness,
+            cudaStream_t s) {
+  SCN_CHECK(C > 0 && C <= 4096, "BatchNorm: channel count out of range");
+  if (n == 0) return;
+  bool v4 = (C % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)d_out % 16 == 0) &&
+            ((uintptr_t)d_in % 16 == 0);
+  DevBuf<double> acc;
+  DevBuf<float> coef;
+  acc.alloc(2 * (size_t)C, s);
+  coef.alloc(2 * (size_t)C, s);
+  SCN_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * 2 * C, s));
+  int grid = (int)std::min<long long>((n + ROWS_PER_STEP - 1) / ROWS_PER_STEP, (long long)sm_count() * 2);
+  if (v4) k_bn_reduce<4, 1><<<grid, dim3(BX, BY), 0, s>>>(in, out, d_out, save_mean, n, C, leakiness, acc.p);
+  else k_bn_reduce<1, 1><<<grid, dim3(BX, BY), 0, s>>>(in, out, d_out, save_mean, n, C, leakiness, acc.p);
+  SCN_LAUNCH_CHECK();
+  k_bn_finalize_bwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, save_invstd, d_gamma, d_beta, coef.p);
+  SCN_LAUNCH_CHECK();
+  size_t smem = sizeof(float) * 4 * C;
+  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, out, d_out, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness);
+  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, out, d_out, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness);
+  SCN_LAUNCH_CHECK();
+  acc.release(s);
+  coef.release(s);
+}
+
+}  // namespace scn

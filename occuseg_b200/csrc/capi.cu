@@ -1,0 +1,345 @@
+// extern "C" boundary of libscn_b200.so -- see include/scn_b200.h for the contract and the reference
+// interface each entry replaces.
+#include "../../include/scn_b200.h"
+#include "common.cuh"
+#include <mutex>
+
+namespace scn {
+
+static thread_local std::string t_last_error;
+void set_last_error(const std::string &s) { t_last_error = s; }
+std::atomic<long long> g_launches{0};
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static Level *need_level(Meta *m, const int64_t size[3], const char *what) {
+  Level *L = find_level(m, size);
+  if (!L) throw Error(std::string(what) + ": no such scale in this handle (size " + std::to_string(size[0]) + ")");
+  return L;
+}
+
+// `w` is the caller's weight array; native_kn says whether, for THIS product, it already reads as
+// [V][K=c_in][N=c_out] (true) or as [V][N][K] (false).  The fp32 kernels want KN, the tensor-core kernels
+// want NK (K-major B operand); whichever is missing is produced by one small per-tap transpose.
+static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, cudaStream_t s) {
+  const bool tcore = precision == SCN_TF32 && conv_tc_supported(a);
+  const bool want_kn = !tcore;
+  DevBuf<float> tmp;
+  const float *use = w;
+  if (want_kn != native_kn) {
+    tmp.alloc((size_t)a.V * a.c_in * a.c_out, s);
+    // source rows/cols: native_kn -> [c_in][c_out], else [c_out][c_in]
+    if (native_kn) transpose_weight(w, tmp.p, a.V, a.c_in, a.c_out, s);
+    else transpose_weight(w, tmp.p, a.V, a.c_out, a.c_in, s);
+    use = tmp.p;
+  }
+  if (tcore) {
+    a.weight_nk = use;
+    conv_tc(a, s);
+  } else {
+    a.weight = use;
+    conv_simt(a, s);
+  }
+  tmp.release(s);
+}
+
+// One-rule-per-fine-row products (Deconvolution forward, strided-Convolution dgrad):
+//   out[i] = in[parent[i]] * Wk(off[i]).   fp32: input-stationary scatter over the child table;
+//   tensor cores: gather over the `up` table (exactly one live tap per row, absent taps are skipped per tile).
+static void run_up(Level *F, Level *C, const float *in, const float *w, bool native_kn, float *out, int c_in, int c_out,
+                   int precision, cudaStream_t s) {
+  ConvArgs g;
+  g.in = in; g.out = out; g.tbl = F->up.p; g.tbl_stride = F->n_pad; g.n_rows = F->n; g.V = 8;
+  g.c_in = c_in; g.c_out = c_out;
+  if (precision == SCN_TF32 && conv_tc_supported(g)) {
+    run_conv(g, w, native_kn, precision, s);
+    return;
+  }
+  ConvArgs a;
+  a.in = in; a.out = out; a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8;
+  a.c_in = c_in; a.c_out = c_out; a.scatter = true;
+  run_conv(a, w, native_kn, SCN_FP32, s);
+}
+
+static void run_wgrad(const WgradArgs &a, int precision, cudaStream_t s) {
+  if (precision == SCN_TF32 && wgrad_tc_supported(a)) wgrad_tc(a, s);
+  else wgrad_simt(a, s);
+}
+
+}  // namespace scn
+
+using namespace scn;
+
+#define SCN_TRY try {
+#define SCN_CATCH                                                                     \
+  }                                                                                   \
+  catch (const std::exception &e) {                                                   \
+    set_last_error(e.what());                                                         \
+    return 1;                                                                         \
+  }                                                                                   \
+  catch (...) {                                                                       \
+    set_last_error("unknown error");                                                  \
+    return 1;                                                                         \
+  }                                                                                   \
+  return 0;
+
+struct scn_meta {
+  Meta m;
+};
+
+static void check_channels(int c_in, int c_out) {
+  SCN_CHECK(c_in > 0 && c_out > 0 && c_in <= 4096 && c_out <= 4096, "channel counts out of range");
+}
+
+extern "C" {
+
+int scn_version(void) { return 100; }
+const char *scn_last_error(void) { return t_last_error.c_str(); }
+int64_t scn_launch_count(void) { return (int64_t)g_launches.load(); }
+
+scn_meta *scn_meta_create(int device) {
+  try {
+    SCN_CUDA(cudaSetDevice(device));
+    scn_meta *h = new scn_meta();
+    h->m.device = device;
+    return h;
+  } catch (const std::exception &e) {
+    set_last_error(e.what());
+    return nullptr;
+  }
+}
+
+void scn_meta_destroy(scn_meta *h) {
+  if (!h) return;
+  cudaSetDevice(h->m.device);
+  delete h;
+}
+
+int scn_input_layer_build(scn_meta *h, const int64_t size[3], const int64_t *coords, int on_device, int64_t P,
+                          int batch, int mode, void *stream, int64_t *n_active) {
+  SCN_TRY
+  SCN_CHECK(h && coords && n_active, "null argument");
+  build_input_level(&h->m, size, coords, on_device != 0, P, batch, mode, (cudaStream_t)stream);
+  *n_active = h->m.levels[0]->n;
+  SCN_CATCH
+}
+
+int scn_input_layer_fwd(scn_meta *h, const float *feats, int C, float *out, void *stream) {
+  SCN_TRY
+  input_layer_fwd(&h->m, feats, C, out, (cudaStream_t)stream);
+  SCN_CATCH
+}
+int scn_input_layer_bwd(scn_meta *h, const float *d_out, int C, float *d_feats, void *stream) {
+  SCN_TRY
+  input_layer_bwd(&h->m, d_out, C, d_feats, (cudaStream_t)stream);
+  SCN_CATCH
+}
+int scn_output_layer_fwd(scn_meta *h, const float *in, int C, float *out, void *stream) {
+  SCN_TRY
+  output_layer_fwd(&h->m, in, C, out, (cudaStream_t)stream);
+  SCN_CATCH
+}
+int scn_output_layer_bwd(scn_meta *h, const float *d_out, int C, float *d_in, void *stream) {
+  SCN_TRY
+  output_layer_bwd(&h->m, d_out, C, d_in, (cudaStream_t)stream);
+  SCN_CATCH
+}
+int64_t scn_n_points(scn_meta *h) { return h ? h->m.n_points : -1; }
+
+int64_t scn_nactive(scn_meta *h, const int64_t size[3]) {
+  if (!h) return -1;
+  Level *L = find_level(&h->m, size);
+  return L ? L->n : -1;
+}
+
+int scn_spatial_locations(scn_meta *h, const int64_t size[3], int64_t *out) {
+  SCN_TRY
+  Level *L = need_level(&h->m, size, "getSpatialLocations");
+  std::vector<uint64_t> keys(L->n);
+  SCN_CUDA(cudaMemcpy(keys.data(), L->keys.p, sizeof(uint64_t) * L->n, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < L->n; ++i) {
+    uint64_t k = keys[i];
+    out[4 * i + 0] = (int64_t)(k & 0xFFFF);
+    out[4 * i + 1] = (int64_t)((k >> 16) & 0xFFFF);
+    out[4 * i + 2] = (int64_t)((k >> 32) & 0xFFFF);
+    out[4 * i + 3] = (int64_t)(k >> 48);
+  }
+  SCN_CATCH
+}
+
+int scn_subm_rulebook(scn_meta *h, const int64_t size[3], void *stream, int64_t *n_rules) {
+  SCN_TRY
+  Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
+  ensure_neighbour_table(&h->m, L, (cudaStream_t)stream);
+  if (n_rules) *n_rules = L->n_rules;
+  SCN_CATCH
+}
+
+int scn_subm_neighbour_table(scn_meta *h, const int64_t size[3], int32_t *out) {
+  SCN_TRY
+  Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
+  SCN_CHECK(L->nbr.p, "neighbour table not built yet (call scn_subm_rulebook)");
+  SCN_CUDA(cudaMemcpy2D(out, sizeof(int) * L->n, L->nbr.p, sizeof(int) * L->n_pad, sizeof(int) * L->n, 27,
+                        cudaMemcpyDeviceToHost));
+  SCN_CATCH
+}
+
+int scn_strided_rulebook(scn_meta *h, const int64_t fine[3], const int64_t coarse[3], void *stream, int64_t *n_coarse) {
+  SCN_TRY
+  Level *F = need_level(&h->m, fine, "Convolution");
+  Level *C = ensure_coarse_level(&h->m, F, coarse, (cudaStream_t)stream);
+  if (n_coarse) *n_coarse = C->n;
+  SCN_CATCH
+}
+
+int scn_strided_table(scn_meta *h, const int64_t fine[3], int32_t *parent, uint8_t *off) {
+  SCN_TRY
+  Level *F = need_level(&h->m, fine, "Convolution");
+  SCN_CHECK(F->coarse, "strided rulebook not built yet (call scn_strided_rulebook)");
+  SCN_CUDA(cudaMemcpy(parent, F->parent.p, sizeof(int) * F->n, cudaMemcpyDeviceToHost));
+  SCN_CUDA(cudaMemcpy(off, F->off8.p, F->n, cudaMemcpyDeviceToHost));
+  SCN_CATCH
+}
+
+// ---- submanifold ------------------------------------------------------------------------------------
+int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const float *weight, const float *bias, float *out,
+                 int c_in, int c_out, int precision, void *stream, double *macs) {
+  SCN_TRY
+  cudaStream_t s = (cudaStream_t)stream;
+  check_channels(c_in, c_out);
+  Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
+  ensure_neighbour_table(&h->m, L, s);
+  ConvArgs a;
+  a.in = in; a.bias = bias; a.out = out;
+  a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_in; a.c_out = c_out;
+  run_conv(a, weight, true, precision, s);
+  if (macs) *macs = (double)L->n_rules * c_in * c_out;   // flops += nRules*ip*op, CPU/Convolution.cpp:134
+  SCN_CATCH
+}
+
+int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const float *d_out, const float *weight,
+                 float *d_in, float *d_weight, float *d_bias, int c_in, int c_out, int precision, void *stream) {
+  SCN_TRY
+  cudaStream_t s = (cudaStream_t)stream;
+  check_channels(c_in, c_out);
+  Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
+  ensure_neighbour_table(&h->m, L, s);
+  // dgrad: d_in[i] = sum_k d_out[nbr[26-k][i]] * W[k]^T  (rule (i,o) at offset k  <=>  o sits at offset 26-k of i)
+  // for this product K = c_out and N = c_in, so the caller's [27][c_in][c_out] array reads as [V][N][K]
+  ConvArgs a;
+  a.in = d_out; a.out = d_in;
+  a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_out; a.c_out = c_in; a.mirror = true;
+  run_conv(a, weight, false, precision, s);
+  WgradArgs w;
+  w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = L->nbr.p; w.tbl_stride = L->n_pad; w.n_rows = L->n; w.V = 27;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true;
+  run_wgrad(w, precision, s);
+  if (d_bias) bias_grad(d_out, d_bias, L->n, c_out, s);
+  SCN_CATCH
+}
+
+// ---- strided convolution: fine -> coarse ------------------------------------------------------------
+int scn_conv_fwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3], const float *in, const float *weight,
+                 const float *bias, float *out, int c_in, int c_out, int precision, void *stream, double *macs) {
+  SCN_TRY
+  cudaStream_t s = (cudaStream_t)stream;
+  check_channels(c_in, c_out);
+  Level *F = need_level(&h->m, in_size, "Convolution");
+  Level *C = ensure_coarse_level(&h->m, F, out_size, s);
+  // out[p] = sum_k in[child[k][p]] * W[k]
+  ConvArgs a;
+  a.in = in; a.bias = bias; a.out = out;
+  a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_in; a.c_out = c_out;
+  run_conv(a, weight, true, precision, s);
+  if (macs) *macs = (double)F->n * c_in * c_out;   // every fine row has exactly one rule
+  SCN_CATCH
+}
+
+int scn_conv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3], const float *in, const float *d_out,
+                 const float *weight, float *d_in, float *d_weight, float *d_bias, int c_in, int c_out, int precision,
+                 void *stream) {
+  SCN_TRY
+  cudaStream_t s = (cudaStream_t)stream;
+  check_channels(c_in, c_out);
+  Level *F = need_level(&h->m, in_size, "Convolution");
+  Level *C = ensure_coarse_level(&h->m, F, out_size, s);
+  // dgrad: d_in[child[k][p]] = d_out[p] * W[k]^T  (scatter; each fine row has one parent)
+  run_up(F, C, d_out, weight, false, d_in, c_out, c_in, precision, s);
+  WgradArgs w;
+  w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true;
+  run_wgrad(w, precision, s);
+  if (d_bias) bias_grad(d_out, d_bias, C->n, c_out, s);
+  SCN_CATCH
+}
+
+// ---- deconvolution: coarse -> fine, same rulebook with the roles swapped ------------------------------
+int scn_deconv_fwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3], const float *in,
+                   const float *weight, const float *bias, float *out, int c_in, int c_out, int precision, void *stream,
+                   double *macs) {
+  SCN_TRY
+  cudaStream_t s = (cudaStream_t)stream;
+  check_channels(c_in, c_out);
+  Level *F = need_level(&h->m, out_size, "Deconvolution");
+  SCN_CHECK(F->coarse && find_level(&h->m, in_size) == F->coarse,
+            "Deconvolution: the matching Convolution has not created this pair of scales");
+  Level *C = F->coarse;
+  SCN_CHECK(bias == nullptr, "Deconvolution: bias is not supported on this path (the UNet uses bias=False)");
+  // out[child[k][p]] = in[p] * W[k]
+  run_up(F, C, in, weight, true, out, c_in, c_out, precision, s);
+  if (macs) *macs = (double)F->n * c_in * c_out;
+  SCN_CATCH
+}
+
+int scn_deconv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3], const float *in,
+                   const float *d_out, const float *weight, float *d_in, float *d_weight, float *d_bias, int c_in,
+                   int c_out, int precision, void *stream) {
+  SCN_TRY
+  cudaStream_t s = (cudaStream_t)stream;
+  check_channels(c_in, c_out);
+  Level *F = need_level(&h->m, out_size, "Deconvolution");
+  SCN_CHECK(F->coarse && find_level(&h->m, in_size) == F->coarse,
+            "Deconvolution: the matching Convolution has not created this pair of scales");
+  Level *C = F->coarse;
+  // dgrad: d_in[p] = sum_k d_out[child[k][p]] * W[k]^T
+  ConvArgs a;
+  a.in = d_out; a.out = d_in;
+  a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_out; a.c_out = c_in;
+  run_conv(a, weight, false, precision, s);
+  // dW[k] = sum_p in[p]^T d_out[child[k][p]]
+  WgradArgs w;
+  w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = false;
+  run_wgrad(w, precision, s);
+  if (d_bias) bias_grad(d_out, d_bias, F->n, c_out, s);
+  SCN_CATCH
+}
+
+// ---- batch norm ---------------------------------------------------------------------------------------
+int scn_bn_fwd(const float *in, float *out, float *save_mean, float *save_invstd, float *running_mean,
+               float *running_var, const float *gamma, const float *beta, int64_t n, int C, float eps, float momentum,
+               int train, float leakiness, void *stream) {
+  SCN_TRY
+  bn_fwd(in, out, save_mean, save_invstd, running_mean, running_var, gamma, beta, n, C, eps, momentum, train != 0,
+         leakiness, (cudaStream_t)stream);
+  SCN_CATCH
+}
+
+int scn_bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
+               const float *gamma, float *d_in, float *d_gamma, float *d_beta, int64_t n, int C, float leakiness,
+               void *stream) {
+  SCN_TRY
+  bn_bwd(in, out, d_out, save_mean, save_invstd, gamma, d_in, d_gamma, d_beta, n, C, leakiness, (cudaStream_t)stream);
+  SCN_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+// Shared declarations for libscn_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <atomic>
+#include <stdexcept>
+
+namespace scn {
+
+// ---- error plumbing: exceptions inside, int status + scn_last_error() at the C boundary ----------
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+void set_last_error(const std::string &s);
+
+#define SCN_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      throw ::scn::Error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" +         \
+                         __FILE__ + ":" + std::to_string(__LINE__) + ")");                          \
+  } while (0)
+
+#define SCN_CHECK(cond, msg)                                                                        \
+  do {                                                                                              \
+    if (!(cond)) throw ::scn::Error(std::string(msg) + " [" #cond "]");                             \
+  } while (0)
+
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+#define SCN_LAUNCH_CHECK()                                                                          \
+  do {                                                                                              \
+    ::scn::count_launch();                                                                          \
+    SCN_CUDA(cudaGetLastError());                                                                   \
+  } while (0)
+
+int sm_count();
+
+// ---- stream-ordered device buffers -------------------------------------------------------------------
+template <typename T> struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  void alloc(size_t count, cudaStream_t s) {
+    release(s);
+    n = count;
+    if (count) SCN_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), s));
+  }
+  void release(cudaStream_t s) {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { if (p) cudaFreeAsync(p, 0); }
+};
+
+// ---- voxel key: 16 bits per field, (batch, z, y, x) most->least significant -------------------------
+// Sorting by this key reproduces the reference's row order: per sample, rank of the 31-bit key
+// z<<21|y<<10|x (CUDA/CUDPPWrapper.cu:80-81) with samples concatenated (IOLayersRules.h:164-169),
+// but without the reference's 10/11/10-bit aliasing.
+__host__ __device__ inline uint64_t make_key(uint32_t b, uint32_t z, uint32_t y, uint32_t x) {
+  return ((uint64_t)b << 48) | ((uint64_t)z << 32) | ((uint64_t)y << 16) | (uint64_t)x;
+}
+constexpr int COORD_LIMIT = 65535;          // exclusive upper bound on coordinates and batch index
+constexpr uint64_t EMPTY_KEY = ~0ull;       // never a valid key (batch 65535 is rejected)
+
+// ---- one scale of one batch -------------------------------------------------------------------------
+struct Level {
+  int64_t size[3] = {0, 0, 0};
+  int n = 0;                 // active rows
+  int n_pad = 0;             // row stride of the [V][n_pad] tables (multiple of 128)
+  DevBuf<uint64_t> keys;     // [n] sorted unique voxel keys; row id == index
+  // open-addressing hash: key -> row
+  DevBuf<uint64_t> hkeys;
+  DevBuf<int> hvals;
+  uint32_t hmask = 0;
+  // submanifold 3x3x3 neighbour table (output-stationary form of the reference's 27 rule lists)
+  DevBuf<int> nbr;           // [27][n_pad], -1 = absent
+  long long n_rules = -1;    // sum_k n_k, centre offset included
+  // size-2/stride-2 link to the next coarser scale
+  Level *coarse = nullptr;
+  DevBuf<int> parent;        // [n]   coarse row of every fine row
+  DevBuf<uint8_t> off8;      // [n]   (x&1)*4+(y&1)*2+(z&1)
+  DevBuf<int> child;         // [8][coarse->n_pad] fine row or -1
+  DevBuf<int> up;            // [8][n_pad]  up[k][i] = parent[i] if off8[i]==k else -1 (one tap per fine row)
+};
+
+struct Meta {
+  int device = 0;
+  int batch = 0;
+  int mode = 0;
+  long long n_points = 0;
+  std::vector<Level *> levels;
+  // InputLayer rules, CSR form of the reference's [N][1+maxRepeat] table (CUDPPWrapper.cu:53-64)
+  DevBuf<int> row_of_point;  // [P]
+  DevBuf<int> rule_ptr;      // [N+1]
+  DevBuf<int> rule_pts;      // [P] point ids grouped by row, original order inside a row
+  ~Meta();
+};
+
+Level *find_level(Meta *m, const int64_t size[3]);
+
+// meta.cu
+void build_input_level(Meta *m, const int64_t size[3], const int64_t *coords, bool on_device, long long P, int batch,
+                       int mode, cudaStream_t s);
+void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s);
+Level *ensure_coarse_level(Meta *m, Level *fine, const int64_t coarse_size[3], cudaStream_t s);
+
+// io.cu
+void input_layer_fwd(Meta *m, const float *feats, int C, float *out, cudaStream_t s);
+void input_layer_bwd(Meta *m, const float *d_out, int C, float *d_feats, cudaStream_t s);
+void output_layer_fwd(Meta *m, const float *in, int C, float *out, cudaStream_t s);
+void output_layer_bwd(Meta *m, const float *d_out, int C, float *d_in, cudaStream_t s);
+
+// conv_simt.cu / conv_tc.cu ---------------------------------------------------------------------------
+// Generic "table convolution".  tbl is [V][stride] (row index or -1).
+//  GATHER : out[o,:]        = sum_k in[tbl[wk(k)][o],:] * Wk      for o in [0,n_rows)
+//  SCATTER: out[tbl[k][p],:] =        in[p,:]            * Wk      for p in [0,n_rows), tbl>=0
+// Wk is weight[k] ([Cin][Cout]) or, when transpose_w, weight[k]^T read from the original [V][Cout'][Cin'] array.
+struct ConvArgs {
+  const float *in = nullptr;
+  const float *weight = nullptr;   // [V][c_in][c_out] as seen by THIS product (fp32 FMA kernels)
+  const float *weight_nk = nullptr;// [V][c_out][c_in] as seen by THIS product (tensor-core kernels: K-major B operand)
+  const float *bias = nullptr;     // GATHER only
+  float *out = nullptr;
+  const int *tbl = nullptr;
+  int tbl_stride = 0;
+  int n_rows = 0;                  // rows iterated (outputs for GATHER, inputs for SCATTER)
+  int V = 27;
+  int c_in = 0, c_out = 0;
+  bool mirror = false;             // GATHER: use table row V-1-k for weight tap k (dgrad of a submanifold conv)
+  bool scatter = false;
+};
+void conv_simt(const ConvArgs &a, cudaStream_t s);
+bool conv_tc_supported(const ConvArgs &a);
+void conv_tc(const ConvArgs &a, cudaStream_t s);
+
+// weight preparation: dst[k][co][ci] = src[k][ci][co]   (per-tap transpose, used by every dgrad)
+void transpose_weight(const float *src, float *dst, int V, int c_in, int c_out, cudaStream_t s);
+
+// dW[k] = sum_r A[ia(k,r),:]^T * B[ib(k,r),:]    A: [*,c_a], B: [*,c_b], dW: [V][c_a][c_b] (zeroed here)
+//   table_on_a:  ia = tbl[k][r], ib = r      (submanifold / strided conv: A = input, B = d_out)
+//   !table_on_a: ia = r, ib = tbl[k][r]      (deconvolution: A = coarse input, B = fine d_out)
+struct WgradArgs {
+  const float *a = nullptr;
+  const float *b = nullptr;
+  float *dw = nullptr;
+  const int *tbl = nullptr;
+  int tbl_stride = 0;
+  int n_rows = 0;
+  int V = 27;
+  int c_a = 0, c_b = 0;
+  bool table_on_a = true;
+};
+void wgrad_simt(const WgradArgs &a, cudaStream_t s);
+bool wgrad_tc_supported(const WgradArgs &a);
+void wgrad_tc(const WgradArgs &a, cudaStream_t s);
+
+void bias_grad(const float *d_out, float *d_bias, long long n_rows, int C, cudaStream_t s);
+
+// bn.cu
+void bn_fwd(const float *in, float *out, float *save_mean, float *save_invstd, float *running_mean, float *running_var,
+            const float *gamma, const float *beta, long long n, int C, float eps, float momentum, bool train,
+            float leakiness, cudaStream_t s);
+void bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
+            const float *gamma, float *d_in, float *d_gamma, float *d_beta, long long n, int C, float leakiness,
+            cudaStream_t s);
+
+}  // namespace scn

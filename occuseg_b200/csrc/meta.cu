@@ -1,0 +1,370 @@
+// Rulebook construction on the GPU: voxelisation, open-addressing coordinate hash, 27-offset
+// neighbour query, size-2/stride-2 links.  Replaces the reference's Metadata layer + cudpp:
+//   Metadata/IOLayersRules.h:136-202, CUDA/CUDPPWrapper.{cu,hpp}, extra/cudpp/src/cudpp_hash/*,
+//   CUDA/SubmanifoldRules_cuda.{cu,cpp}:20-203, Metadata/ConvolutionRules.h:344-378.
+// Everything stays device-resident; the reference copies every rule list to the host and back.
+#include "common.cuh"
+#include <cub/cub.cuh>
+
+namespace scn {
+
+Meta::~Meta() {
+  for (Level *L : levels) delete L;
+}
+
+Level *find_level(Meta *m, const int64_t size[3]) {
+  for (Level *L : m->levels)
+    if (L->size[0] == size[0] && L->size[1] == size[1] && L->size[2] == size[2]) return L;
+  return nullptr;
+}
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  return (int)(g < 1 ? 1 : g);
+}
+
+// -----------------------------------------------------------------------------------------------------
+// keys
+// -----------------------------------------------------------------------------------------------------
+__global__ void k_point_keys(const int64_t *__restrict__ coords, long long P, int batch, uint64_t *__restrict__ keys,
+                             int *__restrict__ idx, int *__restrict__ err) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  // one 32-byte row per point: two 16-byte loads
+  const longlong2 *row = reinterpret_cast<const longlong2 *>(coords + 4 * i);
+  longlong2 xy = row[0], zb = row[1];
+  bool ok = xy.x >= 0 && xy.x < COORD_LIMIT && xy.y >= 0 && xy.y < COORD_LIMIT && zb.x >= 0 && zb.x < COORD_LIMIT &&
+            zb.y >= 0 && zb.y < batch;
+  if (!ok) atomicExch(err, 1);
+  keys[i] = ok ? make_key((uint32_t)zb.y, (uint32_t)zb.x, (uint32_t)xy.y, (uint32_t)xy.x) : EMPTY_KEY - 1;
+  idx[i] = (int)i;
+}
+
+__global__ void k_coarse_keys(const uint64_t *__restrict__ fine, int n, uint64_t *__restrict__ ckeys,
+                              int *__restrict__ idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k = fine[i];
+  // halve x, y, z fields in place (out = in/2, ConvolutionRules.h:364); batch field untouched
+  uint64_t lo = (k >> 1) & 0x00007FFF7FFF7FFFull;
+  ckeys[i] = (k & 0xFFFF000000000000ull) | lo;
+  idx[i] = i;
+}
+
+// rows = runs of equal keys in the sorted list; fan the row id back out to the members of each run
+__global__ void k_rows_of_points(const int *__restrict__ run_ptr, const int *__restrict__ sorted_idx, int n_runs,
+                                 int *__restrict__ row_of_point) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  for (int j = run_ptr[r]; j < run_ptr[r + 1]; ++j) row_of_point[sorted_idx[j]] = r;
+}
+
+// stride-2 link: parent / offset of every fine row, child table of every coarse row
+__global__ void k_link_levels(const int *__restrict__ run_ptr, const int *__restrict__ sorted_idx,
+                              const uint64_t *__restrict__ fine_keys, int n_runs, int child_stride,
+                              int *__restrict__ parent, uint8_t *__restrict__ off8, int *__restrict__ child,
+                              int up_stride, int *__restrict__ up) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  for (int j = run_ptr[r]; j < run_ptr[r + 1]; ++j) {
+    int i = sorted_idx[j];
+    uint64_t k = fine_keys[i];
+    // offset index ((x&1)*2 + (y&1))*2 + (z&1): SubmanifoldRules_cuda.cu:549-554
+    int off = (int)(((k & 1ull) << 2) | (((k >> 16) & 1ull) << 1) | ((k >> 32) & 1ull));
+    parent[i] = r;
+    off8[i] = (uint8_t)off;
+    child[off * child_stride + r] = i;
+    up[off * up_stride + i] = r;
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------
+// open-addressing hash (linear probing, load <= 0.5).  Replaces cudpp's cuckoo tables
+// (extra/cudpp/src/cudpp_hash/hash_table.cuh:94-295): no stash, no rebuild loop, one CAS per insert.
+// -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash_key(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+__global__ void k_hash_insert(const uint64_t *__restrict__ keys, int n, uint64_t *__restrict__ hkeys,
+                              int *__restrict__ hvals, uint32_t mask) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t k = keys[i];
+  uint32_t slot = hash_key(k) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS((unsigned long long *)&hkeys[slot], (unsigned long long)EMPTY_KEY,
+                                        (unsigned long long)k);
+    if (prev == EMPTY_KEY) {  // keys are unique, so a slot is never claimed twice for the same key
+      hvals[slot] = i;
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ int hash_find(uint64_t k, const uint64_t *__restrict__ hkeys, const int *__restrict__ hvals,
+                                         uint32_t mask) {
+  uint32_t slot = hash_key(k) & mask;
+  while (true) {
+    uint64_t cur = __ldg(&hkeys[slot]);
+    if (cur == k) return __ldg(&hvals[slot]);
+    if (cur == EMPTY_KEY) return -1;
+    slot = (slot + 1) & mask;
+  }
+}
+
+// One thread per output voxel, 27 probes.  Offset order k=(dx+1)*9+(dy+1)*3+(dz+1) follows the GPU builder
+// (CUDA/SubmanifoldRules_cuda.cu:63-73), NOT the dormant CPU-grid enumeration.  A neighbour exists only
+// inside the same sample (the reference keeps one hash per sample, Metadata.h:110-122).  Writes are
+// coalesced: consecutive threads -> consecutive rows of nbr[k][*].
+__global__ void k_neighbours(const uint64_t *__restrict__ keys, int n, int stride, const uint64_t *__restrict__ hkeys,
+                             const int *__restrict__ hvals, uint32_t mask, int *__restrict__ nbr,
+                             unsigned long long *__restrict__ n_rules) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int hits = 0;
+  if (i < n) {
+    uint64_t k = keys[i];
+    int x = (int)(k & 0xFFFF), y = (int)((k >> 16) & 0xFFFF), z = (int)((k >> 32) & 0xFFFF);
+    uint32_t b = (uint32_t)(k >> 48);
+    int t = 0;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx)
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dz = -1; dz <= 1; ++dz, ++t) {
+          int r;
+          if (t == 13) {
+            r = i;
+          } else {
+            int qx = x + dx, qy = y + dy, qz = z + dz;
+            bool inside = qx >= 0 && qy >= 0 && qz >= 0 && qx < COORD_LIMIT && qy < COORD_LIMIT && qz < COORD_LIMIT;
+            r = inside ? hash_find(make_key(b, qz, qy, qx), hkeys, hvals, mask) : -1;
+          }
+          nbr[t * stride + i] = r;
+          hits += (r >= 0);
+        }
+  }
+  // block-level count -> one atomic per block
+  typedef cub::BlockReduce<int, 256> BR;
+  __shared__ typename BR::TempStorage tmp;
+  int total = BR(tmp).Sum(hits);
+  if (threadIdx.x == 0 && total) atomicAdd(n_rules, (unsigned long long)total);
+}
+
+__global__ void k_fill_int(int *p, long long n, int v) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// sort + run-length encode: (keys, payload) -> unique keys, run pointers, payload grouped by run.
+// Radix sort is stable, so members of a run keep their original order -- this is what fixes the
+// summation order of duplicate points in InputLayer mode 3/4.
+// -----------------------------------------------------------------------------------------------------
+__global__ void k_fill_int(int *p, long long n, int v);
+
+struct Runs {
+  DevBuf<uint64_t> unique;   // [n_runs] (allocated n)
+  DevBuf<int> ptr;           // [n_runs+1] (allocated n+1)
+  DevBuf<int> sorted_idx;    // [n]
+  int n_runs = 0;
+};
+
+static void sort_and_group(DevBuf<uint64_t> &keys, DevBuf<int> &idx, long long n, int end_bit, Runs &out,
+                           cudaStream_t s) {
+  DevBuf<uint64_t> keys_sorted;
+  DevBuf<int> counts, d_nruns;
+  keys_sorted.alloc(n, s);
+  out.sorted_idx.alloc(n, s);
+  out.unique.alloc(n, s);
+  out.ptr.alloc(n + 1, s);
+  counts.alloc(n, s);
+  d_nruns.alloc(1, s);
+
+  size_t t1 = 0, t2 = 0, t3 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t1, keys.p, keys_sorted.p, idx.p, out.sorted_idx.p, (int)n, 0, end_bit, s);
+  cub::DeviceRunLengthEncode::Encode(nullptr, t2, keys_sorted.p, out.unique.p, counts.p, d_nruns.p, (int)n, s);
+  cub::DeviceScan::ExclusiveSum(nullptr, t3, counts.p, out.ptr.p, (int)n, s);
+  DevBuf<uint8_t> tmp;
+  tmp.alloc(std::max(t1, std::max(t2, t3)), s);
+  size_t tb = tmp.n;
+  SCN_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys_sorted.p, idx.p, out.sorted_idx.p, (int)n, 0,
+                                           end_bit, s));
+  count_launch(4);
+  tb = tmp.n;
+  SCN_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, tb, keys_sorted.p, out.unique.p, counts.p, d_nruns.p, (int)n, s));
+  count_launch(2);
+  int h_runs = 0;
+  SCN_CUDA(cudaMemcpyAsync(&h_runs, d_nruns.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));   // the caller needs the row count to size its tensors
+  out.n_runs = h_runs;
+  tb = tmp.n;
+  // exclusive sum over n_runs+1 entries: counts[n_runs] is garbage but only feeds ptr[n_runs+1..]; write the
+  // terminal pointer explicitly instead
+  SCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, counts.p, out.ptr.p, h_runs, s));
+  count_launch(2);
+  k_fill_int<<<1, 32, 0, s>>>(out.ptr.p + h_runs, 1, (int)n);
+  SCN_LAUNCH_CHECK();
+  keys_sorted.release(s);
+  counts.release(s);
+  d_nruns.release(s);
+  tmp.release(s);
+}
+
+static int bits_for(unsigned v) {
+  int b = 0;
+  while ((1u << b) <= v && b < 16) ++b;
+  return b;
+}
+
+void build_input_level(Meta *m, const int64_t size[3], const int64_t *coords, bool on_device, long long P, int batch,
+                       int mode, cudaStream_t s) {
+  SCN_CHECK(mode == 3 || mode == 4, "InputLayer: only modes 3 (sum) and 4 (mean) are supported, like the reference GPU path");
+  SCN_CHECK(m->levels.empty(), "InputLayer: this handle already holds a batch");
+  SCN_CHECK(P > 0 && P < (1ll << 31) - 1, "InputLayer: point count must be in (0, 2^31)");
+  SCN_CHECK(batch > 0 && batch < COORD_LIMIT, "InputLayer: bad batch size");
+  m->batch = batch;
+  m->mode = mode;
+  m->n_points = P;
+
+  DevBuf<int64_t> dcoords;
+  const int64_t *dc = coords;
+  if (!on_device) {
+    dcoords.alloc((size_t)P * 4, s);
+    SCN_CUDA(cudaMemcpyAsync(dcoords.p, coords, sizeof(int64_t) * 4 * P, cudaMemcpyHostToDevice, s));
+    dc = dcoords.p;
+  }
+  DevBuf<uint64_t> keys;
+  DevBuf<int> idx, err;
+  keys.alloc(P, s);
+  idx.alloc(P, s);
+  err.alloc(1, s);
+  SCN_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+  k_point_keys<<<grid_for(P, 256), 256, 0, s>>>(dc, P, batch, keys.p, idx.p, err.p);
+  SCN_LAUNCH_CHECK();
+  int h_err = 0;
+  SCN_CUDA(cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+
+  Runs runs;
+  sort_and_group(keys, idx, P, 48 + bits_for((unsigned)(batch > 1 ? batch - 1 : 1)), runs, s);
+  SCN_CHECK(h_err == 0, "InputLayer: coordinate outside [0,65535) or batch index outside [0,batch_size)");
+
+  Level *L = new Level();
+  for (int d = 0; d < 3; ++d) L->size[d] = size[d];
+  L->n = runs.n_runs;
+  L->n_pad = round_up(L->n, 128);
+  L->keys.alloc(L->n, s);
+  SCN_CUDA(cudaMemcpyAsync(L->keys.p, runs.unique.p, sizeof(uint64_t) * L->n, cudaMemcpyDeviceToDevice, s));
+  m->levels.push_back(L);
+
+  m->row_of_point.alloc(P, s);
+  k_rows_of_points<<<grid_for(L->n, 256), 256, 0, s>>>(runs.ptr.p, runs.sorted_idx.p, L->n, m->row_of_point.p);
+  SCN_LAUNCH_CHECK();
+  m->rule_ptr.alloc(L->n + 1, s);
+  SCN_CUDA(cudaMemcpyAsync(m->rule_ptr.p, runs.ptr.p, sizeof(int) * (L->n + 1), cudaMemcpyDeviceToDevice, s));
+  // hand the grouped point list over without a copy
+  m->rule_pts.p = runs.sorted_idx.p;
+  m->rule_pts.n = runs.sorted_idx.n;
+  runs.sorted_idx.p = nullptr;
+  runs.sorted_idx.n = 0;
+
+  keys.release(s);
+  idx.release(s);
+  err.release(s);
+  dcoords.release(s);
+  runs.unique.release(s);
+  runs.ptr.release(s);
+}
+
+static void build_hash(Level *L, cudaStream_t s) {
+  if (L->hkeys.p) return;
+  uint32_t cap = 1024;
+  while (cap < 2u * (uint32_t)L->n) cap <<= 1;
+  L->hmask = cap - 1;
+  L->hkeys.alloc(cap, s);
+  L->hvals.alloc(cap, s);
+  SCN_CUDA(cudaMemsetAsync(L->hkeys.p, 0xFF, sizeof(uint64_t) * cap, s));
+  if (L->n) {
+    k_hash_insert<<<grid_for(L->n, 256), 256, 0, s>>>(L->keys.p, L->n, L->hkeys.p, L->hvals.p, L->hmask);
+    SCN_LAUNCH_CHECK();
+  }
+}
+
+void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
+  (void)m;
+  if (L->nbr.p) return;
+  build_hash(L, s);
+  L->nbr.alloc((size_t)27 * L->n_pad, s);
+  DevBuf<unsigned long long> cnt;
+  cnt.alloc(1, s);
+  SCN_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), s));
+  if (L->n_pad != L->n) {
+    // padding rows read as "absent" so tile kernels need no tail checks on the table
+    k_fill_int<<<grid_for((long long)27 * L->n_pad, 256), 256, 0, s>>>(L->nbr.p, (long long)27 * L->n_pad, -1);
+    SCN_LAUNCH_CHECK();
+  }
+  if (L->n) {
+    k_neighbours<<<grid_for(L->n, 256), 256, 0, s>>>(L->keys.p, L->n, L->n_pad, L->hkeys.p, L->hvals.p, L->hmask,
+                                                     L->nbr.p, cnt.p);
+    SCN_LAUNCH_CHECK();
+  }
+  unsigned long long h = 0;
+  SCN_CUDA(cudaMemcpyAsync(&h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));   // once per scale per batch: the MAC count is part of the API
+  L->n_rules = (long long)h;
+  cnt.release(s);
+}
+
+Level *ensure_coarse_level(Meta *m, Level *F, const int64_t coarse_size[3], cudaStream_t s) {
+  if (F->coarse) {
+    SCN_CHECK(F->coarse->size[0] == coarse_size[0], "Convolution: a different output size was already linked to this scale");
+    return F->coarse;
+  }
+  for (int d = 0; d < 3; ++d)
+    SCN_CHECK((coarse_size[d] - 1) * 2 + 2 == F->size[d], "Convolution: only filter size 2 / stride 2 is supported (reference FastDownSampleMode)");
+  SCN_CHECK(find_level(m, coarse_size) == nullptr, "Convolution: output scale already exists in this handle");
+  DevBuf<uint64_t> ckeys;
+  DevBuf<int> idx;
+  ckeys.alloc(F->n, s);
+  idx.alloc(F->n, s);
+  k_coarse_keys<<<grid_for(F->n, 256), 256, 0, s>>>(F->keys.p, F->n, ckeys.p, idx.p);
+  SCN_LAUNCH_CHECK();
+  Runs runs;
+  sort_and_group(ckeys, idx, F->n, 48 + bits_for((unsigned)(m->batch > 1 ? m->batch - 1 : 1)), runs, s);
+
+  Level *C = new Level();
+  for (int d = 0; d < 3; ++d) C->size[d] = coarse_size[d];
+  C->n = runs.n_runs;
+  C->n_pad = round_up(C->n, 128);
+  C->keys.alloc(C->n, s);
+  SCN_CUDA(cudaMemcpyAsync(C->keys.p, runs.unique.p, sizeof(uint64_t) * C->n, cudaMemcpyDeviceToDevice, s));
+  F->parent.alloc(F->n, s);
+  F->off8.alloc(F->n, s);
+  F->child.alloc((size_t)8 * C->n_pad, s);
+  k_fill_int<<<grid_for((long long)8 * C->n_pad, 256), 256, 0, s>>>(F->child.p, (long long)8 * C->n_pad, -1);
+  SCN_LAUNCH_CHECK();
+  F->up.alloc((size_t)8 * F->n_pad, s);
+  k_fill_int<<<grid_for((long long)8 * F->n_pad, 256), 256, 0, s>>>(F->up.p, (long long)8 * F->n_pad, -1);
+  SCN_LAUNCH_CHECK();
+  k_link_levels<<<grid_for(C->n, 256), 256, 0, s>>>(runs.ptr.p, runs.sorted_idx.p, F->keys.p, C->n, C->n_pad,
+                                                    F->parent.p, F->off8.p, F->child.p, F->n_pad, F->up.p);
+  SCN_LAUNCH_CHECK();
+  F->coarse = C;
+  m->levels.push_back(C);
+  ckeys.release(s);
+  idx.release(s);
+  runs.unique.release(s);
+  runs.ptr.release(s);
+  runs.sorted_idx.release(s);
+  return C;
+}
+
+}  // namespace scn

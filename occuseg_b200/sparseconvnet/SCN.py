@@ -1,0 +1,304 @@
+"""Host-side mirror of the reference's pybind11 module `sparseconvnet.SCN` for the hot path
+(reference: sparseconvnet/SCN/pybind.cpp:11-239, sparseconvnet/SCN/sparseconvnet.h).
+
+Same names, same argument order and meaning, same ownership rule (the caller passes EMPTY output
+tensors, the callee resizes and fills them; sparseconvnet/SCN/CUDA/Convolution.cpp:122), but every
+call goes straight to libscn_b200.so through the C ABI in include/scn_b200.h with raw device pointers
+and the current torch stream.  Errors are Python exceptions instead of exit()/abort().
+There is no CPU path: tensors must be CUDA float32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from .. import _lib
+
+_PRECISIONS = {"fp32": _lib.FP32, "tf32": _lib.TF32}
+_precision = _PRECISIONS[os.environ.get("SCN_B200_PRECISION", "tf32").lower()]
+
+
+def set_precision(name):
+    """'fp32' = exact FMA path everywhere; 'tf32' = tcgen05 tiles (fp32 accumulate) where channels allow."""
+    global _precision
+    _precision = _PRECISIONS[name.lower()]
+
+
+def get_precision():
+    return {v: k for k, v in _PRECISIONS.items()}[_precision]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else C.c_void_p(0)
+
+
+def _cuda_f32(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise TypeError(f"{name}: expected a CUDA float32 tensor (there is no CPU path), got {t.device} {t.dtype}")
+    return t.contiguous()
+
+
+def _opt(t):
+    """optionalTensor convention of the reference (utils.py:23-24): an empty tensor means 'absent'."""
+    return t if (t is not None and t.numel()) else None
+
+
+class Metadata_3:
+    """Replaces Metadata<3> (Metadata/Metadata.h:218-364): one handle per batch, owns every scale's voxel
+    keys, hash, neighbour tables and stride-2 links on the device; freed with the last Python reference."""
+
+    def __init__(self):
+        self._h = None
+        self._device = None
+        self.normal_guide_scale = None
+
+    # the handle is created lazily so that it lands on the device of the first tensor it sees
+    def _handle(self, device_index=None):
+        if self._h is None:
+            if device_index is None:
+                device_index = torch.cuda.current_device()
+            h = _lib.lib().scn_meta_create(int(device_index))
+            if not h:
+                raise _lib.ScnError(_lib.lib().scn_last_error().decode())
+            self._h, self._device = C.c_void_p(h), device_index
+        return self._h
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.lib().scn_meta_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def clear(self):
+        self.__del__()
+
+    def setNormalGuideScale(self, v):          # normal-guided kernels are out of scope
+        self.normal_guide_scale = v
+
+    def getNActive(self, spatial_size):
+        return int(_lib.lib().scn_nactive(self._handle(), _lib.size3(spatial_size)))
+
+    def getSpatialLocations(self, spatial_size):
+        """CPU LongTensor [N,4] = (x,y,z,batch) in row order (Metadata.cpp:724-748)."""
+        n = self.getNActive(spatial_size)
+        if n < 0:
+            raise _lib.ScnError("getSpatialLocations: no such scale")
+        out = torch.empty((n, 4), dtype=torch.int64)
+        _lib.check(_lib.lib().scn_spatial_locations(self._handle(), _lib.size3(spatial_size), _ptr(out)))
+        return out
+
+    # --- rulebook access for parity tests ------------------------------------------------------------
+    def submanifoldNeighbourTable(self, spatial_size):
+        """int32 [27,N] CPU tensor: input row feeding output row o at offset k, or -1."""
+        sz = _lib.size3(spatial_size)
+        nr = C.c_int64(0)
+        _lib.check(_lib.lib().scn_subm_rulebook(self._handle(), sz, _stream(), C.byref(nr)))
+        n = self.getNActive(spatial_size)
+        out = torch.empty((27, n), dtype=torch.int32)
+        _lib.check(_lib.lib().scn_subm_neighbour_table(self._handle(), sz, _ptr(out)))
+        return out, int(nr.value)
+
+    def stridedTable(self, fine_size, coarse_size):
+        """(parent int32 [Nfine], offset uint8 [Nfine], nCoarse)."""
+        nc = C.c_int64(0)
+        _lib.check(_lib.lib().scn_strided_rulebook(self._handle(), _lib.size3(fine_size), _lib.size3(coarse_size),
+                                                   _stream(), C.byref(nc)))
+        n = self.getNActive(fine_size)
+        parent = torch.empty(n, dtype=torch.int32)
+        off = torch.empty(n, dtype=torch.uint8)
+        _lib.check(_lib.lib().scn_strided_table(self._handle(), _lib.size3(fine_size), _ptr(parent), _ptr(off)))
+        return parent, off, int(nc.value)
+
+
+def n_rulebook_bits():
+    return 32
+
+
+# ---- IO layers (sparseconvnet.h:151-179) -------------------------------------------------------------
+def InputLayer_updateOutput(m, spatial_size, input_coords, input_features, output_features, batch_size, mode,
+                            input_normal=None):
+    feats = _cuda_f32(input_features, "InputLayer features")
+    coords = input_coords
+    if coords.dtype != torch.int64:
+        coords = coords.long()
+    coords = coords.contiguous()
+    if coords.dim() != 2 or coords.size(1) != 4:
+        raise ValueError("InputLayer: coords must be [P,4] = (x,y,z,batch) on this (3-D, batched) path")
+    if coords.size(0) != feats.size(0):
+        raise ValueError("InputLayer: coords and features disagree on the number of points")
+    on_dev = coords.is_cuda
+    n = C.c_int64(0)
+    h = m._handle(feats.device.index)
+    with torch.cuda.device(feats.device):
+        _lib.check(_lib.lib().scn_input_layer_build(h, _lib.size3(spatial_size), _ptr(coords), int(on_dev),
+                                                    coords.size(0), int(batch_size), int(mode), _stream(), C.byref(n)))
+        m._input_size = _lib.size3(spatial_size)[:]
+        output_features.resize_(n.value, feats.size(1))
+        _lib.check(_lib.lib().scn_input_layer_fwd(h, _ptr(feats), feats.size(1), _ptr(output_features), _stream()))
+
+
+def InputLayer_updateGradInput(m, d_input_features, d_output_features):
+    g = _cuda_f32(d_output_features, "InputLayer grad")
+    with torch.cuda.device(g.device):
+        d_input_features.resize_(int(_lib.lib().scn_n_points(m._handle())), g.size(1))
+        _lib.check(_lib.lib().scn_input_layer_bwd(m._handle(), _ptr(g), g.size(1), _ptr(d_input_features), _stream()))
+
+
+def OutputLayer_updateOutput(m, input_features, output_features):
+    x = _cuda_f32(input_features, "OutputLayer input")
+    with torch.cuda.device(x.device):
+        output_features.resize_(int(_lib.lib().scn_n_points(m._handle())), x.size(1))
+        _lib.check(_lib.lib().scn_output_layer_fwd(m._handle(), _ptr(x), x.size(1), _ptr(output_features), _stream()))
+
+
+def OutputLayer_updateGradInput(m, d_input_features, d_output_features):
+    g = _cuda_f32(d_output_features, "OutputLayer grad")
+    with torch.cuda.device(g.device):
+        n = int(_lib.lib().scn_nactive(m._handle(), _lib.size3(m._input_size)))
+        d_input_features.resize_(n, g.size(1))
+        _lib.check(_lib.lib().scn_output_layer_bwd(m._handle(), _ptr(g), g.size(1), _ptr(d_input_features), _stream()))
+
+
+# ---- convolutions (sparseconvnet.h:50-61, 89-116) ------------------------------------------------------
+def _check_weight(weight, v):
+    w = _cuda_f32(weight, "weight")
+    if w.dim() != 3 or w.size(0) != v:
+        raise ValueError(f"weight must be [{v}, nIn, nOut]")
+    return w
+
+
+def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_features, output_features, weight, bias,
+                                        dilated_rate=1):
+    if int(dilated_rate) != 1 or any(int(f) != 3 for f in filter_size.tolist()):
+        raise NotImplementedError("SubmanifoldConvolution: only 3x3x3, dilation 1 is on this path")
+    x, w, b = _cuda_f32(input_features, "input"), _check_weight(weight, 27), _opt(bias)
+    macs = C.c_double(0.0)
+    with torch.cuda.device(x.device):
+        n = m.getNActive(spatial_size)
+        if x.size(0) != n or x.size(1) != w.size(1):
+            raise ValueError(f"SubmanifoldConvolution: input is {tuple(x.shape)}, scale has {n} rows, nIn={w.size(1)}")
+        output_features.resize_(n, w.size(2))
+        _lib.check(_lib.lib().scn_subm_fwd(m._handle(), _lib.size3(spatial_size), _ptr(x), _ptr(w), _ptr(b),
+                                           _ptr(output_features), w.size(1), w.size(2), _precision, _stream(),
+                                           C.byref(macs)))
+    return macs.value
+
+
+def SubmanifoldConvolution_backward(spatial_size, filter_size, m, input_features, d_input_features, d_output_features,
+                                    weight, d_weight, d_bias, dilated_rate=1):
+    x, g, w = _cuda_f32(input_features, "input"), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 27)
+    with torch.cuda.device(x.device):
+        d_input_features.resize_(x.size(0), x.size(1))
+        _lib.check(_lib.lib().scn_subm_bwd(m._handle(), _lib.size3(spatial_size), _ptr(x), _ptr(g), _ptr(w),
+                                           _ptr(d_input_features), _ptr(d_weight), _ptr(_opt(d_bias)), w.size(1),
+                                           w.size(2), _precision, _stream()))
+
+
+def _check_2s2(filter_size, filter_stride):
+    if any(int(f) != 2 for f in filter_size.tolist()) or any(int(f) != 2 for f in filter_stride.tolist()):
+        raise NotImplementedError("Convolution/Deconvolution: only size 2 / stride 2 is on this path "
+                                  "(the reference GPU builder asserts the same, ConvolutionRules.h:354-358)")
+
+
+def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, input_features, output_features, weight,
+                             bias):
+    _check_2s2(filter_size, filter_stride)
+    x, w, b = _cuda_f32(input_features, "input"), _check_weight(weight, 8), _opt(bias)
+    macs, nc = C.c_double(0.0), C.c_int64(0)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().scn_strided_rulebook(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _stream(),
+                                                   C.byref(nc)))
+        output_features.resize_(nc.value, w.size(2))
+        _lib.check(_lib.lib().scn_conv_fwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(w),
+                                           _ptr(b), _ptr(output_features), w.size(1), w.size(2), _precision, _stream(),
+                                           C.byref(macs)))
+    return macs.value
+
+
+def Convolution_backward(in_size, out_size, filter_size, filter_stride, m, input_features, d_input_features,
+                         d_output_features, weight, d_weight, d_bias):
+    x, g, w = _cuda_f32(input_features, "input"), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 8)
+    with torch.cuda.device(x.device):
+        d_input_features.resize_(x.size(0), x.size(1))
+        _lib.check(_lib.lib().scn_conv_bwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(g),
+                                           _ptr(w), _ptr(d_input_features), _ptr(d_weight), _ptr(_opt(d_bias)),
+                                           w.size(1), w.size(2), _precision, _stream()))
+
+
+def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, input_features, output_features,
+                               weight, bias):
+    _check_2s2(filter_size, filter_stride)
+    x, w, b = _cuda_f32(input_features, "input"), _check_weight(weight, 8), _opt(bias)
+    macs = C.c_double(0.0)
+    with torch.cuda.device(x.device):
+        n = m.getNActive(out_size)
+        if n < 0:
+            raise _lib.ScnError("Deconvolution: output scale does not exist (no matching Convolution ran on this batch)")
+        output_features.resize_(n, w.size(2))
+        _lib.check(_lib.lib().scn_deconv_fwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(w),
+                                             _ptr(b), _ptr(output_features), w.size(1), w.size(2), _precision,
+                                             _stream(), C.byref(macs)))
+    return macs.value
+
+
+def Deconvolution_backward(in_size, out_size, filter_size, filter_stride, m, input_features, d_input_features,
+                           d_output_features, weight, d_weight, d_bias):
+    x, g, w = _cuda_f32(input_features, "input"), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 8)
+    with torch.cuda.device(x.device):
+        d_input_features.resize_(x.size(0), x.size(1))
+        _lib.check(_lib.lib().scn_deconv_bwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(g),
+                                             _ptr(w), _ptr(d_input_features), _ptr(d_weight), _ptr(_opt(d_bias)),
+                                             w.size(1), w.size(2), _precision, _stream()))
+
+
+# ---- batch norm (sparseconvnet.h:21-33) ------------------------------------------------------------------
+def BatchNormalization_updateOutput(input_features, output_features, saveMean, saveInvStd, runningMean, runningVar,
+                                    weight, bias, eps, momentum, train, leakiness):
+    x = _cuda_f32(input_features, "input")
+    with torch.cuda.device(x.device):
+        output_features.resize_(x.size(0), x.size(1))
+        _lib.check(_lib.lib().scn_bn_fwd(_ptr(x), _ptr(output_features), _ptr(saveMean), _ptr(saveInvStd),
+                                         _ptr(runningMean), _ptr(runningVar), _ptr(_opt(weight)), _ptr(_opt(bias)),
+                                         x.size(0), x.size(1), float(eps), float(momentum), int(bool(train)),
+                                         float(leakiness), _stream()))
+
+
+def BatchNormalization_backward(input_features, d_input_features, output_features, d_output_features, saveMean,
+                                saveInvStd, runningMean, runningVar, weight, bias, d_weight, d_bias, leakiness):
+    x, g = _cuda_f32(input_features, "input"), _cuda_f32(d_output_features, "grad")
+    with torch.cuda.device(x.device):
+        d_input_features.resize_(x.size(0), x.size(1))
+        _lib.check(_lib.lib().scn_bn_bwd(_ptr(x), _ptr(output_features), _ptr(g), _ptr(saveMean), _ptr(saveInvStd),
+                                         _ptr(_opt(weight)), _ptr(d_input_features), _ptr(_opt(d_weight)),
+                                         _ptr(_opt(d_bias)), x.size(0), x.size(1), float(leakiness), _stream()))
+
+
+# ---- 1x1 "NetworkInNetwork": the reference itself calls ATen's GEMM here (CUDA/NetworkInNetwork.cpp:9-50)
+def NetworkInNetwork_updateOutput(input_features, output_features, weight, bias):
+    n = input_features.size(0)
+    output_features.resize_(n, weight.size(1))
+    if _opt(bias) is not None:
+        torch.addmm(bias, input_features, weight, out=output_features)
+    else:
+        torch.mm(input_features, weight, out=output_features)
+    return float(n * weight.size(0) * weight.size(1))
+
+
+def NetworkInNetwork_updateGradInput(d_input_features, d_output_features, weight):
+    d_input_features.resize_(d_output_features.size(0), weight.size(0))
+    torch.mm(d_output_features, weight.t(), out=d_input_features)
+
+
+def NetworkInNetwork_accGradParameters(input_features, d_output_features, d_weight, d_bias):
+    if input_features.size(0):
+        if d_bias is not None and d_bias.numel():
+            torch.sum(d_output_features, 0, out=d_bias)
+        torch.mm(input_features.t(), d_output_features, out=d_weight)

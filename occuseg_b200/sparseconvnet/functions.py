@@ -1,0 +1,161 @@
+"""autograd glue between the nn.Modules in layers.py and the SCN entry points.
+
+Same division of labour as the reference Function classes (submanifoldConvolution.py:76-128,
+convolution.py:72-127, deconvolution.py:87-155, batchNormalization.py:90-161, ioLayers.py:157-223,
+networkInNetwork.py:14-59): forward allocates an empty output, calls SCN.*_updateOutput, keeps the
+Metadata alive on ctx; backward hands zero-initialised parameter gradients to SCN.*_backward.
+"""
+import torch
+from torch.autograd import Function
+
+from . import SCN
+from .utils import optionalTensorReturn
+
+# the reference keeps two global counters on the package (sparseconvnet/__init__.py:7-8)
+counters = {"multiplyAdd": 0.0, "hidden_states": 0}
+
+
+def _count(macs, out):
+    counters["multiplyAdd"] += macs
+    counters["hidden_states"] += out.nelement()
+
+
+class SubmanifoldConvolutionFunction(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, metadata, spatial_size, dimension, filter_size, dilated_rate=1):
+        ctx.scn_meta, ctx.dilated_rate = metadata, dilated_rate
+        ctx.save_for_backward(x, spatial_size, weight, bias, filter_size)
+        out = x.new_empty(0)
+        _count(SCN.SubmanifoldConvolution_updateOutput(spatial_size, filter_size, metadata, x, out, weight, bias,
+                                                       dilated_rate), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, spatial_size, weight, bias, filter_size = ctx.saved_tensors
+        gx, gw, gb = grad_out.new_empty(0), torch.zeros_like(weight), torch.zeros_like(bias)
+        SCN.SubmanifoldConvolution_backward(spatial_size, filter_size, ctx.scn_meta, x, gx, grad_out.contiguous(),
+                                            weight, gw, gb, ctx.dilated_rate)
+        del ctx.scn_meta
+        return gx, gw, optionalTensorReturn(gb), None, None, None, None, None
+
+
+class _StridedFunction(Function):
+    """Shared body of Convolution / Deconvolution (they differ only in the SCN entry they call)."""
+    fwd = bwd = None
+
+    @classmethod
+    def _forward(cls, ctx, x, weight, bias, metadata, in_size, out_size, dimension, filter_size, filter_stride):
+        ctx.scn_meta = metadata
+        ctx.save_for_backward(x, in_size, weight, bias, out_size, filter_size, filter_stride)
+        out = x.new_empty(0)
+        _count(cls.fwd(in_size, out_size, filter_size, filter_stride, metadata, x, out, weight, bias), out)
+        return out
+
+    @classmethod
+    def _backward(cls, ctx, grad_out):
+        x, in_size, weight, bias, out_size, filter_size, filter_stride = ctx.saved_tensors
+        gx, gw, gb = grad_out.new_empty(0), torch.zeros_like(weight), torch.zeros_like(bias)
+        cls.bwd(in_size, out_size, filter_size, filter_stride, ctx.scn_meta, x, gx, grad_out.contiguous(), weight, gw, gb)
+        del ctx.scn_meta
+        return gx, gw, optionalTensorReturn(gb), None, None, None, None, None, None
+
+
+class ConvolutionFunction(_StridedFunction):
+    fwd, bwd = staticmethod(SCN.Convolution_updateOutput), staticmethod(SCN.Convolution_backward)
+
+    @staticmethod
+    def forward(ctx, *a):
+        return ConvolutionFunction._forward(ctx, *a)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ConvolutionFunction._backward(ctx, g)
+
+
+class DeconvolutionFunction(_StridedFunction):
+    fwd, bwd = staticmethod(SCN.Deconvolution_updateOutput), staticmethod(SCN.Deconvolution_backward)
+
+    @staticmethod
+    def forward(ctx, *a):
+        return DeconvolutionFunction._forward(ctx, *a)
+
+    @staticmethod
+    def backward(ctx, g):
+        return DeconvolutionFunction._backward(ctx, g)
+
+
+class BatchNormalizationFunction(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, train, leakiness):
+        ctx.train, ctx.leakiness = train, leakiness
+        n_planes = running_mean.shape[0]
+        out = x.new_empty(0)
+        save_mean, save_invstd = x.new_empty(n_planes), x.new_empty(n_planes)
+        SCN.BatchNormalization_updateOutput(x, out, save_mean, save_invstd, running_mean, running_var, weight, bias,
+                                            eps, momentum, train, leakiness)
+        ctx.save_for_backward(x, out, weight, bias, running_mean, running_var, save_mean, save_invstd)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, out, weight, bias, running_mean, running_var, save_mean, save_invstd = ctx.saved_tensors
+        assert ctx.train, "BatchNormalization backward is only defined in training mode (as in the reference)"
+        gx, gw, gb = grad_out.new_empty(0), torch.zeros_like(weight), torch.zeros_like(bias)
+        SCN.BatchNormalization_backward(x, gx, out, grad_out.contiguous(), save_mean, save_invstd, running_mean,
+                                        running_var, weight, bias, gw, gb, ctx.leakiness)
+        return gx, optionalTensorReturn(gw), optionalTensorReturn(gb), None, None, None, None, None, None
+
+
+class NetworkInNetworkFunction(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        out = x.new_empty(0)
+        ctx.save_for_backward(x, weight, bias)
+        _count(SCN.NetworkInNetwork_updateOutput(x, out, weight, bias), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight, bias = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        gx, gw = grad_out.new_empty(0), torch.zeros_like(weight)
+        gb = torch.zeros_like(bias) if bias is not None and bias.numel() else None
+        SCN.NetworkInNetwork_updateGradInput(gx, grad_out, weight)
+        SCN.NetworkInNetwork_accGradParameters(x, grad_out, gw, gb)
+        return gx, gw, gb
+
+
+class InputLayerFunction(Function):
+    @staticmethod
+    def forward(ctx, dimension, metadata, spatial_size, coords, features, batch_size, mode, normals,
+                normal_guide_scale=10241):
+        ctx.scn_meta = metadata
+        metadata.setNormalGuideScale(normal_guide_scale)
+        out = features.new_empty(0)
+        SCN.InputLayer_updateOutput(metadata, spatial_size, coords, features.contiguous(), out, batch_size, mode,
+                                    normals)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        gx = grad_out.new_empty(0)
+        SCN.InputLayer_updateGradInput(ctx.scn_meta, gx, grad_out.contiguous())
+        del ctx.scn_meta
+        return None, None, None, None, gx, None, None, None, None
+
+
+class OutputLayerFunction(Function):
+    @staticmethod
+    def forward(ctx, dimension, metadata, features):
+        ctx.scn_meta = metadata
+        out = features.new_empty(0)
+        SCN.OutputLayer_updateOutput(metadata, features.contiguous(), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        gx = grad_out.new_empty(0)
+        SCN.OutputLayer_updateGradInput(ctx.scn_meta, gx, grad_out.contiguous())
+        del ctx.scn_meta
+        return None, None, gx

@@ -1,0 +1,261 @@
+"""nn.Module surface of the hot path, constructor-compatible with the reference classes so that
+examples/ScanNet/model.py (InstanceDenseUNet) and reference state_dicts work unchanged:
+
+  InputLayer / OutputLayer        sparseconvnet/ioLayers.py:15-87
+  SubmanifoldConvolution          sparseconvnet/submanifoldConvolution.py:18-69   weight [27, nIn, nOut]
+  Convolution / Deconvolution     sparseconvnet/convolution.py:14-70, deconvolution.py:13-85   weight [8, nIn, nOut]
+  BatchNormalization (+ReLU...)   sparseconvnet/batchNormalization.py:13-88       weight, bias, running_mean, running_var
+  NetworkInNetwork                sparseconvnet/networkInNetwork.py:62-88         weight [nIn, nOut]
+  Sequential / ConcatTable / AddTable / JoinTable / Identity   sequential.py, tables.py, identity.py
+
+Parameter names, shapes and initialisation (normal(0, sqrt(2/(nIn*volume)))) follow the reference.
+"""
+import torch
+from torch.nn import Module, Parameter
+
+from . import functions as F
+from .SCN import Metadata_3
+from .tensor import SparseConvNetTensor
+from .utils import optionalTensor, toLongTensor
+
+
+def Metadata(dim):
+    if dim != 3:
+        raise NotImplementedError("only 3-D grids are on the B200 hot path")
+    return Metadata_3()
+
+
+def _same(ref, features, spatial_size=None):
+    t = SparseConvNetTensor(features, ref.metadata, ref.spatial_size if spatial_size is None else spatial_size)
+    return t
+
+
+def _size_str(v):
+    v = v.tolist()
+    return str(v[0]) if min(v) == max(v) else "(" + ",".join(map(str, v)) + ")"
+
+
+# ---- containers -------------------------------------------------------------------------------------------
+class Sequential(torch.nn.Sequential):
+    def add(self, module):
+        self._modules[str(len(self._modules))] = module
+        return self
+
+    def input_spatial_size(self, out_size):
+        for m in reversed(list(self._modules.values())):
+            out_size = m.input_spatial_size(out_size)
+        return out_size
+
+
+class ConcatTable(torch.nn.Sequential):
+    def add(self, module):
+        self._modules[str(len(self._modules))] = module
+        return self
+
+    def forward(self, input):
+        return [m(input) for m in self._modules.values()]
+
+    def input_spatial_size(self, out_size):
+        return self._modules["0"].input_spatial_size(out_size)
+
+
+class AddTable(torch.nn.Sequential):
+    def forward(self, input):
+        total = input[0].features
+        for t in input[1:]:
+            total = total + t.features
+        return _same(input[0], total)
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+
+class JoinTable(torch.nn.Sequential):
+    def forward(self, input):
+        return _same(input[0], torch.cat([t.features for t in input], 1))
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+
+class Identity(Module):
+    def forward(self, input):
+        return input
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+
+# ---- IO -------------------------------------------------------------------------------------------------
+class InputLayer(Module):
+    """input = [coords [P,4] (x,y,z,batch; float or long), features [P,C] CUDA float, normals (ignored),
+    batch_size].  mode 3 sums, mode 4 averages the features of points sharing a voxel."""
+
+    def __init__(self, dimension, spatial_size, mode=3, normal_guide_scale=10240):
+        super().__init__()
+        self.dimension = dimension
+        self.spatial_size = toLongTensor(dimension, spatial_size)
+        self.mode = mode
+        self.normal_guide_scale = normal_guide_scale
+
+    def forward(self, input):
+        coords = input[0]
+        if not coords.is_cuda:
+            coords = coords.type(torch.LongTensor)     # truncation toward zero, as ioLayers.py:56
+        out = SparseConvNetTensor(metadata=Metadata(self.dimension), spatial_size=self.spatial_size)
+        batch_size = input[3] if len(input) > 3 else int(coords[:, -1].max().item()) + 1
+        normals = input[2] if len(input) > 2 else None
+        out.features = F.InputLayerFunction.apply(self.dimension, out.metadata, self.spatial_size, coords, input[1],
+                                                  batch_size, self.mode, normals, self.normal_guide_scale)
+        return out
+
+
+class OutputLayer(Module):
+    def __init__(self, dimension):
+        super().__init__()
+        self.dimension = dimension
+
+    def forward(self, input):
+        return F.OutputLayerFunction.apply(self.dimension, input.metadata, input.features)
+
+
+# ---- convolutions -----------------------------------------------------------------------------------------
+class _ConvBase(Module):
+    def _init_weight(self, dimension, nIn, nOut, filter_size, bias):
+        self.dimension, self.nIn, self.nOut = dimension, nIn, nOut
+        self.filter_size = toLongTensor(dimension, filter_size)
+        self.filter_volume = int(self.filter_size.prod().item())
+        std = (2.0 / nIn / self.filter_volume) ** 0.5
+        self.weight = Parameter(torch.empty(self.filter_volume, nIn, nOut).normal_(0, std))
+        if bias:
+            self.bias = Parameter(torch.zeros(nOut))
+
+    def _check(self, input):
+        assert input.features.nelement() == 0 or input.features.size(1) == self.nIn, (self.nIn, self.nOut, input)
+
+
+class SubmanifoldConvolution(_ConvBase):
+    def __init__(self, dimension, nIn, nOut, filter_size, bias, dilated_rate=1):
+        super().__init__()
+        self._init_weight(dimension, nIn, nOut, filter_size, bias)
+        self.dilated_rate = dilated_rate
+
+    def forward(self, input):
+        self._check(input)
+        feats = F.SubmanifoldConvolutionFunction.apply(input.features, self.weight, optionalTensor(self, "bias"),
+                                                       input.metadata, input.spatial_size, self.dimension,
+                                                       self.filter_size, self.dilated_rate)
+        return _same(input, feats)
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+    def __repr__(self):
+        return f"SubmanifoldConvolution {self.nIn}->{self.nOut} C{_size_str(self.filter_size)}"
+
+
+ValidConvolution = SubmanifoldConvolution
+
+
+class Convolution(_ConvBase):
+    def __init__(self, dimension, nIn, nOut, filter_size, filter_stride, bias):
+        super().__init__()
+        self._init_weight(dimension, nIn, nOut, filter_size, bias)
+        self.filter_stride = toLongTensor(dimension, filter_stride)
+
+    def forward(self, input):
+        self._check(input)
+        out_size = (input.spatial_size - self.filter_size) // self.filter_stride + 1
+        assert ((out_size - 1) * self.filter_stride + self.filter_size == input.spatial_size).all(), \
+            (input.spatial_size, out_size, self.filter_size, self.filter_stride)
+        feats = F.ConvolutionFunction.apply(input.features, self.weight, optionalTensor(self, "bias"), input.metadata,
+                                            input.spatial_size, out_size, self.dimension, self.filter_size,
+                                            self.filter_stride)
+        return _same(input, feats, out_size)
+
+    def input_spatial_size(self, out_size):
+        return (out_size - 1) * self.filter_stride + self.filter_size
+
+    def __repr__(self):
+        return f"Convolution {self.nIn}->{self.nOut} C{_size_str(self.filter_size)}/{_size_str(self.filter_stride)}"
+
+
+class Deconvolution(_ConvBase):
+    def __init__(self, dimension, nIn, nOut, filter_size, filter_stride, bias):
+        super().__init__()
+        self._init_weight(dimension, nIn, nOut, filter_size, bias)
+        self.filter_stride = toLongTensor(dimension, filter_stride)
+
+    def forward(self, input):
+        self._check(input)
+        out_size = (input.spatial_size - 1) * self.filter_stride + self.filter_size
+        feats = F.DeconvolutionFunction.apply(input.features, self.weight, optionalTensor(self, "bias"), input.metadata,
+                                              input.spatial_size, out_size, self.dimension, self.filter_size,
+                                              self.filter_stride)
+        return _same(input, feats, out_size)
+
+    def input_spatial_size(self, out_size):
+        in_size = (out_size - self.filter_size) // self.filter_stride + 1
+        assert ((in_size - 1) * self.filter_stride + self.filter_size == out_size).all()
+        return in_size
+
+    def __repr__(self):
+        return f"Deconvolution {self.nIn}->{self.nOut} C{_size_str(self.filter_size)}/{_size_str(self.filter_stride)}"
+
+
+class NetworkInNetwork(Module):
+    def __init__(self, nIn, nOut, bias):
+        super().__init__()
+        self.nIn, self.nOut = nIn, nOut
+        self.weight = Parameter(torch.empty(nIn, nOut).normal_(0, (2.0 / nIn) ** 0.5))
+        if bias:
+            self.bias = Parameter(torch.zeros(nOut))
+
+    def forward(self, input):
+        assert input.features.nelement() == 0 or input.features.size(1) == self.nIn, (self.nIn, input.features.shape)
+        return _same(input, F.NetworkInNetworkFunction.apply(input.features, self.weight, optionalTensor(self, "bias")))
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+    def __repr__(self):
+        return f"NetworkInNetwork{self.nIn}->{self.nOut}"
+
+
+# ---- batch norm ---------------------------------------------------------------------------------------------
+class BatchNormalization(Module):
+    """eps 1e-4, momentum 0.9 (running = 0.9*running + 0.1*batch), leakiness: 0 ReLU, (0,1) leaky, 1 none."""
+
+    def __init__(self, nPlanes, eps=1e-4, momentum=0.9, affine=True, leakiness=1):
+        super().__init__()
+        self.nPlanes, self.eps, self.momentum, self.affine, self.leakiness = nPlanes, eps, momentum, affine, leakiness
+        self.register_buffer("running_mean", torch.zeros(nPlanes))
+        self.register_buffer("running_var", torch.ones(nPlanes))
+        if affine:
+            self.weight = Parameter(torch.ones(nPlanes))
+            self.bias = Parameter(torch.zeros(nPlanes))
+
+    def forward(self, input):
+        assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes, \
+            (self.nPlanes, input.features.shape)
+        feats = F.BatchNormalizationFunction.apply(input.features, optionalTensor(self, "weight"),
+                                                   optionalTensor(self, "bias"), self.running_mean, self.running_var,
+                                                   self.eps, self.momentum, self.training, self.leakiness)
+        return _same(input, feats)
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+    def __repr__(self):
+        s = f"BatchNorm({self.nPlanes},eps={self.eps},momentum={self.momentum},affine={self.affine}"
+        return s + (f",leakiness={self.leakiness})" if self.leakiness > 0 else ")")
+
+
+class BatchNormReLU(BatchNormalization):
+    def __init__(self, nPlanes, eps=1e-4, momentum=0.9):
+        super().__init__(nPlanes, eps, momentum, True, 0)
+
+
+class BatchNormLeakyReLU(BatchNormalization):
+    def __init__(self, nPlanes, eps=1e-4, momentum=0.9, leakiness=0.333):
+        super().__init__(nPlanes, eps, momentum, True, leakiness)

@@ -79,7 +79,7 @@ def voxelize(coords, batch_size=None):
         counts = np.diff(np.concatenate([starts, [e - s]]))
         if n:
             max_repeat = max(max_repeat, int(counts.max()))
-        rule_ptr.append(rule_ptr[-1][-1] + np.cumsum(counts))
+        rule_ptr.append(int(s) + np.cumsum(counts))                 # points before this sample = s
         rule_pts.append((order + s).astype(np.int32))              # d_index[tid] = tid is global (CUDPPWrapper.cu:82)
         ctr.append(ctr[-1] + n)
     return dict(

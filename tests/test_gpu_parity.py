@@ -1,0 +1,288 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI (ctypes -> libscn_b200.so), against
+ (a) the committed golden vectors = outputs of the reference's own CPU code (tests/golden/make_golden.py),
+ (b) the oracle on seeded scenes at sizes it finishes in seconds,
+ (c) size-independent properties at BASELINE.json's full sizes.
+Tolerances (max-norm relative, conftest.rel_err): fp32 path 1e-5; tf32 tensor-core tiles 2e-2 (north_star).
+Integer results (row order, rulebooks, MAC counts) must be bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NAMES, have_cuda, load_golden, rel_err, unpack
+
+pytestmark = pytest.mark.gpu
+
+if have_cuda():
+    import torch
+    import occuseg_b200.sparseconvnet as scn
+    from occuseg_b200.sparseconvnet import SCN
+    from occuseg_b200 import scenes
+from oracle import arith, rulebook as rb
+
+FP32_TOL = 1e-5
+TF32_TOL = 2e-2
+SIZE = 4096
+
+
+def lt(v):
+    return torch.LongTensor([v, v, v])
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def build_meta(coords, batch, feats=None, mode=4):
+    m = SCN.Metadata_3()
+    c = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.int64))
+    f = cu(feats if feats is not None else np.zeros((len(coords), 1), np.float32))
+    out = torch.empty(0, device="cuda")
+    SCN.InputLayer_updateOutput(m, lt(SIZE), c, f, out, batch, mode, None)
+    return m, out
+
+
+def canon_equal(a, b):
+    a, b = rb.canonical(a), rb.canonical(b)
+    return len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def strided_lists(parent, off):
+    rows = np.arange(len(parent), dtype=np.int32)
+    return [np.stack([rows[off == k], parent[off == k]], 1) for k in range(8)]
+
+
+# ---------------------------------------------------------------------------------------- rulebooks (bit-exact)
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_rulebooks_match_golden(name):
+    g = load_golden(name)
+    B = int(g["batch"])
+    m, feats = build_meta(g["coords"], B, g["feats"])
+    assert np.array_equal(m.getSpatialLocations(lt(SIZE)).numpy(), g["locs"].astype(np.int64))
+    nbr, n_rules = m.submanifoldNeighbourTable(lt(SIZE))
+    assert n_rules == len(g["subm_flat"])
+    assert canon_equal(rb.rules_from_neighbour_table(nbr.numpy()), unpack(g["subm_flat"], g["subm_off"]))
+    parent, off, nc = m.stridedTable(lt(SIZE), lt(SIZE // 2))
+    assert nc == len(g["coarse_locs"])
+    assert canon_equal(strided_lists(parent.numpy(), off.numpy()), unpack(g["strided_flat"], g["strided_off"]))
+    assert np.array_equal(m.getSpatialLocations(lt(SIZE // 2)).numpy(), g["coarse_locs"].astype(np.int64))
+    nbr_c, _ = m.submanifoldNeighbourTable(lt(SIZE // 2))
+    assert canon_equal(rb.rules_from_neighbour_table(nbr_c.numpy()), unpack(g["subm_coarse_flat"], g["subm_coarse_off"]))
+    # InputLayer mode 4 mean (fp32, same summation order as the reference kernel)
+    assert rel_err(feats.cpu().numpy(), g["input_mean"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("preset,seeds", [("small", (0, 1, 2)), ("S100k", (0,))])
+def test_rulebooks_match_oracle_on_scenes(preset, seeds):
+    coords, feats = scenes.make_batch(preset, seeds)
+    B = len(seeds)
+    vox = rb.voxelize(coords, B)
+    m, _ = build_meta(coords, B)
+    locs = vox["locs"]
+    size = SIZE
+    for level in range(4):
+        assert np.array_equal(m.getSpatialLocations(lt(size)).numpy(), locs)
+        nbr, n_rules = m.submanifoldNeighbourTable(lt(size))
+        want = rb.submanifold_rules(locs, B)
+        assert n_rules == sum(len(r) for r in want)
+        assert canon_equal(rb.rules_from_neighbour_table(nbr.numpy()), want)
+        parent, off, nc = m.stridedTable(lt(size), lt(size // 2))
+        locs, want_s = rb.strided_rules(locs, B)
+        assert nc == len(locs)
+        assert canon_equal(strided_lists(parent.numpy(), off.numpy()), want_s)
+        size //= 2
+
+
+def test_rulebook_edge_cases():
+    # duplicates, an empty sample in the middle, a single-voxel sample, unsorted points inside a sample
+    coords = np.array([[5, 5, 5, 0], [4, 5, 5, 0], [5, 5, 5, 0], [5, 5, 4, 0], [0, 0, 0, 2], [1, 0, 0, 2], [0, 0, 0, 2],
+                       [7, 7, 7, 3]], np.int64)
+    feats = np.arange(16, dtype=np.float32).reshape(8, 2)
+    m, out = build_meta(coords, 4, feats)
+    vox = rb.voxelize(coords, 4)
+    assert np.array_equal(m.getSpatialLocations(lt(SIZE)).numpy(), vox["locs"])
+    assert rel_err(out.cpu().numpy(), rb.input_layer_mean(feats, vox, True)) < FP32_TOL
+    nbr, n_rules = m.submanifoldNeighbourTable(lt(SIZE))
+    assert canon_equal(rb.rules_from_neighbour_table(nbr.numpy()), rb.submanifold_rules(vox["locs"], 4))
+    parent, off, nc = m.stridedTable(lt(SIZE), lt(SIZE // 2))
+    clocs, want = rb.strided_rules(vox["locs"], 4)
+    assert nc == len(clocs) and canon_equal(strided_lists(parent.numpy(), off.numpy()), want)
+
+
+def test_bad_inputs_raise():
+    from occuseg_b200._lib import ScnError
+    with pytest.raises(ScnError):
+        build_meta(np.array([[1, 2, -3, 0]], np.int64), 1)            # negative coordinate
+    with pytest.raises(ScnError):
+        build_meta(np.array([[1, 2, 3, 5]], np.int64), 2)             # batch index out of range
+    m, _ = build_meta(np.array([[1, 2, 3, 0]], np.int64), 1)
+    with pytest.raises(ScnError):
+        m.submanifoldNeighbourTable(lt(123))                          # unknown scale
+    with pytest.raises(TypeError):
+        SCN.BatchNormalization_updateOutput(torch.zeros(4, 4), torch.empty(0), None, None, None, None, None, None,
+                                            1e-4, 0.9, True, 0.0)     # CPU tensor: no CPU path
+
+
+# ---------------------------------------------------------------------------------------- arithmetic vs golden
+def _subm(m, x, w, g, size=SIZE):
+    y = torch.empty(0, device="cuda")
+    macs = SCN.SubmanifoldConvolution_updateOutput(lt(size), lt(3), m, x, y, w, torch.empty(0), 1)
+    dx, dw = torch.empty(0, device="cuda"), torch.zeros_like(w)
+    SCN.SubmanifoldConvolution_backward(lt(size), lt(3), m, x, dx, g, w, dw, torch.empty(0), 1)
+    return y, macs, dx, dw
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_convolutions_match_reference_outputs(name, precision):
+    g = load_golden(name)
+    tol = FP32_TOL if precision == "fp32" else TF32_TOL
+    scn.set_precision(precision)
+    try:
+        m, _ = build_meta(g["coords"], int(g["batch"]))
+        x, w, go = cu(g["x"]), cu(g["w"]), cu(g["g"])
+        y, macs, dx, dw = _subm(m, x, w, go)
+        assert macs == float(g["macs"])
+        assert rel_err(y.cpu().numpy(), g["y"]) < tol
+        assert rel_err(dx.cpu().numpy(), g["dx"]) < tol
+        assert rel_err(dw.cpu().numpy(), g["dw"]) < tol
+        # strided convolution
+        w8, gc = cu(g["w8"]), cu(g["gc"])
+        yc = torch.empty(0, device="cuda")
+        SCN.Convolution_updateOutput(lt(SIZE), lt(SIZE // 2), lt(2), lt(2), m, x, yc, w8, torch.empty(0))
+        assert rel_err(yc.cpu().numpy(), g["yc"]) < tol
+        dxc, dw8 = torch.empty(0, device="cuda"), torch.zeros_like(w8)
+        SCN.Convolution_backward(lt(SIZE), lt(SIZE // 2), lt(2), lt(2), m, x, dxc, gc, w8, dw8, torch.empty(0))
+        assert rel_err(dxc.cpu().numpy(), g["dxc"]) < tol
+        assert rel_err(dw8.cpu().numpy(), g["dw8"]) < tol
+        # deconvolution over the same rulebook
+        xd, wd, gd = cu(g["xd"]), cu(g["wd"]), cu(g["gd"])
+        yd = torch.empty(0, device="cuda")
+        SCN.Deconvolution_updateOutput(lt(SIZE // 2), lt(SIZE), lt(2), lt(2), m, xd, yd, wd, torch.empty(0))
+        assert rel_err(yd.cpu().numpy(), g["yd"]) < tol
+        dxd, dwd = torch.empty(0, device="cuda"), torch.zeros_like(wd)
+        SCN.Deconvolution_backward(lt(SIZE // 2), lt(SIZE), lt(2), lt(2), m, xd, dxd, gd, wd, dwd, torch.empty(0))
+        assert rel_err(dxd.cpu().numpy(), g["dxd"]) < tol
+        assert rel_err(dwd.cpu().numpy(), g["dwd"]) < tol
+    finally:
+        scn.set_precision("tf32")
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_batchnorm_matches_reference_outputs(name):
+    g = load_golden(name)
+    C = g["x"].shape[1]
+    x, gamma, beta = cu(g["x"]), cu(g["gamma"]), cu(g["beta"])
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    y, sm, si = torch.empty(0, device="cuda"), torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    SCN.BatchNormalization_updateOutput(x, y, sm, si, rm, rv, gamma, beta, 1e-4, 0.9, True, 0.0)
+    for got, key in [(y, "bn_y"), (sm, "bn_mean"), (si, "bn_invstd"), (rm, "bn_rm"), (rv, "bn_rv")]:
+        assert rel_err(got.cpu().numpy(), g[key]) < FP32_TOL, key
+    gb = cu(g["gb"])
+    gb_before = gb.clone()
+    dx, dg, db = torch.empty(0, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    SCN.BatchNormalization_backward(x, dx, y, gb, sm, si, rm, rv, gamma, beta, dg, db, 0.0)
+    assert torch.equal(gb, gb_before)       # d_output is not mutated (documented deviation)
+    assert rel_err(dx.cpu().numpy(), g["bn_dx"]) < FP32_TOL
+    assert rel_err(dg.cpu().numpy(), g["bn_dgamma"]) < FP32_TOL
+    assert rel_err(db.cpu().numpy(), g["bn_dbeta"]) < FP32_TOL
+    # eval mode uses the running statistics
+    y2 = torch.empty(0, device="cuda")
+    SCN.BatchNormalization_updateOutput(x, y2, sm, si, rm, rv, gamma, beta, 1e-4, 0.9, False, 0.333)
+    want = arith.batchnorm_forward(g["x"], g["gamma"], g["beta"], rm.cpu().numpy(), rv.cpu().numpy(), train=False,
+                                   leakiness=0.333)[0]
+    assert rel_err(y2.cpu().numpy(), want) < FP32_TOL
+
+
+def test_io_layers_roundtrip_and_grads():
+    coords, feats = scenes.make_batch("tiny", (3, 4))
+    vox = rb.voxelize(coords, 2)
+    N, P = len(vox["locs"]), len(coords)
+    m, out = build_meta(coords, 2, feats, mode=4)
+    assert out.shape == (N, 3)
+    rng = np.random.default_rng(0)
+    cnt = np.diff(vox["rule_ptr"]).astype(np.float32)
+    # InputLayer backward: d_point = (1/n) * d_row
+    gr = rng.standard_normal((N, 5)).astype(np.float32)
+    gp = torch.empty(0, device="cuda")
+    SCN.InputLayer_updateGradInput(m, gp, cu(gr))
+    want = gr[vox["row_of_point"]] / cnt[vox["row_of_point"], None]
+    assert gp.shape == (P, 5) and rel_err(gp.cpu().numpy(), want) < FP32_TOL
+    # OutputLayer forward = copy of the voxel row; backward = sum over the voxel's points
+    xr = rng.standard_normal((N, 8)).astype(np.float32)
+    op = torch.empty(0, device="cuda")
+    SCN.OutputLayer_updateOutput(m, cu(xr), op)
+    assert np.array_equal(op.cpu().numpy(), xr[vox["row_of_point"]])
+    gpo = rng.standard_normal((P, 8)).astype(np.float32)
+    gi = torch.empty(0, device="cuda")
+    SCN.OutputLayer_updateGradInput(m, gi, cu(gpo))
+    want = np.zeros((N, 8), np.float32)
+    np.add.at(want, vox["row_of_point"], gpo)
+    assert rel_err(gi.cpu().numpy(), want) < FP32_TOL
+    # mode 3 sums
+    m3, out3 = build_meta(coords, 2, feats, mode=3)
+    assert rel_err(out3.cpu().numpy(), rb.input_layer_mean(feats, vox, False)) < FP32_TOL
+
+
+# ---------------------------------------------------------------------------------------- config 1 + properties
+@pytest.mark.parametrize("precision,cin,cout", [("fp32", 16, 16), ("fp32", 3, 32), ("tf32", 32, 32), ("tf32", 64, 64),
+                                                ("tf32", 128, 64), ("tf32", 64, 96)])
+def test_submanifold_on_scene_vs_oracle(precision, cin, cout):
+    """BASELINE.json config 1 shape (100k-voxel scene, 3x3x3, 16->16) plus the tensor-core channel shapes."""
+    tol = FP32_TOL if precision == "fp32" else TF32_TOL
+    coords, _ = scenes.make_batch("S100k", (0,))
+    vox = rb.voxelize(coords, 1)
+    rules = rb.submanifold_rules(vox["locs"], 1)
+    N = len(vox["locs"])
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((N, cin)).astype(np.float32)
+    w = (rng.standard_normal((27, cin, cout)) * (2.0 / cin / 27) ** 0.5).astype(np.float32)
+    go = rng.standard_normal((N, cout)).astype(np.float32)
+    scn.set_precision(precision)
+    try:
+        m, _ = build_meta(coords, 1)
+        y, macs, dx, dw = _subm(m, cu(x), cu(w), cu(go))
+    finally:
+        scn.set_precision("tf32")
+    y0, macs0 = arith.rule_conv_forward(x, w, rules, N)
+    dx0, dw0 = arith.rule_conv_backward(x, go, w, rules)
+    assert macs == macs0
+    assert rel_err(y.cpu().numpy(), y0) < tol
+    assert rel_err(dx.cpu().numpy(), dx0) < tol
+    assert rel_err(dw.cpu().numpy(), dw0) < tol
+
+
+def test_full_size_properties():
+    """BASELINE.json config 3 size (8 x S250k ~ 2 M voxels): properties that need no oracle run.
+    linearity in the input, centre-only weights == x @ W[13], adjointness <conv(x),g> == <x,dgrad(g)> and
+    == <W, wgrad> (the three passes describe one bilinear form)."""
+    coords, _ = scenes.make_batch("S250k", tuple(range(8)))
+    m, _ = build_meta(coords, 8)
+    N = m.getNActive(lt(SIZE))
+    assert N > 1_800_000
+    C = 32
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(N, C, device="cuda", generator=gen)
+    g = torch.randn(N, C, device="cuda", generator=gen)
+    w = torch.randn(27, C, C, device="cuda", generator=gen) * 0.05
+    for precision, tol in (("fp32", 1e-4), ("tf32", TF32_TOL)):
+        scn.set_precision(precision)
+        try:
+            y, macs, dx, dw = _subm(m, x, w, g)
+            y2 = _subm(m, 2 * x, w, g)[0]
+            assert rel_err(y2.cpu().numpy(), (2 * y).cpu().numpy()) < 1e-6          # exact: scaling by 2
+            wc = torch.zeros_like(w)
+            wc[13] = w[13]
+            yc = _subm(m, x, wc, g)[0]
+            assert rel_err(yc.cpu().numpy(), (x @ w[13]).cpu().numpy()) < max(tol, 2e-3)  # torch.mm may use tf32
+            a = (y.double() * g.double()).sum().item()
+            b = (x.double() * dx.double()).sum().item()
+            c = (w.double() * dw.double()).sum().item()
+            assert abs(a - b) / abs(a) < tol and abs(a - c) / abs(a) < tol
+        finally:
+            scn.set_precision("tf32")
+    nbr, n_rules = m.submanifoldNeighbourTable(lt(SIZE))
+    nbr = nbr.numpy()
+    # symmetry of the rule relation: nbr[26-k][nbr[k][o]] == o
+    for k in (0, 4, 13, 22):
+        o = np.flatnonzero(nbr[k] >= 0)
+        assert np.array_equal(nbr[26 - k][nbr[k][o]], o)
+    assert n_rules == int((nbr >= 0).sum())

@@ -1,0 +1,154 @@
+"""CPU tests of the checker itself: the numpy restatement against the committed golden vectors (which
+were produced by the reference's own compiled CPU code), the compiled reference (oracle/_ref) when present,
+and the edge cases the domain has (duplicates, single voxels, empty samples, sample boundaries, key aliasing)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err, unpack
+from oracle import arith, rulebook as rb
+
+
+def _canon_equal(a, b):
+    a, b = rb.canonical(a), rb.canonical(b)
+    return len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_rulebook_restatement_matches_golden(golden):
+    g = golden
+    B = int(g["batch"])
+    vox = rb.voxelize(g["coords"].astype(np.int64), B)
+    assert np.array_equal(vox["locs"], g["locs"])
+    assert np.array_equal(vox["row_of_point"], g["row_of_point"])
+    assert _canon_equal(rb.submanifold_rules(vox["locs"], B), unpack(g["subm_flat"], g["subm_off"]))
+    clocs, strided = rb.strided_rules(vox["locs"], B)
+    assert np.array_equal(clocs, g["coarse_locs"])
+    assert _canon_equal(strided, unpack(g["strided_flat"], g["strided_off"]))
+    assert _canon_equal(rb.submanifold_rules(clocs, B), unpack(g["subm_coarse_flat"], g["subm_coarse_off"]))
+
+
+def test_arith_port_matches_reference_outputs(golden):
+    """golden y/dx/dw... are outputs of sparseconvnet/SCN/CPU/*.cpp; tolerance 1e-5 (fp32, GEMM summation order)."""
+    g = golden
+    N, Nc = len(g["locs"]), len(g["coarse_locs"])
+    subm = unpack(g["subm_flat"], g["subm_off"])
+    strided = unpack(g["strided_flat"], g["strided_off"])
+    y, macs = arith.rule_conv_forward(g["x"], g["w"], subm, N)
+    assert rel_err(y, g["y"]) < 1e-5 and macs == float(g["macs"])
+    dx, dw = arith.rule_conv_backward(g["x"], g["g"], g["w"], subm)
+    assert rel_err(dx, g["dx"]) < 1e-5 and rel_err(dw, g["dw"]) < 1e-5
+    yc, _ = arith.rule_conv_forward(g["x"], g["w8"], strided, Nc)
+    assert rel_err(yc, g["yc"]) < 1e-5
+    dxc, dw8 = arith.rule_conv_backward(g["x"], g["gc"], g["w8"], strided)
+    assert rel_err(dxc, g["dxc"]) < 1e-5 and rel_err(dw8, g["dw8"]) < 1e-5
+    yd, _ = arith.rule_conv_forward(g["xd"], g["wd"], strided, N, in_col=1, out_col=0)
+    assert rel_err(yd, g["yd"]) < 1e-5
+    dxd, dwd = arith.rule_conv_backward(g["xd"], g["gd"], g["wd"], strided, in_col=1, out_col=0)
+    assert rel_err(dxd, g["dxd"]) < 1e-5 and rel_err(dwd, g["dwd"]) < 1e-5
+    C = g["x"].shape[1]
+    out = arith.batchnorm_forward(g["x"], g["gamma"], g["beta"], np.zeros(C, np.float32), np.ones(C, np.float32))
+    for got, key in zip(out, ["bn_y", "bn_mean", "bn_invstd", "bn_rm", "bn_rv"]):
+        assert rel_err(got, g[key]) < 1e-5, key
+    bdx, bdg, bdb = arith.batchnorm_backward(g["x"], g["bn_y"], g["gb"], g["gamma"], g["bn_mean"], g["bn_invstd"])
+    assert rel_err(bdx, g["bn_dx"]) < 1e-5 and rel_err(bdg, g["bn_dgamma"]) < 1e-5 and rel_err(bdb, g["bn_dbeta"]) < 1e-5
+
+
+def test_compiled_reference_reproduces_golden(golden):
+    """When oracle/_ref is loadable (authoring container, or the prebuilt .so on the GPU box) the reference code must
+    reproduce its own fixtures bit for bit (same binary, same inputs)."""
+    from oracle import reference
+    if not reference.available():
+        pytest.skip("oracle/_ref not available")
+    g = golden
+    N, Nc = len(g["locs"]), len(g["coarse_locs"])
+    R = reference.Ref()
+    R.load_submanifold(4096, unpack(g["subm_flat"], g["subm_off"]), N)
+    R.load_strided(4096, 2048, unpack(g["strided_flat"], g["strided_off"]), N, Nc)
+    y, macs = R.subm_forward(4096, g["x"], g["w"])
+    assert rel_err(y, g["y"]) < 1e-6 and macs == float(g["macs"])
+    dx, dw = R.subm_backward(4096, g["x"], g["g"], g["w"])
+    assert rel_err(dx, g["dx"]) < 1e-6 and rel_err(dw, g["dw"]) < 1e-6
+    yc, _ = R.conv_forward(4096, 2048, g["x"], g["w8"])
+    assert rel_err(yc, g["yc"]) < 1e-6
+
+
+def test_identity_offset_known_answer():
+    """Known-answer test: a rulebook holding only the centre offset turns the convolution into x @ W[13]."""
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((50, 5)).astype(np.float32)
+    w = rng.standard_normal((27, 5, 7)).astype(np.float32)
+    rules = [np.zeros((0, 2), np.int32) for _ in range(27)]
+    rules[13] = np.stack([np.arange(50), np.arange(50)], 1).astype(np.int32)
+    y, macs = arith.rule_conv_forward(x, w, rules, 50)
+    assert np.allclose(y, x @ w[13], rtol=1e-6, atol=1e-6) and macs == 50 * 5 * 7
+
+
+def test_offset_convention_is_x_major():
+    """Two voxels differing by +1 in x only: the rule must land in offset (dx+1)*9+(0+1)*3+(0+1) (GPU builder
+    convention, SubmanifoldRules_cuda.cu:63-73), i.e. 22 for dx=+1 and 4 for dx=-1."""
+    locs = np.array([[10, 10, 10, 0], [11, 10, 10, 0]], np.int64)
+    rules = rb.submanifold_rules(locs, 1)
+    assert rules[22].tolist() == [[1, 0]] and rules[4].tolist() == [[0, 1]]
+    assert rules[13].tolist() == [[0, 0], [1, 1]]
+    assert sum(len(r) for r in rules) == 4
+    # +1 in z -> offset 14
+    locs = np.array([[10, 10, 10, 0], [10, 10, 11, 0]], np.int64)
+    assert rb.submanifold_rules(locs, 1)[14].tolist() == [[1, 0]]
+
+
+def test_voxelize_duplicates_order_and_batches():
+    coords = np.array([[5, 5, 5, 0], [4, 5, 5, 0], [5, 5, 5, 0], [5, 5, 4, 0], [5, 5, 5, 1], [5, 5, 5, 1]], np.int64)
+    v = rb.voxelize(coords, 2)
+    # sample 0 sorted by (z,y,x): (5,5,4) < (4,5,5) < (5,5,5); sample 1 continues the numbering
+    assert v["locs"].tolist() == [[5, 5, 4, 0], [4, 5, 5, 0], [5, 5, 5, 0], [5, 5, 5, 1]]
+    assert v["row_of_point"].tolist() == [2, 1, 2, 0, 3, 3]
+    assert v["max_repeat"] == 2 and v["sample_ctr"].tolist() == [0, 3, 4]
+    # points of row 2 keep their original order (stable sort)
+    assert v["rule_pts"][v["rule_ptr"][2]:v["rule_ptr"][3]].tolist() == [0, 2]
+    feats = np.arange(12, dtype=np.float32).reshape(6, 2)
+    mean = rb.input_layer_mean(feats, v, True)
+    assert np.allclose(mean[2], (feats[0] + feats[2]) / 2) and np.allclose(mean[3], (feats[4] + feats[5]) / 2)
+
+
+def test_no_rules_across_samples():
+    locs = np.array([[10, 10, 10, 0], [11, 10, 10, 1]], np.int64)
+    rules = rb.submanifold_rules(locs, 2)
+    assert sum(len(r) for r in rules) == 2 and len(rules[13]) == 2
+
+
+def test_empty_sample_in_batch():
+    coords = np.array([[3, 3, 3, 0], [4, 3, 3, 2]], np.int64)   # sample 1 is empty
+    v = rb.voxelize(coords, 3)
+    assert v["sample_ctr"].tolist() == [0, 1, 1, 2]
+    rules = rb.submanifold_rules(v["locs"], 3)
+    assert sum(len(r) for r in rules) == 2
+    clocs, strided = rb.strided_rules(v["locs"], 3)
+    assert clocs.tolist() == [[1, 1, 1, 0], [2, 1, 1, 2]]
+
+
+def test_strided_offsets_and_parent():
+    locs = np.array([[2, 2, 2, 0], [3, 2, 2, 0], [2, 3, 2, 0], [2, 2, 3, 0], [4, 2, 2, 0]], np.int64)
+    v = rb.voxelize(locs, 1)
+    clocs, rules = rb.strided_rules(v["locs"], 1)
+    assert clocs.tolist() == [[1, 1, 1, 0], [2, 1, 1, 0]]
+    got = {}
+    for k, r in enumerate(rules):
+        for i, o in r.tolist():
+            got[tuple(v["locs"][i, :3])] = (k, o)
+    assert got[(2, 2, 2)] == (0, 0) and got[(3, 2, 2)] == (4, 0) and got[(2, 3, 2)] == (2, 0)
+    assert got[(2, 2, 3)] == (1, 0) and got[(4, 2, 2)] == (0, 1)
+
+
+def test_key31_aliasing_is_reproduced():
+    """x=-1 wraps to an all-ones word exactly as on the device (never matches a voxel inside the valid range)."""
+    assert int(rb.key31(-1, 5, 5)) == 0x7FFFFFFF
+    assert int(rb.key31(3, 2, 1)) == (1 << 21) | (2 << 10) | 3
+
+
+def test_total_rules_symmetry():
+    """Property: the rule relation is symmetric -- list k reversed is list 26-k."""
+    from occuseg_b200 import scenes
+    c, _ = scenes.make_batch("tiny", (1, 2))
+    v = rb.voxelize(c, 2)
+    rules = rb.submanifold_rules(v["locs"], 2)
+    for k in range(27):
+        assert _canon_equal([rules[k][:, ::-1]], [rules[26 - k]])
