@@ -41,6 +41,12 @@ int scn_version(void);
 const char *scn_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t scn_launch_count(void);
+/* optional per-kernel-family timing with CUDA events on the launching stream (used by bench.py for the roofline
+ * line).  scn_profile(1) clears and starts, scn_profile_read fills out[kind*4 + {launches, milliseconds,
+ * algorithmic bytes, flops}] for kinds 0..n-1 and returns n; scn_profile_kind_name(kind) names them. */
+void scn_profile(int enable);
+int scn_profile_read(double *out, int max_kinds);
+const char *scn_profile_kind_name(int kind);
 
 /* ---- handle: replaces py `Metadata_3()` / ~Metadata (pybind.cpp:11-13) ------------------------ */
 scn_meta *scn_meta_create(int device);

@@ -18,6 +18,9 @@ PROTOTYPES = {
     "scn_version": (C.c_int, []),
     "scn_last_error": (C.c_char_p, []),
     "scn_launch_count": (C.c_int64, []),
+    "scn_profile": (None, [C.c_int]),
+    "scn_profile_read": (C.c_int, [C.POINTER(C.c_double), C.c_int]),
+    "scn_profile_kind_name": (C.c_char_p, [C.c_int]),
     "scn_meta_create": (_vp, [C.c_int]),
     "scn_meta_destroy": (None, [_vp]),
     "scn_input_layer_build": (C.c_int, [_vp, _i64p, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _i64p]),
@@ -84,3 +87,18 @@ def size3(v):
 
 def launch_count():
     return int(lib().scn_launch_count())
+
+
+def profile(enable):
+    lib().scn_profile(int(bool(enable)))
+
+
+def profile_read():
+    """{kind: dict(launches, ms, bytes, flops)} accumulated since profile(True)."""
+    buf = (C.c_double * 64)()
+    n = lib().scn_profile_read(buf, 16)
+    out = {}
+    for k in range(n):
+        name = lib().scn_profile_kind_name(k).decode()
+        out[name] = dict(launches=int(buf[4 * k]), ms=buf[4 * k + 1], bytes=buf[4 * k + 2], flops=buf[4 * k + 3])
+    return out

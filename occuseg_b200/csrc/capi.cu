@@ -21,6 +21,58 @@ int sm_count() {
   return n;
 }
 
+// ---- profiling ------------------------------------------------------------------------------------------
+struct ProfRec { int kind; cudaEvent_t e0, e1; double bytes, flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static double g_prof_acc[PK_COUNT][4];
+static cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+ProfScope::ProfScope(ProfKind kind, double bytes, double flops, cudaStream_t stream) : s(stream) {
+  if (!g_prof_on) return;
+  ProfRec r{(int)kind, prof_event(), prof_event(), bytes, flops};
+  cudaEventRecord(r.e0, s);
+  slot = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].e1, s);
+}
+static void prof_drain() {
+  for (ProfRec &r : g_prof) {
+    cudaEventSynchronize(r.e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    g_prof_acc[r.kind][0] += 1;
+    g_prof_acc[r.kind][1] += ms;
+    g_prof_acc[r.kind][2] += r.bytes;
+    g_prof_acc[r.kind][3] += r.flops;
+    g_event_pool.push_back(r.e0);
+    g_event_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+}
+void prof_enable(bool on) {
+  prof_drain();
+  if (on) for (auto &k : g_prof_acc) for (double &v : k) v = 0;
+  g_prof_on = on;
+}
+int prof_read(double *out, int max_kinds) {
+  prof_drain();
+  int n = max_kinds < PK_COUNT ? max_kinds : PK_COUNT;
+  for (int k = 0; k < n; ++k) for (int j = 0; j < 4; ++j) out[k * 4 + j] = g_prof_acc[k][j];
+  return n;
+}
+const char *prof_name(int kind) {
+  static const char *names[PK_COUNT] = {"rulebook", "conv_tc", "conv_fp32", "wgrad_tc", "wgrad_fp32", "bn", "io"};
+  return (kind >= 0 && kind < PK_COUNT) ? names[kind] : "";
+}
+
 static Level *need_level(Meta *m, const int64_t size[3], const char *what) {
   Level *L = find_level(m, size);
   if (!L) throw Error(std::string(what) + ": no such scale in this handle (size " + std::to_string(size[0]) + ")");
@@ -42,12 +94,19 @@ static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, 
     else transpose_weight(w, tmp.p, a.V, a.c_out, a.c_in, s);
     use = tmp.p;
   }
-  if (tcore) {
-    a.weight_nk = use;
-    conv_tc(a, s);
-  } else {
-    a.weight = use;
-    conv_simt(a, s);
+  // algorithmic work (gather/scatter model): R*Cin*s + N*Cout*s + 4*R + V*Cin*Cout*s
+  const double bytes = 4.0 * ((double)a.n_rules * a.c_in + (double)(a.scatter ? a.n_rules : a.n_rows) * a.c_out +
+                              (double)a.n_rules + (double)a.V * a.c_in * a.c_out);
+  const double flops = 2.0 * (double)a.n_rules * a.c_in * a.c_out;
+  {
+    ProfScope ps(tcore ? PK_CONV_TC : PK_CONV_FP32, bytes, flops, s);
+    if (tcore) {
+      a.weight_nk = use;
+      conv_tc(a, s);
+    } else {
+      a.weight = use;
+      conv_simt(a, s);
+    }
   }
   tmp.release(s);
 }
@@ -59,19 +118,23 @@ static void run_up(Level *F, Level *C, const float *in, const float *w, bool nat
                    int precision, cudaStream_t s) {
   ConvArgs g;
   g.in = in; g.out = out; g.tbl = F->up.p; g.tbl_stride = F->n_pad; g.n_rows = F->n; g.V = 8;
-  g.c_in = c_in; g.c_out = c_out;
+  g.c_in = c_in; g.c_out = c_out; g.n_rules = F->n;
   if (precision == SCN_TF32 && conv_tc_supported(g)) {
     run_conv(g, w, native_kn, precision, s);
     return;
   }
   ConvArgs a;
   a.in = in; a.out = out; a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8;
-  a.c_in = c_in; a.c_out = c_out; a.scatter = true;
+  a.c_in = c_in; a.c_out = c_out; a.scatter = true; a.n_rules = F->n;
   run_conv(a, w, native_kn, SCN_FP32, s);
 }
 
 static void run_wgrad(const WgradArgs &a, int precision, cudaStream_t s) {
-  if (precision == SCN_TF32 && wgrad_tc_supported(a)) wgrad_tc(a, s);
+  const bool tcore = precision == SCN_TF32 && wgrad_tc_supported(a);
+  // R*(Cin+Cout)*s + 8*R + V*Cin*Cout*4
+  const double bytes = 4.0 * ((double)a.n_rules * (a.c_a + a.c_b) + 2.0 * a.n_rules + (double)a.V * a.c_a * a.c_b);
+  ProfScope ps(tcore ? PK_WGRAD_TC : PK_WGRAD_FP32, bytes, 2.0 * (double)a.n_rules * a.c_a * a.c_b, s);
+  if (tcore) wgrad_tc(a, s);
   else wgrad_simt(a, s);
 }
 
@@ -105,6 +168,9 @@ extern "C" {
 int scn_version(void) { return 100; }
 const char *scn_last_error(void) { return t_last_error.c_str(); }
 int64_t scn_launch_count(void) { return (int64_t)g_launches.load(); }
+void scn_profile(int enable) { prof_enable(enable != 0); }
+int scn_profile_read(double *out, int max_kinds) { return prof_read(out, max_kinds); }
+const char *scn_profile_kind_name(int kind) { return prof_name(kind); }
 
 scn_meta *scn_meta_create(int device) {
   try {
@@ -220,7 +286,7 @@ int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   ensure_neighbour_table(&h->m, L, s);
   ConvArgs a;
   a.in = in; a.bias = bias; a.out = out;
-  a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_in; a.c_out = c_out;
+  a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_in; a.c_out = c_out; a.n_rules = L->n_rules;
   run_conv(a, weight, true, precision, s);
   if (macs) *macs = (double)L->n_rules * c_in * c_out;   // flops += nRules*ip*op, CPU/Convolution.cpp:134
   SCN_CATCH
@@ -237,11 +303,11 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   // for this product K = c_out and N = c_in, so the caller's [27][c_in][c_out] array reads as [V][N][K]
   ConvArgs a;
   a.in = d_out; a.out = d_in;
-  a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_out; a.c_out = c_in; a.mirror = true;
+  a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_out; a.c_out = c_in; a.mirror = true; a.n_rules = L->n_rules;
   run_conv(a, weight, false, precision, s);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = L->nbr.p; w.tbl_stride = L->n_pad; w.n_rows = L->n; w.V = 27;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules;
   run_wgrad(w, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, L->n, c_out, s);
   SCN_CATCH
@@ -258,7 +324,7 @@ int scn_conv_fwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   // out[p] = sum_k in[child[k][p]] * W[k]
   ConvArgs a;
   a.in = in; a.bias = bias; a.out = out;
-  a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_in; a.c_out = c_out;
+  a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_in; a.c_out = c_out; a.n_rules = F->n;
   run_conv(a, weight, true, precision, s);
   if (macs) *macs = (double)F->n * c_in * c_out;   // every fine row has exactly one rule
   SCN_CATCH
@@ -276,7 +342,7 @@ int scn_conv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   run_up(F, C, d_out, weight, false, d_in, c_out, c_in, precision, s);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = F->n;
   run_wgrad(w, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, C->n, c_out, s);
   SCN_CATCH
@@ -313,12 +379,12 @@ int scn_deconv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
   // dgrad: d_in[p] = sum_k d_out[child[k][p]] * W[k]^T
   ConvArgs a;
   a.in = d_out; a.out = d_in;
-  a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_out; a.c_out = c_in;
+  a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_out; a.c_out = c_in; a.n_rules = F->n;
   run_conv(a, weight, false, precision, s);
   // dW[k] = sum_p in[p]^T d_out[child[k][p]]
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = false;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = false; w.n_rules = F->n;
   run_wgrad(w, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, F->n, c_out, s);
   SCN_CATCH
@@ -329,6 +395,7 @@ int scn_bn_fwd(const float *in, float *out, float *save_mean, float *save_invstd
                float *running_var, const float *gamma, const float *beta, int64_t n, int C, float eps, float momentum,
                int train, float leakiness, void *stream) {
   SCN_TRY
+  ProfScope ps(PK_BN, 3.0 * 4.0 * (double)n * C, 0.0, (cudaStream_t)stream);
   bn_fwd(in, out, save_mean, save_invstd, running_mean, running_var, gamma, beta, n, C, eps, momentum, train != 0,
          leakiness, (cudaStream_t)stream);
   SCN_CATCH
@@ -338,6 +405,7 @@ int scn_bn_bwd(const float *in, const float *out, const float *d_out, const floa
                const float *gamma, float *d_in, float *d_gamma, float *d_beta, int64_t n, int C, float leakiness,
                void *stream) {
   SCN_TRY
+  ProfScope ps(PK_BN, 5.0 * 4.0 * (double)n * C, 0.0, (cudaStream_t)stream);
   bn_bwd(in, out, d_out, save_mean, save_invstd, gamma, d_in, d_gamma, d_beta, n, C, leakiness, (cudaStream_t)stream);
   SCN_CATCH
 }

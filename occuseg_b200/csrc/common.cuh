@@ -36,6 +36,18 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 int sm_count();
 
+// ---- optional per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline) ----
+enum ProfKind { PK_RULEBOOK = 0, PK_CONV_TC, PK_CONV_FP32, PK_WGRAD_TC, PK_WGRAD_FP32, PK_BN, PK_IO, PK_COUNT };
+struct ProfScope {   // no-op unless scn_profile(1) was called
+  int slot = -1;
+  cudaStream_t s;
+  ProfScope(ProfKind kind, double bytes, double flops, cudaStream_t stream);
+  ~ProfScope();
+};
+void prof_enable(bool on);
+int prof_read(double *out, int max_kinds);   // out[kind*4 + {launches, ms, bytes, flops}]
+const char *prof_name(int kind);
+
 // ---- stream-ordered device buffers -------------------------------------------------------------------
 template <typename T> struct DevBuf {
   T *p = nullptr;
@@ -130,6 +142,7 @@ struct ConvArgs {
   int n_rows = 0;                  // rows iterated (outputs for GATHER, inputs for SCATTER)
   int V = 27;
   int c_in = 0, c_out = 0;
+  long long n_rules = 0;           // live table entries (for the algorithmic-bytes model only)
   bool mirror = false;             // GATHER: use table row V-1-k for weight tap k (dgrad of a submanifold conv)
   bool scatter = false;
 };
@@ -152,6 +165,7 @@ struct WgradArgs {
   int n_rows = 0;
   int V = 27;
   int c_a = 0, c_b = 0;
+  long long n_rules = 0;
   bool table_on_a = true;
 };
 void wgrad_simt(const WgradArgs &a, cudaStream_t s);

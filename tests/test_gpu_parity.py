@@ -15,7 +15,7 @@ if have_cuda():
     import torch
     import occuseg_b200.sparseconvnet as scn
     from occuseg_b200.sparseconvnet import SCN
-    from occuseg_b200 import scenes
+    from occuseg_b200 import scenes, _lib
 from oracle import arith, rulebook as rb
 
 FP32_TOL = 1e-5
@@ -239,12 +239,19 @@ def test_submanifold_on_scene_vs_oracle(precision, cin, cout):
     scn.set_precision(precision)
     try:
         m, _ = build_meta(coords, 1)
+        _lib.profile(True)
         y, macs, dx, dw = _subm(m, cu(x), cu(w), cu(go))
     finally:
         scn.set_precision("tf32")
     y0, macs0 = arith.rule_conv_forward(x, w, rules, N)
     dx0, dw0 = arith.rule_conv_backward(x, go, w, rules)
     assert macs == macs0
+    prof = _lib.profile_read()
+    _lib.profile(False)
+    if precision == "tf32":      # the tcgen05 kernels really ran (forward + dgrad), no silent fp32 substitute
+        assert prof["conv_tc"]["launches"] >= 2 and prof["conv_fp32"]["launches"] == 0, prof
+    else:
+        assert prof["conv_tc"]["launches"] == 0 and prof["conv_fp32"]["launches"] >= 2, prof
     assert rel_err(y.cpu().numpy(), y0) < tol
     assert rel_err(dx.cpu().numpy(), dx0) < tol
     assert rel_err(dw.cpu().numpy(), dw0) < tol
