@@ -203,7 +203,7 @@ def run_ours(args):
         return float(ms.item())
 
     # ---- warm-up (also reveals the voxel count)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(args.warmup):
         step(coords_dev, feats_dev)
     torch.cuda.synchronize()
     with torch.no_grad():
@@ -275,7 +275,7 @@ def run_ours(args):
 
     line = {
         "metric": "UNet-m64 SubmConv fwd+bwd voxels/sec", "value": total_voxels * args.steps / (ms * 1e-3),
-        "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "tf32 (fp32 storage, fp32 accumulate)" if args.precision == "tf32" else "f32", "data": "synthetic",
         "config": {"workload": f"OccuSeg UNet m={args.m} (reps 1, residual, 6 levels) fwd+bwd+Adam, "

@@ -175,6 +175,18 @@ const char *scn_profile_kind_name(int kind) { return prof_name(kind); }
 scn_meta *scn_meta_create(int device) {
   try {
     SCN_CUDA(cudaSetDevice(device));
+    {
+      // keep freed blocks in the stream-ordered pool across synchronisation points; with the default
+      // threshold (0) every sync hands the memory back to the driver and the next batch pays for cudaMalloc
+      static bool pool_ready[64] = {};
+      if (device >= 0 && device < 64 && !pool_ready[device]) {
+        cudaMemPool_t pool;
+        SCN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ull;
+        SCN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_ready[device] = true;
+      }
+    }
     scn_meta *h = new scn_meta();
     h->m.device = device;
     return h;
@@ -307,7 +319,7 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   run_conv(a, weight, false, precision, s);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = L->nbr.p; w.tbl_stride = L->n_pad; w.n_rows = L->n; w.V = 27;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules; w.chunk_mask = L->nbr_cm.p;
   run_wgrad(w, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, L->n, c_out, s);
   SCN_CATCH
@@ -342,7 +354,7 @@ int scn_conv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   run_up(F, C, d_out, weight, false, d_in, c_out, c_in, precision, s);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = F->n;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = F->n; w.chunk_mask = F->child_cm.p;
   run_wgrad(w, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, C->n, c_out, s);
   SCN_CATCH
@@ -384,7 +396,7 @@ int scn_deconv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
   // dW[k] = sum_p in[p]^T d_out[child[k][p]]
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = false; w.n_rules = F->n;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = false; w.n_rules = F->n; w.chunk_mask = F->child_cm.p;
   run_wgrad(w, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, F->n, c_out, s);
   SCN_CATCH

@@ -91,11 +91,13 @@ struct Level {
   // submanifold 3x3x3 neighbour table (output-stationary form of the reference's 27 rule lists)
   DevBuf<int> nbr;           // [27][n_pad], -1 = absent
   long long n_rules = -1;    // sum_k n_k, centre offset included
+  DevBuf<uint32_t> nbr_cm;   // [n_pad/32] per 32-row chunk: bit k set when offset k has a rule in the chunk
   // size-2/stride-2 link to the next coarser scale
   Level *coarse = nullptr;
   DevBuf<int> parent;        // [n]   coarse row of every fine row
   DevBuf<uint8_t> off8;      // [n]   (x&1)*4+(y&1)*2+(z&1)
   DevBuf<int> child;         // [8][coarse->n_pad] fine row or -1
+  DevBuf<uint32_t> child_cm; // [coarse->n_pad/32] same for the child table
   DevBuf<int> up;            // [8][n_pad]  up[k][i] = parent[i] if off8[i]==k else -1 (one tap per fine row)
 };
 
@@ -166,6 +168,7 @@ struct WgradArgs {
   int V = 27;
   int c_a = 0, c_b = 0;
   long long n_rules = 0;
+  const uint32_t *chunk_mask = nullptr;  // [ceil(n_rows/32)] bit k: tap k has a rule inside the 32-row chunk
   bool table_on_a = true;
 };
 void wgrad_simt(const WgradArgs &a, cudaStream_t s);

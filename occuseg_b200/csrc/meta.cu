@@ -159,6 +159,19 @@ __global__ void k_neighbours(const uint64_t *__restrict__ keys, int n, int strid
   if (threadIdx.x == 0 && total) atomicAdd(n_rules, (unsigned long long)total);
 }
 
+// per 32-row chunk of a [V][stride] table: bit k <=> some row of the chunk has an entry at tap k
+__global__ void k_chunk_masks(const int *__restrict__ tbl, int stride, int V, int n_chunks, uint32_t *__restrict__ out) {
+  int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chunk >= n_chunks) return;
+  int lane = threadIdx.x & 31;
+  uint32_t m = 0;
+  for (int k = 0; k < V; ++k) {
+    int t = tbl[(long long)k * stride + chunk * 32 + lane];
+    if (__any_sync(0xffffffffu, t >= 0)) m |= 1u << k;
+  }
+  if (lane == 0) out[chunk] = m;
+}
+
 __global__ void k_fill_int(int *p, long long n, int v) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -316,6 +329,9 @@ void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
                                                      L->nbr.p, cnt.p);
     SCN_LAUNCH_CHECK();
   }
+  L->nbr_cm.alloc(L->n_pad / 32, s);
+  k_chunk_masks<<<grid_for(L->n_pad / 32, 8), 256, 0, s>>>(L->nbr.p, L->n_pad, 27, L->n_pad / 32, L->nbr_cm.p);
+  SCN_LAUNCH_CHECK();
   unsigned long long h = 0;
   SCN_CUDA(cudaMemcpyAsync(&h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, s));
   SCN_CUDA(cudaStreamSynchronize(s));   // once per scale per batch: the MAC count is part of the API
@@ -356,6 +372,9 @@ Level *ensure_coarse_level(Meta *m, Level *F, const int64_t coarse_size[3], cuda
   SCN_LAUNCH_CHECK();
   k_link_levels<<<grid_for(C->n, 256), 256, 0, s>>>(runs.ptr.p, runs.sorted_idx.p, F->keys.p, C->n, C->n_pad,
                                                     F->parent.p, F->off8.p, F->child.p, F->n_pad, F->up.p);
+  SCN_LAUNCH_CHECK();
+  F->child_cm.alloc(C->n_pad / 32, s);
+  k_chunk_masks<<<grid_for(C->n_pad / 32, 8), 256, 0, s>>>(F->child.p, C->n_pad, 8, C->n_pad / 32, F->child_cm.p);
   SCN_LAUNCH_CHECK();
   F->coarse = C;
   m->levels.push_back(C);

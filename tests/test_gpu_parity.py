@@ -250,8 +250,10 @@ def test_submanifold_on_scene_vs_oracle(precision, cin, cout):
     _lib.profile(False)
     if precision == "tf32":      # the tcgen05 kernels really ran (forward + dgrad), no silent fp32 substitute
         assert prof["conv_tc"]["launches"] >= 2 and prof["conv_fp32"]["launches"] == 0, prof
+        assert prof["wgrad_tc"]["launches"] >= 1 and prof["wgrad_fp32"]["launches"] == 0, prof
     else:
         assert prof["conv_tc"]["launches"] == 0 and prof["conv_fp32"]["launches"] >= 2, prof
+        assert prof["wgrad_tc"]["launches"] == 0 and prof["wgrad_fp32"]["launches"] >= 1, prof
     assert rel_err(y.cpu().numpy(), y0) < tol
     assert rel_err(dx.cpu().numpy(), dx0) < tol
     assert rel_err(dw.cpu().numpy(), dw0) < tol
