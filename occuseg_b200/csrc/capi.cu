@@ -3,6 +3,7 @@
 #include "../../include/scn_b200.h"
 #include "common.cuh"
 #include <mutex>
+#include <cstdlib>
 
 namespace scn {
 
@@ -82,8 +83,18 @@ static Level *need_level(Meta *m, const int64_t size[3], const char *what) {
 // `w` is the caller's weight array; native_kn says whether, for THIS product, it already reads as
 // [V][K=c_in][N=c_out] (true) or as [V][N][K] (false).  The fp32 kernels want KN, the tensor-core kernels
 // want NK (K-major B operand); whichever is missing is produced by one small per-tap transpose.
+static bool use_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SCN_TC_IMPL");
+    v = (e && std::string(e) == "cpasync") ? 0 : 1;
+  }
+  return v == 1;
+}
+static bool tc_ok(const ConvArgs &a) { return use_tma() ? conv_tma_supported(a) : conv_tc_supported(a); }
+
 static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, cudaStream_t s) {
-  const bool tcore = precision == SCN_TF32 && conv_tc_supported(a);
+  const bool tcore = precision == SCN_TF32 && tc_ok(a);
   const bool want_kn = !tcore;
   DevBuf<float> tmp;
   const float *use = w;
@@ -102,7 +113,8 @@ static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, 
     ProfScope ps(tcore ? PK_CONV_TC : PK_CONV_FP32, bytes, flops, s);
     if (tcore) {
       a.weight_nk = use;
-      conv_tc(a, s);
+      if (use_tma()) conv_tma(a, s);
+      else conv_tc(a, s);
     } else {
       a.weight = use;
       conv_simt(a, s);
@@ -118,8 +130,8 @@ static void run_up(Level *F, Level *C, const float *in, const float *w, bool nat
                    int precision, cudaStream_t s) {
   ConvArgs g;
   g.in = in; g.out = out; g.tbl = F->up.p; g.tbl_stride = F->n_pad; g.n_rows = F->n; g.V = 8;
-  g.c_in = c_in; g.c_out = c_out; g.n_rules = F->n;
-  if (precision == SCN_TF32 && conv_tc_supported(g)) {
+  g.c_in = c_in; g.c_out = c_out; g.n_rules = F->n; g.in_rows = C->n;
+  if (precision == SCN_TF32 && tc_ok(g)) {
     run_conv(g, w, native_kn, precision, s);
     return;
   }
@@ -130,11 +142,12 @@ static void run_up(Level *F, Level *C, const float *in, const float *w, bool nat
 }
 
 static void run_wgrad(const WgradArgs &a, int precision, cudaStream_t s) {
-  const bool tcore = precision == SCN_TF32 && wgrad_tc_supported(a);
+  const bool tcore = precision == SCN_TF32 && (use_tma() ? wgrad_tma_supported(a) : wgrad_tc_supported(a));
   // R*(Cin+Cout)*s + 8*R + V*Cin*Cout*4
   const double bytes = 4.0 * ((double)a.n_rules * (a.c_a + a.c_b) + 2.0 * a.n_rules + (double)a.V * a.c_a * a.c_b);
   ProfScope ps(tcore ? PK_WGRAD_TC : PK_WGRAD_FP32, bytes, 2.0 * (double)a.n_rules * a.c_a * a.c_b, s);
-  if (tcore) wgrad_tc(a, s);
+  if (tcore && use_tma()) wgrad_tma(a, s);
+  else if (tcore) wgrad_tc(a, s);
   else wgrad_simt(a, s);
 }
 
@@ -298,7 +311,7 @@ int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   ensure_neighbour_table(&h->m, L, s);
   ConvArgs a;
   a.in = in; a.bias = bias; a.out = out;
-  a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_in; a.c_out = c_out; a.n_rules = L->n_rules;
+  a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_in; a.c_out = c_out; a.n_rules = L->n_rules; a.in_rows = L->n;
   run_conv(a, weight, true, precision, s);
   if (macs) *macs = (double)L->n_rules * c_in * c_out;   // flops += nRules*ip*op, CPU/Convolution.cpp:134
   SCN_CATCH
@@ -315,11 +328,11 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   // for this product K = c_out and N = c_in, so the caller's [27][c_in][c_out] array reads as [V][N][K]
   ConvArgs a;
   a.in = d_out; a.out = d_in;
-  a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_out; a.c_out = c_in; a.mirror = true; a.n_rules = L->n_rules;
+  a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_out; a.c_out = c_in; a.mirror = true; a.n_rules = L->n_rules; a.in_rows = L->n;
   run_conv(a, weight, false, precision, s);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = L->nbr.p; w.tbl_stride = L->n_pad; w.n_rows = L->n; w.V = 27;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules; w.chunk_mask = L->nbr_cm.p;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules; w.chunk_mask = L->nbr_cm.p; w.g_rows = L->n;
   run_wgrad(w, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, L->n, c_out, s);
   SCN_CATCH
@@ -336,7 +349,7 @@ int scn_conv_fwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   // out[p] = sum_k in[child[k][p]] * W[k]
   ConvArgs a;
   a.in = in; a.bias = bias; a.out = out;
-  a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_in; a.c_out = c_out; a.n_rules = F->n;
+  a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_in; a.c_out = c_out; a.n_rules = F->n; a.in_rows = F->n;
   run_conv(a, weight, true, precision, s);
   if (macs) *macs = (double)F->n * c_in * c_out;   // every fine row has exactly one rule
   SCN_CATCH
@@ -354,7 +367,7 @@ int scn_conv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   run_up(F, C, d_out, weight, false, d_in, c_out, c_in, precision, s);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = F->n; w.chunk_mask = F->child_cm.p;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = F->n; w.chunk_mask = F->child_cm.p; w.g_rows = F->n;
   run_wgrad(w, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, C->n, c_out, s);
   SCN_CATCH
@@ -391,12 +404,12 @@ int scn_deconv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
   // dgrad: d_in[p] = sum_k d_out[child[k][p]] * W[k]^T
   ConvArgs a;
   a.in = d_out; a.out = d_in;
-  a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_out; a.c_out = c_in; a.n_rules = F->n;
+  a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_out; a.c_out = c_in; a.n_rules = F->n; a.in_rows = F->n;
   run_conv(a, weight, false, precision, s);
   // dW[k] = sum_p in[p]^T d_out[child[k][p]]
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = false; w.n_rules = F->n; w.chunk_mask = F->child_cm.p;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = false; w.n_rules = F->n; w.chunk_mask = F->child_cm.p; w.g_rows = F->n;
   run_wgrad(w, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, F->n, c_out, s);
   SCN_CATCH

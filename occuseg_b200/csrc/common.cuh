@@ -142,6 +142,7 @@ struct ConvArgs {
   const int *tbl = nullptr;
   int tbl_stride = 0;
   int n_rows = 0;                  // rows iterated (outputs for GATHER, inputs for SCATTER)
+  int in_rows = 0;                 // rows of the `in` matrix (TMA out-of-bounds index = zero row)
   int V = 27;
   int c_in = 0, c_out = 0;
   long long n_rules = 0;           // live table entries (for the algorithmic-bytes model only)
@@ -150,7 +151,9 @@ struct ConvArgs {
 };
 void conv_simt(const ConvArgs &a, cudaStream_t s);
 bool conv_tc_supported(const ConvArgs &a);
-void conv_tc(const ConvArgs &a, cudaStream_t s);
+void conv_tc(const ConvArgs &a, cudaStream_t s);       // cp.async producers (kept for A/B runs: SCN_TC_IMPL=cpasync)
+bool conv_tma_supported(const ConvArgs &a);
+void conv_tma(const ConvArgs &a, cudaStream_t s);      // TMA gather4 producers (default)
 
 // weight preparation: dst[k][co][ci] = src[k][ci][co]   (per-tap transpose, used by every dgrad)
 void transpose_weight(const float *src, float *dst, int V, int c_in, int c_out, cudaStream_t s);
@@ -165,6 +168,7 @@ struct WgradArgs {
   const int *tbl = nullptr;
   int tbl_stride = 0;
   int n_rows = 0;
+  int g_rows = 0;                  // rows of the gathered matrix (a when table_on_a, else b)
   int V = 27;
   int c_a = 0, c_b = 0;
   long long n_rules = 0;
@@ -174,6 +178,8 @@ struct WgradArgs {
 void wgrad_simt(const WgradArgs &a, cudaStream_t s);
 bool wgrad_tc_supported(const WgradArgs &a);
 void wgrad_tc(const WgradArgs &a, cudaStream_t s);
+bool wgrad_tma_supported(const WgradArgs &a);
+void wgrad_tma(const WgradArgs &a, cudaStream_t s);
 
 void bias_grad(const float *d_out, float *d_bias, long long n_rows, int C, cudaStream_t s);
 

@@ -15,6 +15,7 @@
 // Replaces the reference's scalar shared-memory FMA kernels (CUDA/Convolution.cu:1059-1152 forward,
 // :447-534 dgrad) for channel counts that are multiples of 32.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace scn {
 
@@ -326,6 +327,7 @@ struct Params {
   int tbl_stride, n_rows, V, Cg, Cs, transpose_out;
   int N, acc_per_cta, n_acc_total, rows_per_cta;
   int stages, lag, stage_bytes, tmem_cols;
+  int dbg;   // SCN_WG_DBG bit0: skip atomics, bit1: skip MMAs, bit2: skip gathered loads, bit3: skip stationary loads
 };
 
 // MN-major tf32 operands have exactly one legal shared-memory layout: SWIZZLE_128B_BASE32B (layout type 1).
@@ -426,6 +428,7 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tc(Params p) {
         mbar_wait(empty_bar + 8 * s, ((it / p.stages) & 1) ^ 1);
         const uint32_t st = base + s * p.stage_bytes;
         // gathered operand: 4 slots x 32 rows x 8 sixteen-byte pieces
+        if (!(p.dbg & 4))
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int q = i >> 1;
@@ -444,6 +447,7 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tc(Params p) {
           cp_async16(dst, g, src < 0 ? 0u : 16u);
         }
         // stationary operand: N/32 atoms x 32 rows x 8 pieces
+        if (!(p.dbg & 8))
         for (int q = tid; q < p.N * 8; q += NPROD) {
           const int atom = q >> 8, rem = q & 255, row = rem >> 3, cc = rem & 7;
           const bool live = r0 + row < r_end;
@@ -490,6 +494,7 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tc(Params p) {
       for (int c0 = 0; c0 < p.N; c0 += 32) {
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + jl * p.N + c0, v);
+        if (p.dbg & 1) continue;
         if (!p.transpose_out) {
           float *dst = p.dw + ((long long)tap * p.Cg + cg) * p.Cs + n0 + c0;
 #pragma unroll
@@ -516,6 +521,7 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tc(Params p) {
         const uint32_t st = base + s * p.stage_bytes;
         const uint64_t ad = make_desc_mn(st);
         const uint64_t bd = make_desc_mn(st + 4 * SUB);
+        if (!(p.dbg & 2))
 #pragma unroll
         for (int k = 0; k < KR / 8; ++k)     // K = 8 rows per tf32 MMA = one 1024-byte K group
           mma_tf32(tmem + jl * p.N, ad + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc,
@@ -582,6 +588,10 @@ void wgrad_tc(const WgradArgs &a, cudaStream_t s) {
   if (smem > configured) {
     SCN_CUDA(cudaFuncSetAttribute(wg::k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
+  }
+  {
+    const char *e = getenv("SCN_WG_DBG");
+    p.dbg = e ? atoi(e) : 0;
   }
   dim3 grid(row_splits, groups, n_tiles_n);
   wg::k_wgrad_tc<<<grid, tc::NTHREADS, smem, s>>>(p);
