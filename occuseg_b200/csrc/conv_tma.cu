@@ -329,6 +329,7 @@ struct WgParams {
   int tbl_stride, n_rows, g_rows, V, Cg, Cs, transpose_out;
   int N, acc_per_cta, n_acc_total, rows_per_cta;
   int g_stages, s_stages, s_stage, tmem_cols;
+  int dbg;   // SCN_WG_DBG: bit1 skip MMAs, bit2 skip gathers, bit3 skip stationary loads (timing experiments only)
 };
 
 __global__ void __launch_bounds__(NTHREADS) k_wgrad_tma(const __grid_constant__ CUtensorMap map_g,
@@ -358,6 +359,7 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tma(const __grid_constant__ 
   const int r_begin = blockIdx.x * p.rows_per_cta;
   const int r_end = min(r_begin + p.rows_per_cta, p.n_rows);
   const int n_chunks = (r_end - r_begin + KR - 1) / KR;
+#define CM(i) ((p.dbg & 64) ? 0xFFFFFFFFu : __ldg(&p.cmask[i]))
 
   if (tid == 0) {
     for (int s = 0; s < p.g_stages; ++s) {
@@ -395,15 +397,16 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tma(const __grid_constant__ 
     // =========================== control producer: stationary rows + transaction accounting =========
     if (elect_one()) {
       int it = 0, sc = 0;
-      uint32_t cm_next = __ldg(&p.cmask[r_begin >> 5]);
+      uint32_t cm_next = CM(r_begin >> 5);
       for (int c = 0; c < n_chunks; ++c) {
         const int r0 = r_begin + c * KR;
         const uint32_t cm = cm_next;
-        if (c + 1 < n_chunks) cm_next = __ldg(&p.cmask[(r0 + KR) >> 5]);
+        if (c + 1 < n_chunks) cm_next = CM((r0 + KR) >> 5);
         if (!(cm & cta_taps)) continue;
         const int cs = sc % p.s_stages;
         mbar_wait(s_empty + 8 * cs, ((sc / p.s_stages) & 1) ^ 1);
-        mbar_expect_tx(s_full + 8 * cs, (uint32_t)p.s_stage);
+        mbar_expect_tx(s_full + 8 * cs, (p.dbg & 8) ? 0u : (uint32_t)p.s_stage);
+        if (!(p.dbg & 8))
         for (int a = 0; a < p.N / 32; ++a)
           tma_tile_2d(s_base + cs * p.s_stage + a * SUB, &map_s, n0 + a * 32, r0, s_full + 8 * cs);
         ++sc;
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tma(const __grid_constant__ 
           if (!(cm & acc_tapmask(acc0 + jl))) continue;
           const int gs = it % p.g_stages;
           mbar_wait(g_empty + 8 * gs, ((it / p.g_stages) & 1) ^ 1);
-          mbar_expect_tx(g_full + 8 * gs, (uint32_t)G_STAGE);
+          mbar_expect_tx(g_full + 8 * gs, (p.dbg & 4) ? 0u : (uint32_t)G_STAGE);
           ++it;
         }
       }
@@ -422,10 +425,10 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tma(const __grid_constant__ 
       const uint32_t idesc = idesc_tf32(p.N, 1, 1);
       uint32_t started = 0;
       int it = 0, sc = 0;
-      uint32_t cm_next = __ldg(&p.cmask[r_begin >> 5]);
+      uint32_t cm_next = CM(r_begin >> 5);
       for (int c = 0; c < n_chunks; ++c) {
         const uint32_t cm = cm_next;
-        if (c + 1 < n_chunks) cm_next = __ldg(&p.cmask[(r_begin + (c + 1) * KR) >> 5]);
+        if (c + 1 < n_chunks) cm_next = CM((r_begin + (c + 1) * KR) >> 5);
         if (!(cm & cta_taps)) continue;
         const int cs = sc % p.s_stages;
         mbar_wait(s_full + 8 * cs, (sc / p.s_stages) & 1);
@@ -436,6 +439,7 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tma(const __grid_constant__ 
           mbar_wait(g_full + 8 * gs, (it / p.g_stages) & 1);
           tc_fence_after();
           const uint64_t ad = desc_mn32(g_base + gs * G_STAGE, SUB);
+          if (!(p.dbg & 2))
 #pragma unroll
           for (int k = 0; k < KR / 8; ++k)    // K = 8 rows per MMA = two 512-byte K groups of every atom
             mma_tf32(tmem + jl * p.N, ad + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc,
@@ -462,6 +466,7 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tma(const __grid_constant__ 
     auto stage_idx = [&](int c) {
       int *dst = my_idx + (c & 1) * (p.V * KR);
       const int r0 = r_begin + c * KR;
+      if (!(p.dbg & 16))
       for (int t = 0; t < n_taps_cta; ++t) {
         const int *src = p.tbl + (long long)(tap_lo + t) * p.tbl_stride + r0 + lane;   // table is padded to 128 rows
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + t * KR + lane)), "l"(src) : "memory");
@@ -470,12 +475,12 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tma(const __grid_constant__ 
     };
     stage_idx(0);
     const bool leader = elect_one();
-    uint32_t cm_next = __ldg(&p.cmask[r_begin >> 5]);
+    uint32_t cm_next = CM(r_begin >> 5);
     int it = 0;
     for (int c = 0; c < n_chunks; ++c) {
       const uint32_t cm = cm_next;
       if (c + 1 < n_chunks) {
-        cm_next = __ldg(&p.cmask[(r_begin + (c + 1) * KR) >> 5]);
+        cm_next = CM((r_begin + (c + 1) * KR) >> 5);
         stage_idx(c + 1);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
       } else {
@@ -487,7 +492,7 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tma(const __grid_constant__ 
         if (!(cm & acc_tapmask(acc0 + jl))) continue;
         const int gs = it % p.g_stages;
         ++it;
-        if (!leader) continue;
+        if (!leader || (p.dbg & 4)) continue;
         mbar_wait(g_empty + 8 * gs, (((it - 1) / p.g_stages) & 1) ^ 1);
         const int slot = 4 * (acc0 + jl) + pw;
         const uint32_t dst = g_base + gs * G_STAGE + pw * SUB;
@@ -517,12 +522,13 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tma(const __grid_constant__ 
     const int quarter = warp & 3;
     uint32_t started = 0;
     for (int c = 0; c < n_chunks; ++c) {
-      const uint32_t cm = __ldg(&p.cmask[(r_begin + c * KR) >> 5]);
+      const uint32_t cm = CM((r_begin + c * KR) >> 5);
       for (int jl = 0; jl < n_acc; ++jl)
         if (cm & acc_tapmask(acc0 + jl)) started |= 1u << jl;
     }
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    if (!(p.dbg & 32))
     for (int jl = 0; jl < n_acc; ++jl) {
       if (!(started & (1u << jl))) continue;
       const int slot = 4 * (acc0 + jl) + quarter;
@@ -636,6 +642,10 @@ void wgrad_tma(const WgradArgs &a, cudaStream_t s) {
   if (smem > configured) {
     SCN_CUDA(cudaFuncSetAttribute(k_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
+  }
+  {
+    const char *e = getenv("SCN_WG_DBG");
+    p.dbg = e ? atoi(e) : 0;
   }
   dim3 grid(row_splits, groups, n_tiles_n);
   k_wgrad_tma<<<grid, NTHREADS, smem, s>>>(mg, ms, p);
