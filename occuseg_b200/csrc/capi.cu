@@ -141,7 +141,11 @@ static void run_up(Level *F, Level *C, const float *in, const float *w, bool nat
   run_conv(a, w, native_kn, SCN_FP32, s);
 }
 
-static void run_wgrad(const WgradArgs &a, int precision, cudaStream_t s) {
+static void run_wgrad(WgradArgs a, PairList &pairs, int precision, cudaStream_t s) {
+  if (precision == SCN_TF32 && use_tma()) {
+    build_pair_list(pairs, a.tbl, a.V, a.tbl_stride, a.n_rules, s);
+    a.gi = pairs.gi.p; a.si = pairs.si.p; a.blk_item = pairs.blk_item.p; a.n_blk = pairs.n_blk; a.blk_rows = BLK_ROWS;
+  }
   const bool tcore = precision == SCN_TF32 && (use_tma() ? wgrad_tma_supported(a) : wgrad_tc_supported(a));
   // R*(Cin+Cout)*s + 8*R + V*Cin*Cout*4
   const double bytes = 4.0 * ((double)a.n_rules * (a.c_a + a.c_b) + 2.0 * a.n_rules + (double)a.V * a.c_a * a.c_b);
@@ -332,8 +336,8 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   run_conv(a, weight, false, precision, s);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = L->nbr.p; w.tbl_stride = L->n_pad; w.n_rows = L->n; w.V = 27;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules; w.chunk_mask = L->nbr_cm.p; w.g_rows = L->n;
-  run_wgrad(w, precision, s);
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules; w.chunk_mask = L->nbr_cm.p; w.g_rows = L->n; w.s_rows = L->n;
+  run_wgrad(w, L->nbr_pairs, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, L->n, c_out, s);
   SCN_CATCH
 }
@@ -367,8 +371,8 @@ int scn_conv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   run_up(F, C, d_out, weight, false, d_in, c_out, c_in, precision, s);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = F->n; w.chunk_mask = F->child_cm.p; w.g_rows = F->n;
-  run_wgrad(w, precision, s);
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = F->n; w.chunk_mask = F->child_cm.p; w.g_rows = F->n; w.s_rows = C->n;
+  run_wgrad(w, F->child_pairs, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, C->n, c_out, s);
   SCN_CATCH
 }
@@ -409,8 +413,8 @@ int scn_deconv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
   // dW[k] = sum_p in[p]^T d_out[child[k][p]]
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = false; w.n_rules = F->n; w.chunk_mask = F->child_cm.p; w.g_rows = F->n;
-  run_wgrad(w, precision, s);
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = false; w.n_rules = F->n; w.chunk_mask = F->child_cm.p; w.g_rows = F->n; w.s_rows = C->n;
+  run_wgrad(w, F->child_pairs, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, F->n, c_out, s);
   SCN_CATCH
 }

@@ -78,6 +78,20 @@ __host__ __device__ inline uint64_t make_key(uint32_t b, uint32_t z, uint32_t y,
 constexpr int COORD_LIMIT = 65535;          // exclusive upper bound on coordinates and batch index
 constexpr uint64_t EMPTY_KEY = ~0ull;       // never a valid key (batch 65535 is rejected)
 
+// ---- per-tap compacted rule lists of a [V][stride] table: the reference's rulebook (27 lists of (in,out) pairs
+// ordered by out, SubmanifoldRules_cuda.cpp:167-187) in device memory, each list padded to a multiple of 32
+// rules with an out-of-range index.  gi = table entry (gathered row), si = table column (stationary row).
+constexpr int PAIR_PAD = 0x7F7F7F7F;
+struct PairList {
+  DevBuf<int> gi, si;        // [32 * n_items_ub]
+  DevBuf<int> item_off;      // [V+1] first 32-rule item of every tap; item_off[V] = number of items
+  DevBuf<int> blk_item;      // [V][n_blk+1] item holding tap k's first rule whose column is >= b*BLK_ROWS
+  int n_blk = 0;
+  long long n_items_ub = 0;  // host-side upper bound of item_off[V]
+};
+constexpr int BLK_ROWS = 512;
+void build_pair_list(PairList &out, const int *tbl, int V, int stride, long long n_rules, cudaStream_t s);
+
 // ---- one scale of one batch -------------------------------------------------------------------------
 struct Level {
   int64_t size[3] = {0, 0, 0};
@@ -92,12 +106,14 @@ struct Level {
   DevBuf<int> nbr;           // [27][n_pad], -1 = absent
   long long n_rules = -1;    // sum_k n_k, centre offset included
   DevBuf<uint32_t> nbr_cm;   // [n_pad/32] per 32-row chunk: bit k set when offset k has a rule in the chunk
+  PairList nbr_pairs;        // the same rules as 27 compacted (in, out) lists, built on first weight-gradient use
   // size-2/stride-2 link to the next coarser scale
   Level *coarse = nullptr;
   DevBuf<int> parent;        // [n]   coarse row of every fine row
   DevBuf<uint8_t> off8;      // [n]   (x&1)*4+(y&1)*2+(z&1)
   DevBuf<int> child;         // [8][coarse->n_pad] fine row or -1
   DevBuf<uint32_t> child_cm; // [coarse->n_pad/32] same for the child table
+  PairList child_pairs;      // 8 compacted (fine, coarse) lists
   DevBuf<int> up;            // [8][n_pad]  up[k][i] = parent[i] if off8[i]==k else -1 (one tap per fine row)
 };
 
@@ -172,7 +188,11 @@ struct WgradArgs {
   int V = 27;
   int c_a = 0, c_b = 0;
   long long n_rules = 0;
-  const uint32_t *chunk_mask = nullptr;  // [ceil(n_rows/32)] bit k: tap k has a rule inside the 32-row chunk
+  int s_rows = 0;                  // rows of the other ("stationary") matrix
+  const uint32_t *chunk_mask = nullptr;  // [ceil(n_rows/32)] bit k: tap k has a rule inside the 32-row chunk (cp.async variant)
+  // compacted rule lists (TMA variant): see PairList
+  const int *gi = nullptr, *si = nullptr, *blk_item = nullptr;
+  int n_blk = 0, blk_rows = 0;
   bool table_on_a = true;
 };
 void wgrad_simt(const WgradArgs &a, cudaStream_t s);

@@ -6,13 +6,24 @@
 //     rows (128 bytes each) of the feature matrix into four consecutive swizzled shared-memory rows; an
 //     absent neighbour is requested as the out-of-bounds row index `rows`, which TMA zero-fills;
 //   * weights / stationary rows: ordinary 2-D tile loads.
-// A producer warp issues the copies (each lane one gather4), completion is counted in bytes on an
-// mbarrier (expect_tx), the MMA thread consumes the stage and frees it with tcgen05.commit.  No LSU
-// traffic, no per-thread fences, no 128-way barrier arrivals: the hand-off that dominated the cp.async
-// version (profiles/r01_notes.md) is one arrive + one wait per stage.
+// Completion is counted in bytes on an mbarrier (expect_tx); the MMA thread consumes the stage and frees it
+// with tcgen05.commit.
+//
+// What the micro-benchmarks (tools/ubench_pipe.cu, profiles/r01_ubench.md) say about this machine, and what the
+// kernels do about it:
+//   * one thread issues a gather4 every ~28 clk (58 with a dependent shared-memory load in between); the TMA
+//     engine itself keeps up with at least 8 issuing threads per SM (56 B/clk/SM).  So the copies of ONE pipeline
+//     item are issued by ONE elected thread with the indices already in registers, and consecutive items go to
+//     different producer warps (item-interleaved producers), which also post the item's byte count themselves;
+//   * a row index past the end of the tensor is zero-filled, but costs ~12-14 clk per row against 3.8 clk for a
+//     real row.  Neither kernel asks for such rows any more: the forward/dgrad kernel masks absent neighbours
+//     with tcgen05.mma's disable-output-lane operand (one bit per accumulator row) and does not fetch them at
+//     all; the weight-gradient kernel walks per-tap compacted rule lists, so every fetched row is a real rule;
+//   * a pipeline item costs ~300 clk of fixed hand-off per producer thread, so items are kept at >= 16 KB.
 #include "common.cuh"
 #include <cuda.h>
 #include <cstdlib>
+#include <cstdio>
 
 namespace scn {
 namespace tma {
@@ -53,7 +64,7 @@ static CUtensorMap make_map(const float *base, uint64_t cols, uint64_t rows, uin
 constexpr int TM = 128;
 constexpr int KCH = 32;
 constexpr int A_STAGE = TM * 128;
-constexpr int NTHREADS = 192;     // warp 0 producer, warp 1 MMA + TMEM owner, warps 2-5 epilogue (TMEM quarter = warp & 3)
+constexpr int NTHREADS = 160;     // warp 0: TMEM owner + MMA issuer; warps 1-4: table set-up, TMA producers, epilogue (TMEM quarter = warp & 3)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -127,6 +138,20 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// same, with the disable-output-lane vector: bit i of m[j] set => accumulator row 32*j+i is NOT updated
+__device__ __forceinline__ void mma_tf32_masked(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accum, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -143,6 +168,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// zero 32 consecutive columns of this warp's 32 TMEM lanes
+__device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v4(float *dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols));
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -152,15 +190,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 }
 
 // =====================================================================================================
-// forward / dgrad:  out[o,:] = sum_k in[tbl[k][o],:] * W[k]
+// forward / dgrad:  out[o,:] = sum_k in[tbl[k][o],:] * W[k]          (output stationary, 128 rows x TN per CTA)
 // =====================================================================================================
 struct ConvParams {
+  const float *in;
   const float *bias;
   float *out;
   const int *tbl;
   int tbl_stride, n_rows, in_rows, V, c_in, c_out, mirror;
-  int TN, stages, b_stage, tmem_cols;
+  int TN, stages, nprod, b_stage, tmem_cols, prefetch;
+  long long *trace;     // SCN_TRACE=1: per-CTA clock64 breakdown of sampled tiles (debug only)
 };
+#define TRACE_ON (p.trace != nullptr && (blockIdx.x & 127) == 5 && blockIdx.y == 0)
+#define TRACE_PUT(i, v) do { if (TRACE_ON) p.trace[(blockIdx.x >> 7) * 16 + (i)] = (v); } while (0)
 
 __global__ void __launch_bounds__(NTHREADS) k_conv_tma(const __grid_constant__ CUtensorMap map_x,
                                                        const __grid_constant__ CUtensorMap map_w, ConvParams p) {
@@ -170,12 +212,14 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tma(const __grid_constant__ C
   uint8_t *smem = smem_raw + (base - raw);
   const uint32_t a_base = base;
   const uint32_t b_base = base + p.stages * A_STAGE;
-  int *s_idx = reinterpret_cast<int *>(smem + p.stages * (A_STAGE + p.b_stage));
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_idx + p.V * TM);
+  int *s_idx = reinterpret_cast<int *>(smem + p.stages * (A_STAGE + p.b_stage));     // [V][TM] row to fetch
+  uint32_t *s_pm = reinterpret_cast<uint32_t *>(s_idx + p.V * TM);                    // [V][4] present-row bits
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_pm + p.V * 4);
   const uint32_t full_bar = smem_u32(bars);
   const uint32_t empty_bar = full_bar + 8 * p.stages;
   const uint32_t accum_bar = empty_bar + 8 * p.stages;
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 1);
+  const uint32_t zero_bar = accum_bar + 8;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 2);
   uint32_t *s_mask = s_tmem + 1;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -183,6 +227,7 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tma(const __grid_constant__ C
   const int row0 = blockIdx.x * TM;
   const int n0 = blockIdx.y * p.TN;
   const int KC = p.c_in / KCH;
+  const long long t_entry = clock64();
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -190,23 +235,44 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tma(const __grid_constant__ C
       mbar_init(empty_bar + 8 * s, 1);
     }
     mbar_init(accum_bar, 1);
+    mbar_init(zero_bar, 4);
     *s_mask = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
-  } else if (warp >= 2) {
-    // neighbour rows of this tile for every tap (absent -> the out-of-bounds row TMA zero-fills) + tap mask
-    const int e = tid - 64;
+  } else {
+    // Rows to fetch for every tap.  An absent neighbour is never used by the MMA (its accumulator row is
+    // masked), so it is not fetched either: inside a 4-row gather group that has at least one present row the
+    // absent ones repeat a present row of the group (a cache hit), and groups with no present row are skipped.
+    const int e = tid - 32;
     const int r = row0 + e;
+    const int pw = warp - 1;
+    const int gsh = lane & ~3;
     uint32_t mine = 0;
-    for (int k = 0; k < p.V; ++k) {
-      int t = (r < p.n_rows) ? __ldg(&p.tbl[(long long)k * p.tbl_stride + r]) : -1;
-      s_idx[k * TM + e] = t < 0 ? p.in_rows : t;
-      mine |= (t >= 0 ? 1u : 0u) << k;
+    // all V table entries of this row first (independent loads, one memory latency), then the warp votes
+    int tv[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+      tv[k] = (k < p.V && r < p.n_rows) ? __ldg(&p.tbl[(long long)k * p.tbl_stride + r]) : -1;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (k < p.V) {
+        const int t = tv[k];
+        const uint32_t pm = __ballot_sync(0xffffffffu, t >= 0);
+        const uint32_t gm = (pm >> gsh) & 0xFu;
+        const int src = gsh + (gm ? __ffs(gm) - 1 : 0);
+        const int trep = __shfl_sync(0xffffffffu, t, src);
+        s_idx[k * TM + e] = t >= 0 ? t : (gm ? trep : 0);
+        if (lane == 0) s_pm[k * 4 + pw] = pm;
+        mine |= (pm ? 1u : 0u) << k;
+        if (t >= 0 && p.prefetch) {
+          const char *row = reinterpret_cast<const char *>(p.in + (long long)t * p.c_in);
+          for (int b = 0; b < p.c_in * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
+        }
+      }
     }
-    mine = __reduce_or_sync(0xffffffffu, mine);
     if (lane == 0 && mine) atomicOr(s_mask, mine);
   }
   tc_fence_before();
@@ -214,78 +280,108 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tma(const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
   const uint32_t tapmask = *s_mask;
-  const int n_items = __popc(tapmask) * KC;
+  if (tid == 0) { TRACE_PUT(0, t_entry); TRACE_PUT(1, clock64() - t_entry); TRACE_PUT(8, (long long)__popc(tapmask) * KC); }
 
   if (warp == 0) {
-    // =========================== weight producer + transaction accounting ===========================
+    // =========================== MMA issuer ===========================
     if (elect_one()) {
+      long long w_full = 0;
+      const uint32_t idesc = idesc_tf32(p.TN, 0, 0);
+      mbar_wait(zero_bar, 0);          // the accumulator starts as zeros (every MMA accumulates; rows can be masked from the first tap on)
+      tc_fence_after();
       uint32_t remaining = tapmask;
-      int it = 0;
-      const uint32_t stage_bytes = (uint32_t)(A_STAGE + p.b_stage);
+      int s = 0;
+      uint32_t ph = 0;
+      while (remaining) {
+        const int trow = __ffs(remaining) - 1;
+        remaining &= remaining - 1;
+        const uint4 pm = *reinterpret_cast<const uint4 *>(s_pm + trow * 4);
+        for (int kc = 0; kc < KC; ++kc) {
+          const long long tw = clock64();
+          mbar_wait(full_bar + 8 * s, ph);
+          w_full += clock64() - tw;
+          tc_fence_after();
+          const uint64_t ad = desc_k128(a_base + s * A_STAGE);
+          const uint64_t bd = desc_k128(b_base + s * p.b_stage);
+#pragma unroll
+          for (int k = 0; k < KCH / 8; ++k)
+            mma_tf32_masked(tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, 1u, ~pm.x, ~pm.y, ~pm.z, ~pm.w);
+          mma_commit(empty_bar + 8 * s);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+      mma_commit(accum_bar);
+      TRACE_PUT(2, w_full); TRACE_PUT(3, clock64() - t_entry);
+    }
+  } else {
+    const int quarter = warp & 3;                     // TMEM lanes 32*quarter .. +31 belong to this warp
+    const uint32_t tq = tmem + ((uint32_t)(quarter * 32) << 16);
+    for (int c0 = 0; c0 < p.TN; c0 += 32) tmem_zero32(tq + c0);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(zero_bar);
+    // =========================== TMA producers, item-interleaved ===========================
+    // Producer pw owns items pw, pw+nprod, ... (stages % nprod == 0, so a stage always belongs to the same
+    // producer): it waits for the stage, posts the byte count and issues the weight tile and all gather4 copies
+    // of the item from one thread with the row indices already in registers.
+    const int pw = warp - 1;
+    if (pw < p.nprod && elect_one()) {
+      uint32_t remaining = tapmask;
+      int s = -1, turn = -1;
+      long long w_empty = 0, t_issue = 0;
+      uint32_t ph = 1;                 // parity to wait for on the empty barrier (first pass: already free)
       while (remaining) {
         const int trow = __ffs(remaining) - 1;
         remaining &= remaining - 1;
         const int wtap = p.mirror ? p.V - 1 - trow : trow;
-        for (int kc = 0; kc < KC; ++kc, ++it) {
-          const int s = it % p.stages;
-          mbar_wait(empty_bar + 8 * s, ((it / p.stages) & 1) ^ 1);
-          mbar_expect_tx(full_bar + 8 * s, stage_bytes);
+        for (int kc = 0; kc < KC; ++kc) {
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+          if (++turn == p.nprod) turn = 0;
+          if (turn != pw) continue;
+          const uint4 pm = *reinterpret_cast<const uint4 *>(s_pm + trow * 4);
+          const uint32_t pmq[4] = {pm.x, pm.y, pm.z, pm.w};
+          uint32_t nz[4];
+          int groups = 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            nz[q] = (pmq[q] | (pmq[q] >> 1) | (pmq[q] >> 2) | (pmq[q] >> 3)) & 0x11111111u;
+            groups += __popc(nz[q]);
+          }
+          const long long tw = clock64();
+          mbar_wait(empty_bar + 8 * s, ph);
+          const long long ti = clock64();
+          w_empty += ti - tw;
+          mbar_expect_tx(full_bar + 8 * s, (uint32_t)(p.b_stage + groups * 512));
           tma_tile_2d(b_base + s * p.b_stage, &map_w, kc * KCH, wtap * p.c_out + n0, full_bar + 8 * s);
+          const uint32_t dst = a_base + s * A_STAGE;
+          const int4 *rows4 = reinterpret_cast<const int4 *>(s_idx + trow * TM);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (!nz[q]) continue;
+            int4 r[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) r[g] = rows4[q * 8 + g];
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              if ((nz[q] >> (4 * g)) & 1u)
+                tma_gather4(dst + (q * 8 + g) * 512, &map_x, kc * KCH, r[g].x, r[g].y, r[g].z, r[g].w, full_bar + 8 * s);
+          }
+          t_issue += clock64() - ti;
         }
       }
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (elect_one()) {
-      const uint32_t idesc = idesc_tf32(p.TN, 0, 0);
-      for (int it = 0; it < n_items; ++it) {
-        const int s = it % p.stages;
-        mbar_wait(full_bar + 8 * s, (it / p.stages) & 1);
-        tc_fence_after();
-        const uint64_t ad = desc_k128(a_base + s * A_STAGE);
-        const uint64_t bd = desc_k128(b_base + s * p.b_stage);
-#pragma unroll
-        for (int k = 0; k < KCH / 8; ++k)
-          mma_tf32(tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (it | k) ? 1u : 0u);
-        mma_commit(empty_bar + 8 * s);
-      }
-      mma_commit(accum_bar);
-    }
-  } else {
-    // =========================== gather producers (warps 2-5), then epilogue ===========================
-    // warp w issues the 8 gather4 copies of rows 32*(w-2) .. 32*(w-2)+31 of every stage from ONE elected
-    // thread with warp-uniform operands (indices are read from shared memory at uniform addresses), so each
-    // copy is a single UTMALDG instead of a per-lane vote loop.
-    const int pw = warp - 2;
-    if (elect_one()) {
-      uint32_t remaining = tapmask;
-      int it = 0;
-      while (remaining) {
-        const int trow = __ffs(remaining) - 1;
-        remaining &= remaining - 1;
-        const int4 *rows4 = reinterpret_cast<const int4 *>(s_idx + trow * TM + pw * 32);
-        int4 r[8];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) r[g] = rows4[g];
-        for (int kc = 0; kc < KC; ++kc, ++it) {
-          const int s = it % p.stages;
-          mbar_wait(empty_bar + 8 * s, ((it / p.stages) & 1) ^ 1);
-          const uint32_t dst = a_base + s * A_STAGE + pw * 4096;
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            tma_gather4(dst + g * 512, &map_x, kc * KCH, r[g].x, r[g].y, r[g].z, r[g].w, full_bar + 8 * s);
-        }
-      }
+      if (pw == 0) { TRACE_PUT(4, w_empty); TRACE_PUT(5, clock64() - t_entry); TRACE_PUT(9, t_issue); }
     }
     __syncwarp();
-    const int quarter = warp & 3;                     // TMEM lanes 32*quarter .. +31 belong to this warp
+    // =========================== epilogue ===========================
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    if (tid == 32) TRACE_PUT(6, clock64() - t_entry);
     const int r = row0 + quarter * 32 + lane;
     float *orow = p.out + (long long)r * p.c_out + n0;
     for (int c0 = 0; c0 < p.TN; c0 += 32) {
       float v[32];
-      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + c0, v);
+      tmem_ld32(tq + c0, v);
       if (r < p.n_rows) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -303,7 +399,8 @@ __global__ void __launch_bounds__(NTHREADS) k_conv_tma(const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (tid == 0) TRACE_PUT(7, clock64() - t_entry);
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
   }
@@ -316,243 +413,169 @@ static int pick_tn(int c_out) {
 }
 
 // =====================================================================================================
-// weight gradient:  D_k[Cg x Cs] = sum_r G[tbl[k][r],:]^T S[r,:]     (see conv_tc.cu for the slot scheme)
+// weight gradient over compacted rule lists:
+//   D_k[Cg x Cs] = sum over the rules (g, s) of tap k of  G[g,:]^T S[s,:]
+// The rules of tap k occupy items item_off[k] .. item_off[k+1]-1 of the lists gi/si (32 rules per item, ordered
+// by s, the last item of a tap padded with an out-of-range index that TMA zero-fills).  CTA (tap k, row range rr,
+// column tile) takes the items of tap k whose s falls in rows [rr*range, (rr+1)*range) -- blk_item holds the item
+// index of every 512-row boundary -- keeps D in TMEM (M = 128 channels of G per accumulator tile, N channels of S,
+// K = 32 rules per item) and adds it to dW with vector reductions at the end.  The tap index is the FASTEST grid
+// dimension: the 27 CTAs of one row range run together, so every G and S row is fetched from HBM about once and
+// re-read from L2 by the other taps (a flat split of the rule lists reads every row from HBM once per tap).
+// Both operands are MN-major (the contraction runs over rules = rows), which tcgen05 accepts for tf32 only in
+// the SWIZZLE_128B_BASE32B layout: 32-channel atoms of [32 rules][128 B], 4-rule groups 512 B apart.
 // =====================================================================================================
-constexpr int KR = 32;            // voxel rows (GEMM K) per pipeline item
-constexpr int SUB = KR * 128;     // bytes of one [KR rows x 32 channels] sub-tile
-constexpr int G_STAGE = 4 * SUB;  // four 32-channel slots = UMMA M of 128
+constexpr int KR = 32;            // rules (GEMM K) per pipeline item
+constexpr int SUB = KR * 128;     // bytes of one [KR rules x 32 channels] atom
+constexpr int WG_THREADS = 288;   // warp 0: TMEM + MMA; warps 1-4: producers; warps 5-8: epilogue (TMEM quarter = warp & 3)
 
 struct WgParams {
   float *dw;
-  const int *tbl;
-  const uint32_t *cmask;
-  int tbl_stride, n_rows, g_rows, V, Cg, Cs, transpose_out;
-  int N, acc_per_cta, n_acc_total, rows_per_cta;
-  int g_stages, s_stages, s_stage, tmem_cols;
-  int dbg;   // SCN_WG_DBG: bit1 skip MMAs, bit2 skip gathers, bit3 skip stationary loads (timing experiments only)
+  const int *gi, *si, *blk_item;
+  int V, Cg, Cs, transpose_out, n_blk, blk_per_range;
+  int N, m_tiles, stages, nprod, stage_bytes, tmem_cols;
 };
 
-__global__ void __launch_bounds__(NTHREADS) k_wgrad_tma(const __grid_constant__ CUtensorMap map_g,
-                                                        const __grid_constant__ CUtensorMap map_s, WgParams p) {
+__global__ void __launch_bounds__(WG_THREADS) k_wgrad_tma(const __grid_constant__ CUtensorMap map_g,
+                                                          const __grid_constant__ CUtensorMap map_s, WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (base - raw);
-  const uint32_t g_base = base;
-  const uint32_t s_base = base + p.g_stages * G_STAGE;
-  int *s_idx = reinterpret_cast<int *>(smem + p.g_stages * G_STAGE + p.s_stages * p.s_stage);   // [4 warps][2][V][KR]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_idx + 4 * 2 * p.V * KR);
-  const uint32_t g_full = smem_u32(bars);
-  const uint32_t g_empty = g_full + 8 * p.g_stages;
-  const uint32_t s_full = g_empty + 8 * p.g_stages;
-  const uint32_t s_empty = s_full + 8 * p.s_stages;
-  const uint32_t accum_bar = s_empty + 8 * p.s_stages;
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * p.g_stages + 2 * p.s_stages + 1);
+  int *s_pidx = reinterpret_cast<int *>(smem + p.stages * p.stage_bytes);     // [4 producers][64]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_pidx + 4 * 64);
+  const uint32_t full_bar = smem_u32(bars);
+  const uint32_t empty_bar = full_bar + 8 * p.stages;
+  const uint32_t accum_bar = empty_bar + 8 * p.stages;
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 1);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int spt = p.Cg >> 5;
-  const int n_slots = p.V * spt;
-  const int acc0 = blockIdx.y * p.acc_per_cta;
-  const int n_acc = min(p.acc_per_cta, p.n_acc_total - acc0);
+  const int g_atoms = p.Cg >> 5, s_atoms = p.N >> 5;
+  const int tap = blockIdx.x;
   const int n0 = blockIdx.z * p.N;
-  const int r_begin = blockIdx.x * p.rows_per_cta;
-  const int r_end = min(r_begin + p.rows_per_cta, p.n_rows);
-  const int n_chunks = (r_end - r_begin + KR - 1) / KR;
-#define CM(i) ((p.dbg & 64) ? 0xFFFFFFFFu : __ldg(&p.cmask[i]))
+  const int b0 = blockIdx.y * p.blk_per_range;
+  const int b1 = min(b0 + p.blk_per_range, p.n_blk);
+  const int ib = __ldg(&p.blk_item[tap * (p.n_blk + 1) + b0]);
+  const int ie = __ldg(&p.blk_item[tap * (p.n_blk + 1) + b1]);
+  if (ib >= ie) return;           // uniform: nothing of this tap in this row range
 
   if (tid == 0) {
-    for (int s = 0; s < p.g_stages; ++s) {
-      mbar_init(g_full + 8 * s, 1);
-      mbar_init(g_empty + 8 * s, 1);
-    }
-    for (int s = 0; s < p.s_stages; ++s) {
-      mbar_init(s_full + 8 * s, 1);
-      mbar_init(s_empty + 8 * s, 1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
     }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (warp == 1) tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
+  if (warp == 0) tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  // taps touched by accumulator ja (identical in every thread)
-  auto acc_tapmask = [&](int ja) -> uint32_t {
-    uint32_t m = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      int slot = 4 * ja + q;
-      if (slot < n_slots) m |= 1u << (slot / spt);
-    }
-    return m;
-  };
-  uint32_t cta_taps = 0;
-  for (int jl = 0; jl < n_acc; ++jl) cta_taps |= acc_tapmask(acc0 + jl);
-
   if (warp == 0) {
-    // =========================== control producer: stationary rows + transaction accounting =========
-    if (elect_one()) {
-      int it = 0, sc = 0;
-      uint32_t cm_next = CM(r_begin >> 5);
-      for (int c = 0; c < n_chunks; ++c) {
-        const int r0 = r_begin + c * KR;
-        const uint32_t cm = cm_next;
-        if (c + 1 < n_chunks) cm_next = CM((r0 + KR) >> 5);
-        if (!(cm & cta_taps)) continue;
-        const int cs = sc % p.s_stages;
-        mbar_wait(s_empty + 8 * cs, ((sc / p.s_stages) & 1) ^ 1);
-        mbar_expect_tx(s_full + 8 * cs, (p.dbg & 8) ? 0u : (uint32_t)p.s_stage);
-        if (!(p.dbg & 8))
-        for (int a = 0; a < p.N / 32; ++a)
-          tma_tile_2d(s_base + cs * p.s_stage + a * SUB, &map_s, n0 + a * 32, r0, s_full + 8 * cs);
-        ++sc;
-        for (int jl = 0; jl < n_acc; ++jl) {
-          if (!(cm & acc_tapmask(acc0 + jl))) continue;
-          const int gs = it % p.g_stages;
-          mbar_wait(g_empty + 8 * gs, ((it / p.g_stages) & 1) ^ 1);
-          mbar_expect_tx(g_full + 8 * gs, (p.dbg & 4) ? 0u : (uint32_t)G_STAGE);
-          ++it;
-        }
-      }
-    }
-  } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
       const uint32_t idesc = idesc_tf32(p.N, 1, 1);
-      uint32_t started = 0;
-      int it = 0, sc = 0;
-      uint32_t cm_next = CM(r_begin >> 5);
-      for (int c = 0; c < n_chunks; ++c) {
-        const uint32_t cm = cm_next;
-        if (c + 1 < n_chunks) cm_next = CM((r_begin + (c + 1) * KR) >> 5);
-        if (!(cm & cta_taps)) continue;
-        const int cs = sc % p.s_stages;
-        mbar_wait(s_full + 8 * cs, (sc / p.s_stages) & 1);
-        const uint64_t bd = desc_mn32(s_base + cs * p.s_stage, SUB);
-        for (int jl = 0; jl < n_acc; ++jl) {
-          if (!(cm & acc_tapmask(acc0 + jl))) continue;
-          const int gs = it % p.g_stages;
-          mbar_wait(g_full + 8 * gs, (it / p.g_stages) & 1);
-          tc_fence_after();
-          const uint64_t ad = desc_mn32(g_base + gs * G_STAGE, SUB);
-          if (!(p.dbg & 2))
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = ib; item < ie; ++item) {
+        mbar_wait(full_bar + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t st = base + s * p.stage_bytes;
+        const uint64_t bd = desc_mn32(st + g_atoms * SUB, SUB);
+        for (int mt = 0; mt < p.m_tiles; ++mt) {
+          const uint64_t ad = desc_mn32(st + mt * 4 * SUB, SUB);
 #pragma unroll
-          for (int k = 0; k < KR / 8; ++k)    // K = 8 rows per MMA = two 512-byte K groups of every atom
-            mma_tf32(tmem + jl * p.N, ad + (uint64_t)(k * 64), bd + (uint64_t)(k * 64), idesc,
-                     ((started >> jl) & 1u) | (k ? 1u : 0u));
-          started |= 1u << jl;
-          mma_commit(g_empty + 8 * gs);
-          ++it;
+          for (int kk = 0; kk < KR / 8; ++kk)    // K = 8 rules per MMA = two 512-byte K groups of every atom
+            mma_tf32(tmem + mt * p.N, ad + (uint64_t)(kk * 64), bd + (uint64_t)(kk * 64), idesc,
+                     (item > ib || kk) ? 1u : 0u);
         }
-        mma_commit(s_empty + 8 * cs);
-        ++sc;
+        mma_commit(empty_bar + 8 * s);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
       mma_commit(accum_bar);
     }
-  } else {
-    // =========================== gather producers (warps 2-5), then epilogue ===========================
-    // warp pw fills slot pw (32 channels of one tap) of every stage: 8 gather4 copies issued by one elected
-    // thread with uniform operands.  Each warp keeps its own double-buffered copy of the chunk's table
-    // entries, staged one chunk ahead with 4-byte cp.async, so no cross-warp synchronisation is needed.
-    const int pw = warp - 2;
-    const int tap_lo = (4 * acc0) / spt;
-    const int tap_hi = min(p.V - 1, (4 * (acc0 + n_acc) - 1) / spt);
-    const int n_taps_cta = tap_hi - tap_lo + 1;
-    int *my_idx = s_idx + pw * (2 * p.V * KR);
-    auto stage_idx = [&](int c) {
-      int *dst = my_idx + (c & 1) * (p.V * KR);
-      const int r0 = r_begin + c * KR;
-      if (!(p.dbg & 16))
-      for (int t = 0; t < n_taps_cta; ++t) {
-        const int *src = p.tbl + (long long)(tap_lo + t) * p.tbl_stride + r0 + lane;   // table is padded to 128 rows
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + t * KR + lane)), "l"(src) : "memory");
+  } else if (warp <= 4) {
+    // =========================== TMA producers, item-interleaved ===========================
+    // The whole warp prefetches the next item's 2 x 32 indices (two coalesced 128-byte loads) one item ahead;
+    // lane 0 waits for the stage, posts the byte count and issues the item's copies.
+    const int pw = warp - 1;
+    if (pw < p.nprod) {
+      int *my = s_pidx + pw * 64;
+      int it = ib + pw;
+      int s = pw;                       // stage of item `it` (stages % nprod == 0: a producer cycles over its own stages)
+      uint32_t ph = 1;
+      int g_next = 0, s_next = 0;
+      if (it < ie) {
+        g_next = __ldg(&p.gi[(long long)it * KR + lane]);
+        s_next = __ldg(&p.si[(long long)it * KR + lane]);
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    stage_idx(0);
-    const bool leader = elect_one();
-    uint32_t cm_next = CM(r_begin >> 5);
-    int it = 0;
-    for (int c = 0; c < n_chunks; ++c) {
-      const uint32_t cm = cm_next;
-      if (c + 1 < n_chunks) {
-        cm_next = CM((r_begin + (c + 1) * KR) >> 5);
-        stage_idx(c + 1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
-      __syncwarp();
-      const int *idx = my_idx + (c & 1) * (p.V * KR);
-      for (int jl = 0; jl < n_acc; ++jl) {
-        if (!(cm & acc_tapmask(acc0 + jl))) continue;
-        const int gs = it % p.g_stages;
-        ++it;
-        if (!leader || (p.dbg & 4)) continue;
-        mbar_wait(g_empty + 8 * gs, (((it - 1) / p.g_stages) & 1) ^ 1);
-        const int slot = 4 * (acc0 + jl) + pw;
-        const uint32_t dst = g_base + gs * G_STAGE + pw * SUB;
-        if (slot < n_slots) {
-          const int tap = slot / spt;
-          const int ch = (slot - tap * spt) << 5;
-          const int4 *rows4 = reinterpret_cast<const int4 *>(idx + (tap - tap_lo) * KR);
+      for (; it < ie; it += p.nprod) {
+        my[lane] = g_next;
+        my[32 + lane] = s_next;
+        if (it + p.nprod < ie) {
+          g_next = __ldg(&p.gi[(long long)(it + p.nprod) * KR + lane]);
+          s_next = __ldg(&p.si[(long long)(it + p.nprod) * KR + lane]);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          int4 rg[8], rs[8];
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            int4 r = rows4[g];
-            r.x = r.x < 0 ? p.g_rows : r.x;
-            r.y = r.y < 0 ? p.g_rows : r.y;
-            r.z = r.z < 0 ? p.g_rows : r.z;
-            r.w = r.w < 0 ? p.g_rows : r.w;
-            tma_gather4(dst + g * 512, &map_g, ch, r.x, r.y, r.z, r.w, g_full + 8 * gs);
+            rg[g] = reinterpret_cast<const int4 *>(my)[g];
+            rs[g] = reinterpret_cast<const int4 *>(my + 32)[g];
           }
-        } else {
+          mbar_wait(empty_bar + 8 * s, ph);
+          mbar_expect_tx(full_bar + 8 * s, (uint32_t)p.stage_bytes);
+          const uint32_t dst = base + s * p.stage_bytes;
+          for (int a = 0; a < g_atoms; ++a) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g)   // slot past the last tap: all rows out of bounds -> zeros
-            tma_gather4(dst + g * 512, &map_g, 0, p.g_rows, p.g_rows, p.g_rows, p.g_rows, g_full + 8 * gs);
+            for (int g = 0; g < 8; ++g)
+              tma_gather4(dst + a * SUB + g * 512, &map_g, a * 32, rg[g].x, rg[g].y, rg[g].z, rg[g].w, full_bar + 8 * s);
+          }
+          for (int a = 0; a < s_atoms; ++a) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              tma_gather4(dst + (g_atoms + a) * SUB + g * 512, &map_s, n0 + a * 32, rs[g].x, rs[g].y, rs[g].z, rs[g].w,
+                          full_bar + 8 * s);
+          }
         }
+        s += p.nprod;
+        if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
+        __syncwarp();
       }
-      // the other lanes must not start staging chunk c+2 into this buffer while the leader still reads it
-      __syncwarp();
     }
-    // ---- epilogue: TMEM -> fp32 atomics into dW
+  } else {
+    // =========================== epilogue: TMEM -> fp32 reductions into dW ===========================
     const int quarter = warp & 3;
-    uint32_t started = 0;
-    for (int c = 0; c < n_chunks; ++c) {
-      const uint32_t cm = CM((r_begin + c * KR) >> 5);
-      for (int jl = 0; jl < n_acc; ++jl)
-        if (cm & acc_tapmask(acc0 + jl)) started |= 1u << jl;
-    }
     mbar_wait(accum_bar, 0);
     tc_fence_after();
-    if (!(p.dbg & 32))
-    for (int jl = 0; jl < n_acc; ++jl) {
-      if (!(started & (1u << jl))) continue;
-      const int slot = 4 * (acc0 + jl) + quarter;
-      if (slot >= n_slots) continue;
-      const int tap = slot / spt;
-      const int cg = ((slot - tap * spt) << 5) + lane;
+    const uint32_t acc = tmem + ((uint32_t)(quarter * 32) << 16);
+    for (int mt = 0; mt < p.m_tiles; ++mt) {
+      const int cg = mt * 128 + quarter * 32 + lane;
       for (int c0 = 0; c0 < p.N; c0 += 32) {
         float v[32];
-        tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + jl * p.N + c0, v);
-        if (!p.transpose_out) {
-          float *dst = p.dw + ((long long)tap * p.Cg + cg) * p.Cs + n0 + c0;
+        tmem_ld32(acc + mt * p.N + c0, v);
+        if (cg < p.Cg) {
+          if (!p.transpose_out) {
+            float *dst = p.dw + ((long long)tap * p.Cg + cg) * p.Cs + n0 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
-        } else {
-          float *dst = p.dw + ((long long)tap * p.Cs + n0 + c0) * p.Cg + cg;
+            for (int q = 0; q < 32; q += 4) red_add_v4(dst + q, v[q], v[q + 1], v[q + 2], v[q + 3]);
+          } else {
+            float *dst = p.dw + ((long long)tap * p.Cs + n0 + c0) * p.Cg + cg;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + (long long)j * p.Cg, v[j]);
+            for (int q = 0; q < 32; ++q) atomicAdd(dst + (long long)q * p.Cg, v[q]);
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
   }
@@ -561,6 +584,11 @@ __global__ void __launch_bounds__(NTHREADS) k_wgrad_tma(const __grid_constant__ 
 }  // namespace tma
 
 // ------------------------------------------------------------------------------------------ host launchers
+static int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 bool conv_tma_supported(const ConvArgs &a) {
   return !a.scatter && a.c_in >= 32 && a.c_in % 32 == 0 && a.c_out >= 32 && a.c_out % 32 == 0 && a.V <= 32 &&
          tma::pick_tn(a.c_out) > 0 && a.in_rows > 0 && ((uintptr_t)a.in % 16 == 0) && ((uintptr_t)a.out % 16 == 0);
@@ -571,15 +599,22 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   SCN_CHECK(a.weight_nk != nullptr, "conv_tma needs the [V][Cout][Cin] weight layout");
   if (a.n_rows == 0) return;
   ConvParams p;
-  p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
+  static const int prefetch = env_int("SCN_CONV_PREFETCH", 1);
+  p.prefetch = prefetch;
+  p.in = a.in; p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
   p.in_rows = a.in_rows; p.V = a.V; p.c_in = a.c_in; p.c_out = a.c_out; p.mirror = a.mirror ? 1 : 0;
   p.TN = pick_tn(a.c_out);
   p.b_stage = p.TN * 128;
   const int stage = A_STAGE + p.b_stage;
-  const int fixed = 1024 + a.V * TM * (int)sizeof(int) + 256;
-  p.stages = (112 * 1024 - fixed) / stage;         // two CTAs per SM
-  if (p.stages > 6) p.stages = 6;
-  if (p.stages < 2) p.stages = 2;
+  const int fixed = 1024 + a.V * TM * (int)sizeof(int) + a.V * 16 + 8 * (2 * 8 + 2) + 64;
+  // two CTAs per SM (one's epilogue and table set-up overlap the other's main loop) when that leaves >= 3 stages
+  static const int force_ctas = env_int("SCN_CONV_CTAS", 0);
+  int budget = 113 * 1024;
+  if (force_ctas == 1 || (force_ctas == 0 && (budget - fixed) / stage < 3)) budget = 225 * 1024;
+  int st = (budget - fixed) / stage;
+  st = st >= 8 ? 8 : st >= 6 ? 6 : st >= 4 ? 4 : st >= 3 ? 3 : 2;
+  p.stages = st;
+  p.nprod = st % 4 == 0 ? 4 : st % 3 == 0 ? 3 : 2;
   p.tmem_cols = 32;
   while (p.tmem_cols < p.TN) p.tmem_cols <<= 1;
   const size_t smem = (size_t)fixed + (size_t)p.stages * stage;
@@ -592,63 +627,81 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
     configured = smem;
   }
   dim3 grid((a.n_rows + TM - 1) / TM, a.c_out / p.TN);
+  static const int trace = env_int("SCN_TRACE", 0);
+  p.trace = nullptr;
+  const int n_tr = (int)(grid.x >> 7);
+  if (trace && n_tr > 0) {
+    SCN_CUDA(cudaMalloc((void **)&p.trace, sizeof(long long) * 16 * (n_tr + 1)));
+    SCN_CUDA(cudaMemset(p.trace, 0, sizeof(long long) * 16 * (n_tr + 1)));
+  }
   k_conv_tma<<<grid, NTHREADS, smem, s>>>(mx, mw, p);
   SCN_LAUNCH_CHECK();
+  if (p.trace) {
+    std::vector<long long> h(16 * (n_tr + 1));
+    SCN_CUDA(cudaStreamSynchronize(s));
+    SCN_CUDA(cudaMemcpy(h.data(), p.trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    double m[16] = {0};
+    for (int i = 0; i < n_tr; ++i) for (int j = 1; j < 16; ++j) m[j] += (double)h[i * 16 + j] / n_tr;
+    fprintf(stderr, "[conv trace] rows %d C %d->%d TN %d stages %d nprod %d | tiles sampled %d: setup %.0f, items %.1f, "
+            "mma wait-full %.0f, mma done %.0f | prod0 wait-empty %.0f, issue %.0f, done %.0f | accum %.0f, end %.0f clk\n",
+            a.n_rows, a.c_in, a.c_out, p.TN, p.stages, p.nprod, n_tr, m[1], m[8], m[2], m[3], m[4], m[9], m[5], m[6], m[7]);
+  }
 }
 
 bool wgrad_tma_supported(const WgradArgs &a) {
   const int cg = a.table_on_a ? a.c_a : a.c_b, cs = a.table_on_a ? a.c_b : a.c_a;
-  return a.chunk_mask != nullptr && a.g_rows > 0 && cg >= 32 && cg % 32 == 0 && cs >= 32 && cs % 32 == 0 && a.V <= 32 &&
-         tma::pick_tn(cs) > 0 && ((uintptr_t)a.a % 16 == 0) && ((uintptr_t)a.b % 16 == 0);
+  return a.gi != nullptr && a.g_rows > 0 && a.s_rows > 0 && cg >= 32 && cg % 32 == 0 && cs >= 32 && cs % 32 == 0 &&
+         a.V <= 32 && ((uintptr_t)a.a % 16 == 0) && ((uintptr_t)a.b % 16 == 0);
 }
 
 void wgrad_tma(const WgradArgs &a, cudaStream_t s) {
   using namespace tma;
   SCN_CUDA(cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.V * a.c_a * a.c_b, s));
-  if (a.n_rows == 0) return;
+  if (a.n_rows == 0 || a.n_blk == 0) return;
   WgParams p;
   const float *G = a.table_on_a ? a.a : a.b;
   const float *S = a.table_on_a ? a.b : a.a;
   p.Cg = a.table_on_a ? a.c_a : a.c_b;
   p.Cs = a.table_on_a ? a.c_b : a.c_a;
   p.transpose_out = a.table_on_a ? 0 : 1;
-  p.dw = a.dw; p.tbl = a.tbl; p.cmask = a.chunk_mask; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
-  p.g_rows = a.g_rows; p.V = a.V;
-  p.N = pick_tn(p.Cs);
-  const int n_slots = a.V * (p.Cg / 32);
-  p.n_acc_total = (n_slots + 3) / 4;
-  const int max_acc = 512 / p.N;
-  const int groups = (p.n_acc_total + max_acc - 1) / max_acc;
-  p.acc_per_cta = (p.n_acc_total + groups - 1) / groups;
+  p.dw = a.dw; p.gi = a.gi; p.si = a.si; p.blk_item = a.blk_item; p.V = a.V; p.n_blk = a.n_blk;
+  p.m_tiles = (p.Cg + 127) / 128;
+  p.N = 0;
+  for (int n = 256; n >= 32; n -= 32)
+    if (p.Cs % n == 0 && p.m_tiles * n <= 512) { p.N = n; break; }
+  SCN_CHECK(p.N > 0, "wgrad_tma: no N tile");
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.acc_per_cta * p.N) p.tmem_cols <<= 1;
-  const int n_tiles_n = p.Cs / p.N;
-  int row_splits = sm_count() / (groups * n_tiles_n);
-  if (row_splits < 1) row_splits = 1;
-  int rows = (a.n_rows + row_splits - 1) / row_splits;
-  if (rows < 512) rows = 512;
-  p.rows_per_cta = (rows + KR - 1) / KR * KR;
-  row_splits = (a.n_rows + p.rows_per_cta - 1) / p.rows_per_cta;
-  p.s_stage = (p.N / 32) * SUB;
-  p.s_stages = p.s_stage <= 16384 ? 3 : 2;
-  const int fixed = 1024 + 8 * (2 * 8 + 2 * 3 + 1) + 64 + 4 * 2 * a.V * KR * (int)sizeof(int);
-  p.g_stages = (200 * 1024 - fixed - p.s_stages * p.s_stage) / G_STAGE;
-  if (p.g_stages > 8) p.g_stages = 8;
-  SCN_CHECK(p.g_stages >= 2, "wgrad_tma: shared memory budget");
-  const size_t smem = (size_t)fixed + (size_t)p.g_stages * G_STAGE + (size_t)p.s_stages * p.s_stage;
+  while (p.tmem_cols < p.m_tiles * p.N) p.tmem_cols <<= 1;
+  // every stage holds the item's G atoms, then its S atoms; an accumulator tile always spans 4 G atoms, so the
+  // last tile of a Cg that is not a multiple of 128 reads on into the S atoms (finite data; rows >= Cg are ignored)
+  p.stage_bytes = (p.Cg / 32 + p.N / 32) * SUB;
+  const int fixed = 1024 + 4 * 64 * 4 + 8 * (2 * 8 + 1) + 64;
+  const int tail = p.m_tiles * 128 > p.Cg ? 4 * SUB : 0;
+  int budget = 113 * 1024;
+  if (512 / p.tmem_cols < 2 || (budget - fixed - tail) / p.stage_bytes < 3) budget = 225 * 1024;
+  int st = (budget - fixed - tail) / p.stage_bytes;
+  SCN_CHECK(st >= 2, "wgrad_tma: shared memory budget");
+  st = st >= 8 ? 8 : st >= 6 ? 6 : st >= 4 ? 4 : st >= 3 ? 3 : 2;
+  p.stages = st;
+  p.nprod = st % 4 == 0 ? 4 : st % 3 == 0 ? 3 : 2;
+  const size_t smem = (size_t)fixed + (size_t)p.stages * p.stage_bytes + tail;
+  // row range per CTA: about 8 MB of G + S rows, so the ranges in flight (SMs x CTAs/SM / V of them) fit in L2
+  static const int range_kb = env_int("SCN_WG_RANGE_KB", 8192);
+  long long rows = (long long)range_kb * 1024 / ((long long)(p.Cg + p.Cs) * 4);
+  int bpr = (int)(rows / a.blk_rows);
+  if (bpr < 1) bpr = 1;
+  p.blk_per_range = bpr;
+  const int ranges = (a.n_blk + bpr - 1) / bpr;
   CUtensorMap mg = make_map(G, (uint64_t)p.Cg, (uint64_t)a.g_rows, 32, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  CUtensorMap ms = make_map(S, (uint64_t)p.Cs, (uint64_t)a.n_rows, 32, KR, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  CUtensorMap ms = make_map(S, (uint64_t)p.Cs, (uint64_t)a.s_rows, 32, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
   static size_t configured = 0;
   if (smem > configured) {
     SCN_CUDA(cudaFuncSetAttribute(k_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  {
-    const char *e = getenv("SCN_WG_DBG");
-    p.dbg = e ? atoi(e) : 0;
-  }
-  dim3 grid(row_splits, groups, n_tiles_n);
-  k_wgrad_tma<<<grid, NTHREADS, smem, s>>>(mg, ms, p);
+  dim3 grid(a.V, ranges, p.Cs / p.N);
+  k_wgrad_tma<<<grid, WG_THREADS, smem, s>>>(mg, ms, p);
   SCN_LAUNCH_CHECK();
 }
 

@@ -172,6 +172,51 @@ __global__ void k_chunk_masks(const int *__restrict__ tbl, int stride, int V, in
   if (lane == 0) out[chunk] = m;
 }
 
+// ---- per-tap compaction of a [V][stride] table into padded (entry, column) lists ------------------------------
+struct IsRule {
+  __host__ __device__ int operator()(const int &t) const { return t >= 0 ? 1 : 0; }
+};
+// rank[i] = number of rules before flat position i.  One thread block: tap k owns rules rank[k*stride] ..
+// rank[(k+1)*stride]-1; its list starts at item_off[k] (32 rules per item, every tap rounded up).
+__global__ void k_pair_offsets(const int *__restrict__ tbl, const int *__restrict__ rank, int V, int stride,
+                               int *__restrict__ item_off, int *__restrict__ rank_base) {
+  if (threadIdx.x != 0) return;
+  const long long last = (long long)V * stride - 1;
+  const int total = rank[last] + (tbl[last] >= 0 ? 1 : 0);
+  int items = 0;
+  for (int k = 0; k < V; ++k) {
+    const int b = rank[(long long)k * stride];
+    const int e = (k + 1 < V) ? rank[(long long)(k + 1) * stride] : total;
+    item_off[k] = items;
+    rank_base[k] = b;
+    items += (e - b + 31) / 32;
+  }
+  item_off[V] = items;
+}
+__global__ void k_block_items(const int *__restrict__ rank, int V, int stride, int n_blk, int blk_rows,
+                              const int *__restrict__ item_off, const int *__restrict__ rank_base,
+                              int *__restrict__ blk_item) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V * (n_blk + 1)) return;
+  const int k = i / (n_blk + 1), b = i - k * (n_blk + 1);
+  const long long col = (long long)b * blk_rows;
+  blk_item[i] = (b == n_blk || col >= stride) ? item_off[k + 1]
+                                              : item_off[k] + (rank[(long long)k * stride + col] - rank_base[k]) / 32;
+}
+__global__ void k_scatter_pairs(const int *__restrict__ tbl, const int *__restrict__ rank, long long n_flat, int stride,
+                                const int *__restrict__ item_off, const int *__restrict__ rank_base,
+                                int *__restrict__ gi, int *__restrict__ si) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n_flat) return;
+  const int t = tbl[i];
+  if (t < 0) return;
+  const int k = (int)(i / stride);
+  const int col = (int)(i - (long long)k * stride);
+  const long long pos = (long long)item_off[k] * 32 + (rank[i] - rank_base[k]);
+  gi[pos] = t;
+  si[pos] = col;
+}
+
 __global__ void k_fill_int(int *p, long long n, int v) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -229,6 +274,41 @@ static void sort_and_group(DevBuf<uint64_t> &keys, DevBuf<int> &idx, long long n
   keys_sorted.release(s);
   counts.release(s);
   d_nruns.release(s);
+  tmp.release(s);
+}
+
+void build_pair_list(PairList &out, const int *tbl, int V, int stride, long long n_rules, cudaStream_t s) {
+  if (out.item_off.p) return;
+  const long long n_flat = (long long)V * stride;
+  SCN_CHECK(n_flat > 0 && n_flat < (1ll << 31), "rule table too large for 32-bit ranks");
+  out.n_items_ub = (n_rules + 31ll * V) / 32 + 1;
+  out.gi.alloc((size_t)out.n_items_ub * 32, s);
+  out.si.alloc((size_t)out.n_items_ub * 32, s);
+  out.item_off.alloc(V + 1, s);
+  SCN_CUDA(cudaMemsetAsync(out.gi.p, 0x7F, sizeof(int) * out.gi.n, s));   // PAIR_PAD
+  SCN_CUDA(cudaMemsetAsync(out.si.p, 0x7F, sizeof(int) * out.si.n, s));
+  DevBuf<int> rank, rank_base;
+  rank.alloc((size_t)n_flat, s);
+  rank_base.alloc(V, s);
+  cub::TransformInputIterator<int, IsRule, const int *> flags(tbl, IsRule());
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, flags, rank.p, (int)n_flat, s);
+  DevBuf<uint8_t> tmp;
+  tmp.alloc(tb, s);
+  SCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags, rank.p, (int)n_flat, s));
+  count_launch(2);
+  k_pair_offsets<<<1, 32, 0, s>>>(tbl, rank.p, V, stride, out.item_off.p, rank_base.p);
+  SCN_LAUNCH_CHECK();
+  k_scatter_pairs<<<grid_for(n_flat, 256), 256, 0, s>>>(tbl, rank.p, n_flat, stride, out.item_off.p, rank_base.p,
+                                                         out.gi.p, out.si.p);
+  SCN_LAUNCH_CHECK();
+  out.n_blk = (stride + BLK_ROWS - 1) / BLK_ROWS;
+  out.blk_item.alloc((size_t)V * (out.n_blk + 1), s);
+  k_block_items<<<grid_for((long long)V * (out.n_blk + 1), 256), 256, 0, s>>>(rank.p, V, stride, out.n_blk, BLK_ROWS,
+                                                                             out.item_off.p, rank_base.p, out.blk_item.p);
+  SCN_LAUNCH_CHECK();
+  rank.release(s);
+  rank_base.release(s);
   tmp.release(s);
 }
 
