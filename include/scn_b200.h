@@ -92,7 +92,7 @@ int scn_strided_table(scn_meta *m, const int64_t fine_size[3], int32_t *parent_h
  * out[N,Cout] = sum_k in[nbr_k(o)] * W[k];  *macs = sum_k n_k*Cin*Cout (the reference's return value) */
 int scn_subm_fwd(scn_meta *m, const int64_t spatial_size[3], const float *in, const float *weight, const float *bias,
                  float *out, int c_in, int c_out, int precision, void *stream, double *macs);
-/* d_in[N,Cin], d_weight[27,Cin,Cout], d_bias[Cout] (NULL when no bias) */
+/* d_in[N,Cin] (NULL: the input gradient is not needed and is skipped), d_weight[27,Cin,Cout], d_bias[Cout] (NULL when no bias) */
 int scn_subm_bwd(scn_meta *m, const int64_t spatial_size[3], const float *in, const float *d_out, const float *weight,
                  float *d_in, float *d_weight, float *d_bias, int c_in, int c_out, int precision, void *stream);
 

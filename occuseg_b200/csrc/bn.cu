@@ -2,84 +2,112 @@
 // (CUDA/BatchNormalization.cu:14-199, dispatch :201-238; drivers CUDA/BatchNormalization.cpp:21-71).
 //
 // The reference walks all N rows with at most 16 CTAs (grid = min(16, C/NTX)) and accumulates the
-// statistics as fp32 running sums.  Here the reduction is spread over 2 CTAs per SM, partial sums are
+// statistics as fp32 running sums.  Here the reduction is spread over 4 CTAs per SM, partial sums are
 // short fp32 chains merged in fp64, and the normalise pass is a 128-bit streaming kernel.
 // HBM-bound: forward 3*N*C*4 bytes (read x twice, write y), backward 5*N*C*4.
 #include "common.cuh"
 
 namespace scn {
 
-constexpr int BX = 64, BY = 4;          // block = 64 column lanes x 4 row lanes
-constexpr int ROWS_PER_STEP = 256;      // rows a CTA folds in fp32 before flushing to fp64
+constexpr int RED_THREADS = 256;
+constexpr int ROWS_PER_FLUSH = 64;      // rows a thread folds in fp32 before adding to its fp64 partial
 
 // column sums of u(x) and v(x):  MODE 0: (x, x*x)          (forward statistics)
 //                                MODE 1: (d', (x-mean)*d')  with d' = d * (y>0 ? 1 : leak)   (backward)
+// Thread t owns column group t % cv (VEC columns) and row lane t / cv, so every lane of the block is busy for any
+// C (the block uses cv * floor(256/cv) threads) and a warp reads whole contiguous rows.  Four independent rows
+// are in flight per thread.  fp32 chains of <= 64 rows are merged in fp64 (registers -> shared -> one fp64
+// atomic per column per CTA).
 template <int VEC, int MODE>
-__global__ void __launch_bounds__(BX *BY) k_bn_reduce(const float *__restrict__ x, const float *__restrict__ y,
-                                                       const float *__restrict__ d, const float *__restrict__ mean,
-                                                       long long n, int C, float leak, double *__restrict__ acc) {
+__global__ void __launch_bounds__(RED_THREADS) k_bn_reduce(const float *__restrict__ x, const float *__restrict__ y,
+                                                          const float *__restrict__ d, const float *__restrict__ mean,
+                                                          long long n, int C, float leak, double *__restrict__ acc) {
   const int cv = C / VEC;
-  __shared__ float red[2][BY][BX * VEC];
-  for (int cg0 = 0; cg0 < cv; cg0 += BX) {
-    const int cg = cg0 + threadIdx.x;
-    const bool live = cg < cv;
-    float m[VEC];
+  const int row_lanes = blockDim.x / cv;
+  const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
+  extern __shared__ double red[];          // [2][row_lanes][C]
+  float m[VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) m[j] = (MODE == 1 && live) ? __ldg(&mean[cg * VEC + j]) : 0.f;
-    for (long long rb = (long long)blockIdx.x * ROWS_PER_STEP; rb < n; rb += (long long)gridDim.x * ROWS_PER_STEP) {
-      float s0[VEC], s1[VEC];
+  for (int j = 0; j < VEC; ++j) m[j] = MODE == 1 ? __ldg(&mean[cg * VEC + j]) : 0.f;
+  double t0[VEC], t1[VEC];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) s0[j] = s1[j] = 0.f;
-      if (live) {
-        long long rend = rb + ROWS_PER_STEP < n ? rb + ROWS_PER_STEP : n;
-        for (long long r = rb + threadIdx.y; r < rend; r += BY) {
-          float xv[VEC], yv[VEC], dv[VEC];
-          if (VEC == 4) {
-            float4 t = __ldg(reinterpret_cast<const float4 *>(x + r * C) + cg);
-            xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
-            if (MODE == 1) {
-              float4 u = __ldg(reinterpret_cast<const float4 *>(y + r * C) + cg);
-              float4 w = __ldg(reinterpret_cast<const float4 *>(d + r * C) + cg);
-              yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
-              dv[0] = w.x; dv[1] = w.y; dv[2] = w.z; dv[3] = w.w;
-            }
-          } else {
-            xv[0] = __ldg(x + r * C + cg);
-            if (MODE == 1) { yv[0] = __ldg(y + r * C + cg); dv[0] = __ldg(d + r * C + cg); }
-          }
-#pragma unroll
-          for (int j = 0; j < VEC; ++j) {
-            if (MODE == 0) {
-              s0[j] += xv[j];
-              s1[j] = fmaf(xv[j], xv[j], s1[j]);
-            } else {
-              float dd = yv[j] > 0.f ? dv[j] : dv[j] * leak;
-              s0[j] += dd;
-              s1[j] = fmaf(xv[j] - m[j], dd, s1[j]);
-            }
-          }
-        }
+  for (int j = 0; j < VEC; ++j) t0[j] = t1[j] = 0.0;
+  const long long rows_per_cta = (n + gridDim.x - 1) / gridDim.x;
+  const long long r_begin = blockIdx.x * rows_per_cta;
+  const long long r_end = r_begin + rows_per_cta < n ? r_begin + rows_per_cta : n;
+  auto fold = [&](long long r, float *s0, float *s1) {
+    float xv[VEC], yv[VEC], dv[VEC];
+    if (VEC == 4) {
+      float4 t = __ldg(reinterpret_cast<const float4 *>(x + r * C) + cg);
+      xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+      if (MODE == 1) {
+        float4 u = __ldg(reinterpret_cast<const float4 *>(y + r * C) + cg);
+        float4 w = __ldg(reinterpret_cast<const float4 *>(d + r * C) + cg);
+        yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
+        dv[0] = w.x; dv[1] = w.y; dv[2] = w.z; dv[3] = w.w;
       }
+    } else {
+      xv[0] = __ldg(x + r * C + cg);
+      if (MODE == 1) { yv[0] = __ldg(y + r * C + cg); dv[0] = __ldg(d + r * C + cg); }
+    }
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        red[0][threadIdx.y][threadIdx.x * VEC + j] = s0[j];
-        red[1][threadIdx.y][threadIdx.x * VEC + j] = s1[j];
+    for (int j = 0; j < VEC; ++j) {
+      if (MODE == 0) {
+        s0[j] += xv[j];
+        s1[j] = fmaf(xv[j], xv[j], s1[j]);
+      } else {
+        float dd = yv[j] > 0.f ? dv[j] : dv[j] * leak;
+        s0[j] += dd;
+        s1[j] = fmaf(xv[j] - m[j], dd, s1[j]);
       }
-      __syncthreads();
-      // BY partials per column -> fp64 -> one atomic per column per step
-      for (int e = threadIdx.y * BX + threadIdx.x; e < 2 * BX * VEC; e += BX * BY) {
-        int which = e / (BX * VEC), col = e % (BX * VEC);
-        int c = cg0 * VEC + col;
-        if (c < C) {
-          double t = 0.0;
+    }
+  };
+  for (long long rb = r_begin + rl; rb < r_end; rb += (long long)row_lanes * ROWS_PER_FLUSH) {
+    float s0[4][VEC], s1[4][VEC];
 #pragma unroll
-          for (int i = 0; i < BY; ++i) t += (double)red[which][i][col];
-          atomicAdd(&acc[which * C + c], t);
-        }
-      }
-      __syncthreads();
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) s0[u][j] = s1[u][j] = 0.f;
+    long long r = rb;
+    const long long stop = rb + (long long)row_lanes * ROWS_PER_FLUSH < r_end ? rb + (long long)row_lanes * ROWS_PER_FLUSH : r_end;
+    for (; r + 3ll * row_lanes < stop; r += 4ll * row_lanes) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) fold(r + (long long)u * row_lanes, s0[u], s1[u]);
+    }
+    for (; r < stop; r += row_lanes) fold(r, s0[0], s1[0]);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      t0[j] += (double)((s0[0][j] + s0[1][j]) + (s0[2][j] + s0[3][j]));
+      t1[j] += (double)((s1[0][j] + s1[1][j]) + (s1[2][j] + s1[3][j]));
     }
   }
+  if (threadIdx.x < cv * row_lanes) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      red[(0 * row_lanes + rl) * C + cg * VEC + j] = t0[j];
+      red[(1 * row_lanes + rl) * C + cg * VEC + j] = t1[j];
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * C; e += blockDim.x) {
+    const int which = e / C, c = e - which * C;
+    double t = 0.0;
+    for (int i = 0; i < row_lanes; ++i) t += red[(which * row_lanes + i) * C + c];
+    atomicAdd(&acc[which * C + c], t);
+  }
+}
+
+struct RedCfg { int threads, grid; size_t smem; };
+static RedCfg reduce_cfg(long long n, int C, int vec) {
+  const int cv = C / vec;
+  RedCfg c;
+  const int row_lanes = cv >= RED_THREADS ? 1 : RED_THREADS / cv;
+  c.threads = cv >= RED_THREADS ? RED_THREADS : cv * row_lanes;
+  c.smem = sizeof(double) * 2 * (size_t)row_lanes * C;
+  long long g = (n + (long long)row_lanes * 16 - 1) / ((long long)row_lanes * 16);
+  long long cap = (long long)sm_count() * 4;
+  c.grid = (int)(g < 1 ? 1 : g > cap ? cap : g);
+  return c;
 }
 
 // forward finalize: mean / invstd / running statistics.  Formulas follow BatchNormalization.cu:38-51
@@ -209,9 +237,11 @@ void bn_fwd(const float *in, float *out, float *save_mean, float *save_invstd, f
   if (train) {
     SCN_CHECK(n > 1, "BatchNorm (train): needs at least two active rows");
     SCN_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * 2 * C, s));
-    int grid = (int)std::min<long long>((n + ROWS_PER_STEP - 1) / ROWS_PER_STEP, (long long)sm_count() * 2);
-    if (v4) k_bn_reduce<4, 0><<<grid, dim3(BX, BY), 0, s>>>(in, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
-    else k_bn_reduce<1, 0><<<grid, dim3(BX, BY), 0, s>>>(in, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
+    const bool r4 = v4 && C / 4 <= RED_THREADS;
+    SCN_CHECK(r4 || C <= RED_THREADS, "BatchNorm: more than 256 channels need 16-byte aligned rows");
+    const RedCfg rc = reduce_cfg(n, C, r4 ? 4 : 1);
+    if (r4) k_bn_reduce<4, 0><<<rc.grid, rc.threads, rc.smem, s>>>(in, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
+    else k_bn_reduce<1, 0><<<rc.grid, rc.threads, rc.smem, s>>>(in, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
     SCN_LAUNCH_CHECK();
   }
   k_bn_finalize_fwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, eps, momentum, train, save_mean, save_invstd,
@@ -236,9 +266,11 @@ void bn_bwd(const float *in, const float *out, const float *d_out, const float *
   acc.alloc(2 * (size_t)C, s);
   coef.alloc(2 * (size_t)C, s);
   SCN_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * 2 * C, s));
-  int grid = (int)std::min<long long>((n + ROWS_PER_STEP - 1) / ROWS_PER_STEP, (long long)sm_count() * 2);
-  if (v4) k_bn_reduce<4, 1><<<grid, dim3(BX, BY), 0, s>>>(in, out, d_out, save_mean, n, C, leakiness, acc.p);
-  else k_bn_reduce<1, 1><<<grid, dim3(BX, BY), 0, s>>>(in, out, d_out, save_mean, n, C, leakiness, acc.p);
+  const bool r4 = v4 && C / 4 <= RED_THREADS;
+  SCN_CHECK(r4 || C <= RED_THREADS, "BatchNorm: more than 256 channels need 16-byte aligned rows");
+  const RedCfg rc = reduce_cfg(n, C, r4 ? 4 : 1);
+  if (r4) k_bn_reduce<4, 1><<<rc.grid, rc.threads, rc.smem, s>>>(in, out, d_out, save_mean, n, C, leakiness, acc.p);
+  else k_bn_reduce<1, 1><<<rc.grid, rc.threads, rc.smem, s>>>(in, out, d_out, save_mean, n, C, leakiness, acc.p);
   SCN_LAUNCH_CHECK();
   k_bn_finalize_bwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, save_invstd, d_gamma, d_beta, coef.p);
   SCN_LAUNCH_CHECK();

@@ -117,7 +117,8 @@ static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, 
       else conv_tc(a, s);
     } else {
       a.weight = use;
-      conv_simt(a, s);
+      if (conv_small_supported(a)) conv_small(a, s);
+      else conv_simt(a, s);
     }
   }
   tmp.release(s);
@@ -152,6 +153,7 @@ static void run_wgrad(WgradArgs a, PairList &pairs, int precision, cudaStream_t 
   ProfScope ps(tcore ? PK_WGRAD_TC : PK_WGRAD_FP32, bytes, 2.0 * (double)a.n_rules * a.c_a * a.c_b, s);
   if (tcore && use_tma()) wgrad_tma(a, s);
   else if (tcore) wgrad_tc(a, s);
+  else if (wgrad_small_supported(a)) wgrad_small(a, s);
   else wgrad_simt(a, s);
 }
 
@@ -333,7 +335,7 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   ConvArgs a;
   a.in = d_out; a.out = d_in;
   a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_out; a.c_out = c_in; a.mirror = true; a.n_rules = L->n_rules; a.in_rows = L->n;
-  run_conv(a, weight, false, precision, s);
+  if (d_in) run_conv(a, weight, false, precision, s);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = L->nbr.p; w.tbl_stride = L->n_pad; w.n_rows = L->n; w.V = 27;
   w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules; w.chunk_mask = L->nbr_cm.p; w.g_rows = L->n; w.s_rows = L->n;

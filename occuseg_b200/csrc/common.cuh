@@ -166,6 +166,8 @@ struct ConvArgs {
   bool scatter = false;
 };
 void conv_simt(const ConvArgs &a, cudaStream_t s);
+bool conv_small_supported(const ConvArgs &a);
+void conv_small(const ConvArgs &a, cudaStream_t s);   // c_in <= 4: one thread per output row (conv_small.cu)
 bool conv_tc_supported(const ConvArgs &a);
 void conv_tc(const ConvArgs &a, cudaStream_t s);       // cp.async producers (kept for A/B runs: SCN_TC_IMPL=cpasync)
 bool conv_tma_supported(const ConvArgs &a);
@@ -196,6 +198,8 @@ struct WgradArgs {
   bool table_on_a = true;
 };
 void wgrad_simt(const WgradArgs &a, cudaStream_t s);
+bool wgrad_small_supported(const WgradArgs &a);
+void wgrad_small(const WgradArgs &a, cudaStream_t s);
 bool wgrad_tc_supported(const WgradArgs &a);
 void wgrad_tc(const WgradArgs &a, cudaStream_t s);
 bool wgrad_tma_supported(const WgradArgs &a);

@@ -196,7 +196,8 @@ def SubmanifoldConvolution_backward(spatial_size, filter_size, m, input_features
                                     weight, d_weight, d_bias, dilated_rate=1):
     x, g, w = _cuda_f32(input_features, "input"), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 27)
     with torch.cuda.device(x.device):
-        d_input_features.resize_(x.size(0), x.size(1))
+        if d_input_features is not None:      # None: the caller does not need the input gradient (first layer)
+            d_input_features.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_subm_bwd(m._handle(), _lib.size3(spatial_size), _ptr(x), _ptr(g), _ptr(w),
                                            _ptr(d_input_features), _ptr(d_weight), _ptr(_opt(d_bias)), w.size(1),
                                            w.size(2), _precision, _stream()))
@@ -281,24 +282,37 @@ def BatchNormalization_backward(input_features, d_input_features, output_feature
                                          _ptr(_opt(d_bias)), x.size(0), x.size(1), float(leakiness), _stream()))
 
 
-# ---- 1x1 "NetworkInNetwork": the reference itself calls ATen's GEMM here (CUDA/NetworkInNetwork.cpp:9-50)
+# ---- 1x1 "NetworkInNetwork": the reference itself calls ATen's GEMM here (CUDA/NetworkInNetwork.cpp:9-50).
+# Plain library GEMMs; in 'tf32' precision they run on the tensor cores like the convolutions around them.
+class _gemm_precision:
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = _precision == _lib.TF32
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
 def NetworkInNetwork_updateOutput(input_features, output_features, weight, bias):
     n = input_features.size(0)
     output_features.resize_(n, weight.size(1))
-    if _opt(bias) is not None:
-        torch.addmm(bias, input_features, weight, out=output_features)
-    else:
-        torch.mm(input_features, weight, out=output_features)
+    with _gemm_precision():
+        if _opt(bias) is not None:
+            torch.addmm(bias, input_features, weight, out=output_features)
+        else:
+            torch.mm(input_features, weight, out=output_features)
     return float(n * weight.size(0) * weight.size(1))
 
 
 def NetworkInNetwork_updateGradInput(d_input_features, d_output_features, weight):
     d_input_features.resize_(d_output_features.size(0), weight.size(0))
-    torch.mm(d_output_features, weight.t(), out=d_input_features)
+    with _gemm_precision():
+        torch.mm(d_output_features, weight.t(), out=d_input_features)
 
 
 def NetworkInNetwork_accGradParameters(input_features, d_output_features, d_weight, d_bias):
     if input_features.size(0):
         if d_bias is not None and d_bias.numel():
             torch.sum(d_output_features, 0, out=d_bias)
-        torch.mm(input_features.t(), d_output_features, out=d_weight)
+        with _gemm_precision():
+            torch.mm(input_features.t(), d_output_features, out=d_weight)

@@ -33,7 +33,9 @@ class SubmanifoldConvolutionFunction(Function):
     @staticmethod
     def backward(ctx, grad_out):
         x, spatial_size, weight, bias, filter_size = ctx.saved_tensors
-        gx, gw, gb = grad_out.new_empty(0), torch.zeros_like(weight), torch.zeros_like(bias)
+        gw, gb = torch.zeros_like(weight), torch.zeros_like(bias)
+        # the layer behind the InputLayer has no use for d_input (point features are data): skip that product
+        gx = grad_out.new_empty(0) if ctx.needs_input_grad[0] else None
         SCN.SubmanifoldConvolution_backward(spatial_size, filter_size, ctx.scn_meta, x, gx, grad_out.contiguous(),
                                             weight, gw, gb, ctx.dilated_rate)
         del ctx.scn_meta
