@@ -21,7 +21,10 @@
  *
  * precision: SCN_FP32 = exact fp32 FMA path (rel 1e-5 vs the reference CPU arithmetic);
  *            SCN_TF32 = tcgen05 kind::tf32 tiles, fp32 accumulate in TMEM (rel 2e-2), used only
- *                       when Cin and Cout are multiples of 32 and >= 32, else falls to SCN_FP32.
+ *                       when Cin and Cout are multiples of 32 and >= 32, else falls to SCN_FP32;
+ *            SCN_BF16 = tcgen05 kind::f16 tiles on bf16 COPIES of the fp32 operands (made inside the call), fp32
+ *                       accumulate, fp32 outputs (rel 2e-2); needs the contraction width to be a multiple of 64,
+ *                       else falls to SCN_TF32.
  */
 #ifndef SCN_B200_H
 #define SCN_B200_H
@@ -34,7 +37,7 @@ extern "C" {
 
 typedef struct scn_meta scn_meta; /* opaque; replaces Metadata<3> (Metadata/Metadata.h:218-364) */
 
-enum { SCN_FP32 = 0, SCN_TF32 = 1 };
+enum { SCN_FP32 = 0, SCN_TF32 = 1, SCN_BF16 = 2 };
 
 /* ---- library --------------------------------------------------------------------------------- */
 int scn_version(void);

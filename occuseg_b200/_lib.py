@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libscn_b200.so")
 
-FP32, TF32 = 0, 1
+FP32, TF32, BF16 = 0, 1, 2
 
 _i64p = C.POINTER(C.c_int64)
 _vp = C.c_void_p

@@ -70,7 +70,7 @@ int prof_read(double *out, int max_kinds) {
   return n;
 }
 const char *prof_name(int kind) {
-  static const char *names[PK_COUNT] = {"rulebook", "conv_tc", "conv_fp32", "wgrad_tc", "wgrad_fp32", "bn", "io"};
+  static const char *names[PK_COUNT] = {"rulebook", "conv_tc", "conv_fp32", "wgrad_tc", "wgrad_fp32", "bn", "io", "cast"};
   return (kind >= 0 && kind < PK_COUNT) ? names[kind] : "";
 }
 
@@ -80,41 +80,63 @@ static Level *need_level(Meta *m, const int64_t size[3], const char *what) {
   return L;
 }
 
-// `w` is the caller's weight array; native_kn says whether, for THIS product, it already reads as
-// [V][K=c_in][N=c_out] (true) or as [V][N][K] (false).  The fp32 kernels want KN, the tensor-core kernels
-// want NK (K-major B operand); whichever is missing is produced by one small per-tap transpose.
-static bool use_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("SCN_TC_IMPL");
-    v = (e && std::string(e) == "cpasync") ? 0 : 1;
-  }
-  return v == 1;
-}
-static bool tc_ok(const ConvArgs &a) { return use_tma() ? conv_tma_supported(a) : conv_tc_supported(a); }
+// ---- precision plumbing ----------------------------------------------------------------------------------
+// SCN_BF16: operands of the tensor-core kernels are bf16 COPIES of the caller's fp32 matrices (made here, one
+// streaming pass each, or handed in by the caller when two products share one), products accumulate in fp32 and
+// outputs stay fp32.  Needs K % 64 == 0 (128-byte swizzle rows of bf16); other shapes fall to SCN_TF32 tiles
+// (K % 32 == 0) and then to the exact fp32 kernels.
+static bool bf16_conv_shape(int k, int n, int precision) { return precision == SCN_BF16 && k % 64 == 0 && n % 32 == 0; }
+static bool bf16_wgrad_shape(int cg, int cs, int precision) { return precision == SCN_BF16 && cg % 64 == 0 && cs % 64 == 0; }
 
-static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, cudaStream_t s) {
-  const bool tcore = precision == SCN_TF32 && tc_ok(a);
+struct Bf16Copy {
+  DevBuf<uint16_t> buf;
+  const uint16_t *make(const float *src, long long n, cudaStream_t s) {
+    buf.alloc((size_t)n, s);
+    ProfScope ps(PK_CAST, 6.0 * (double)n, 0.0, s);
+    cast_bf16(src, buf.p, n, s);
+    return buf.p;
+  }
+  void release(cudaStream_t s) { buf.release(s); }
+};
+
+// `w` is the caller's weight array; native_kn says whether, for THIS product, it already reads as
+// [V][K=c_in][N=c_out] (true) or as [V][N][K] (false).  The fp32 kernels want KN, the tensor-core kernel
+// wants NK (K-major B operand); whichever is missing is produced by one small per-tap transpose.
+// in16: optional bf16 copy of a.in made by the caller.
+static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, cudaStream_t s,
+                     const uint16_t *in16 = nullptr) {
+  a.bf16 = bf16_conv_shape(a.c_in, a.c_out, precision);
+  const bool tcore = precision != SCN_FP32 && conv_tma_supported(a);
+  if (!tcore) a.bf16 = false;
   const bool want_kn = !tcore;
   DevBuf<float> tmp;
+  DevBuf<uint16_t> w16;
+  Bf16Copy x16;
   const float *use = w;
+  const size_t wn = (size_t)a.V * a.c_in * a.c_out;
   if (want_kn != native_kn) {
-    tmp.alloc((size_t)a.V * a.c_in * a.c_out, s);
+    tmp.alloc(wn, s);
     // source rows/cols: native_kn -> [c_in][c_out], else [c_out][c_in]
     if (native_kn) transpose_weight(w, tmp.p, a.V, a.c_in, a.c_out, s);
     else transpose_weight(w, tmp.p, a.V, a.c_out, a.c_in, s);
     use = tmp.p;
   }
-  // algorithmic work (gather/scatter model): R*Cin*s + N*Cout*s + 4*R + V*Cin*Cout*s
-  const double bytes = 4.0 * ((double)a.n_rules * a.c_in + (double)(a.scatter ? a.n_rules : a.n_rows) * a.c_out +
-                              (double)a.n_rules + (double)a.V * a.c_in * a.c_out);
+  const double es = a.bf16 ? 2.0 : 4.0;      // bytes per gathered element
+  // algorithmic work (gather/scatter model): R*Cin*s + N*Cout*4 + 4*R + V*Cin*Cout*s
+  const double bytes = es * (double)a.n_rules * a.c_in + 4.0 * (double)(a.scatter ? a.n_rules : a.n_rows) * a.c_out +
+                       4.0 * (double)a.n_rules + es * (double)a.V * a.c_in * a.c_out;
   const double flops = 2.0 * (double)a.n_rules * a.c_in * a.c_out;
+  if (a.bf16) {
+    w16.alloc(wn, s);
+    cast_bf16(use, w16.p, (long long)wn, s);
+    if (!in16) in16 = x16.make(a.in, (long long)a.in_rows * a.c_in, s);
+  }
   {
     ProfScope ps(tcore ? PK_CONV_TC : PK_CONV_FP32, bytes, flops, s);
     if (tcore) {
-      a.weight_nk = use;
-      if (use_tma()) conv_tma(a, s);
-      else conv_tc(a, s);
+      a.weight_nk = a.bf16 ? (const void *)w16.p : (const void *)use;
+      if (a.bf16) a.in = reinterpret_cast<const float *>(in16);
+      conv_tma(a, s);
     } else {
       a.weight = use;
       if (conv_small_supported(a)) conv_small(a, s);
@@ -122,18 +144,20 @@ static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, 
     }
   }
   tmp.release(s);
+  w16.release(s);
+  x16.release(s);
 }
 
 // One-rule-per-fine-row products (Deconvolution forward, strided-Convolution dgrad):
 //   out[i] = in[parent[i]] * Wk(off[i]).   fp32: input-stationary scatter over the child table;
 //   tensor cores: gather over the `up` table (exactly one live tap per row, absent taps are skipped per tile).
 static void run_up(Level *F, Level *C, const float *in, const float *w, bool native_kn, float *out, int c_in, int c_out,
-                   int precision, cudaStream_t s) {
+                   int precision, cudaStream_t s, const uint16_t *in16 = nullptr) {
   ConvArgs g;
   g.in = in; g.out = out; g.tbl = F->up.p; g.tbl_stride = F->n_pad; g.n_rows = F->n; g.V = 8;
   g.c_in = c_in; g.c_out = c_out; g.n_rules = F->n; g.in_rows = C->n;
-  if (precision == SCN_TF32 && tc_ok(g)) {
-    run_conv(g, w, native_kn, precision, s);
+  if (precision != SCN_FP32 && conv_tma_supported(g)) {
+    run_conv(g, w, native_kn, precision, s, in16);
     return;
   }
   ConvArgs a;
@@ -142,19 +166,36 @@ static void run_up(Level *F, Level *C, const float *in, const float *w, bool nat
   run_conv(a, w, native_kn, SCN_FP32, s);
 }
 
-static void run_wgrad(WgradArgs a, PairList &pairs, int precision, cudaStream_t s) {
-  if (precision == SCN_TF32 && use_tma()) {
+// a16 / b16: optional bf16 copies of a.a / a.b made by the caller
+static void run_wgrad(WgradArgs a, PairList &pairs, int precision, cudaStream_t s, const uint16_t *a16 = nullptr,
+                      const uint16_t *b16 = nullptr) {
+  const int cg = a.table_on_a ? a.c_a : a.c_b, cs = a.table_on_a ? a.c_b : a.c_a;
+  a.bf16 = bf16_wgrad_shape(cg, cs, precision);
+  if (precision != SCN_FP32) {
     build_pair_list(pairs, a.tbl, a.V, a.tbl_stride, a.n_rules, s);
     a.gi = pairs.gi.p; a.si = pairs.si.p; a.blk_item = pairs.blk_item.p; a.n_blk = pairs.n_blk; a.blk_rows = BLK_ROWS;
   }
-  const bool tcore = precision == SCN_TF32 && (use_tma() ? wgrad_tma_supported(a) : wgrad_tc_supported(a));
+  const bool tcore = precision != SCN_FP32 && wgrad_tma_supported(a);
+  if (!tcore) a.bf16 = false;
+  Bf16Copy ca, cb;
+  if (a.bf16) {
+    const long long rows_a = a.table_on_a ? a.g_rows : a.s_rows, rows_b = a.table_on_a ? a.s_rows : a.g_rows;
+    if (!a16) a16 = ca.make(a.a, rows_a * a.c_a, s);
+    if (!b16) b16 = cb.make(a.b, rows_b * a.c_b, s);
+    a.a = reinterpret_cast<const float *>(a16);
+    a.b = reinterpret_cast<const float *>(b16);
+  }
+  const double es = a.bf16 ? 2.0 : 4.0;
   // R*(Cin+Cout)*s + 8*R + V*Cin*Cout*4
-  const double bytes = 4.0 * ((double)a.n_rules * (a.c_a + a.c_b) + 2.0 * a.n_rules + (double)a.V * a.c_a * a.c_b);
-  ProfScope ps(tcore ? PK_WGRAD_TC : PK_WGRAD_FP32, bytes, 2.0 * (double)a.n_rules * a.c_a * a.c_b, s);
-  if (tcore && use_tma()) wgrad_tma(a, s);
-  else if (tcore) wgrad_tc(a, s);
-  else if (wgrad_small_supported(a)) wgrad_small(a, s);
-  else wgrad_simt(a, s);
+  const double bytes = es * (double)a.n_rules * (a.c_a + a.c_b) + 8.0 * a.n_rules + 4.0 * (double)a.V * a.c_a * a.c_b;
+  {
+    ProfScope ps(tcore ? PK_WGRAD_TC : PK_WGRAD_FP32, bytes, 2.0 * (double)a.n_rules * a.c_a * a.c_b, s);
+    if (tcore) wgrad_tma(a, s);
+    else if (wgrad_small_supported(a)) wgrad_small(a, s);
+    else wgrad_simt(a, s);
+  }
+  ca.release(s);
+  cb.release(s);
 }
 
 }  // namespace scn
@@ -332,14 +373,20 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   ensure_neighbour_table(&h->m, L, s);
   // dgrad: d_in[i] = sum_k d_out[nbr[26-k][i]] * W[k]^T  (rule (i,o) at offset k  <=>  o sits at offset 26-k of i)
   // for this product K = c_out and N = c_in, so the caller's [27][c_in][c_out] array reads as [V][N][K]
+  const bool dgrad16 = d_in && bf16_conv_shape(c_out, c_in, precision), wgrad16 = bf16_wgrad_shape(c_in, c_out, precision);
+  Bf16Copy g16, x16;
+  const uint16_t *pg = (dgrad16 || wgrad16) ? g16.make(d_out, (long long)L->n * c_out, s) : nullptr;
+  const uint16_t *px = wgrad16 ? x16.make(in, (long long)L->n * c_in, s) : nullptr;
   ConvArgs a;
   a.in = d_out; a.out = d_in;
   a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_out; a.c_out = c_in; a.mirror = true; a.n_rules = L->n_rules; a.in_rows = L->n;
-  if (d_in) run_conv(a, weight, false, precision, s);
+  if (d_in) run_conv(a, weight, false, precision, s, dgrad16 ? pg : nullptr);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = L->nbr.p; w.tbl_stride = L->n_pad; w.n_rows = L->n; w.V = 27;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules; w.chunk_mask = L->nbr_cm.p; w.g_rows = L->n; w.s_rows = L->n;
-  run_wgrad(w, L->nbr_pairs, precision, s);
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules; w.g_rows = L->n; w.s_rows = L->n;
+  run_wgrad(w, L->nbr_pairs, precision, s, px, pg);
+  g16.release(s);
+  x16.release(s);
   if (d_bias) bias_grad(d_out, d_bias, L->n, c_out, s);
   SCN_CATCH
 }
@@ -373,7 +420,7 @@ int scn_conv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   run_up(F, C, d_out, weight, false, d_in, c_out, c_in, precision, s);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = F->n; w.chunk_mask = F->child_cm.p; w.g_rows = F->n; w.s_rows = C->n;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = F->n; w.g_rows = F->n; w.s_rows = C->n;
   run_wgrad(w, F->child_pairs, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, C->n, c_out, s);
   SCN_CATCH
@@ -415,7 +462,7 @@ int scn_deconv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
   // dW[k] = sum_p in[p]^T d_out[child[k][p]]
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
-  w.c_a = c_in; w.c_b = c_out; w.table_on_a = false; w.n_rules = F->n; w.chunk_mask = F->child_cm.p; w.g_rows = F->n; w.s_rows = C->n;
+  w.c_a = c_in; w.c_b = c_out; w.table_on_a = false; w.n_rules = F->n; w.g_rows = F->n; w.s_rows = C->n;
   run_wgrad(w, F->child_pairs, precision, s);
   if (d_bias) bias_grad(d_out, d_bias, F->n, c_out, s);
   SCN_CATCH

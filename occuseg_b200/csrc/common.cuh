@@ -37,7 +37,7 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 int sm_count();
 
 // ---- optional per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline) ----
-enum ProfKind { PK_RULEBOOK = 0, PK_CONV_TC, PK_CONV_FP32, PK_WGRAD_TC, PK_WGRAD_FP32, PK_BN, PK_IO, PK_COUNT };
+enum ProfKind { PK_RULEBOOK = 0, PK_CONV_TC, PK_CONV_FP32, PK_WGRAD_TC, PK_WGRAD_FP32, PK_BN, PK_IO, PK_CAST, PK_COUNT };
 struct ProfScope {   // no-op unless scn_profile(1) was called
   int slot = -1;
   cudaStream_t s;
@@ -79,12 +79,13 @@ constexpr int COORD_LIMIT = 65535;          // exclusive upper bound on coordina
 constexpr uint64_t EMPTY_KEY = ~0ull;       // never a valid key (batch 65535 is rejected)
 
 // ---- per-tap compacted rule lists of a [V][stride] table: the reference's rulebook (27 lists of (in,out) pairs
-// ordered by out, SubmanifoldRules_cuda.cpp:167-187) in device memory, each list padded to a multiple of 32
+// ordered by out, SubmanifoldRules_cuda.cpp:167-187) in device memory, each list padded to a multiple of PAIR_ITEM
 // rules with an out-of-range index.  gi = table entry (gathered row), si = table column (stationary row).
 constexpr int PAIR_PAD = 0x7F7F7F7F;
+constexpr int PAIR_ITEM = 64;   // rules per pipeline item of the weight-gradient kernel
 struct PairList {
-  DevBuf<int> gi, si;        // [32 * n_items_ub]
-  DevBuf<int> item_off;      // [V+1] first 32-rule item of every tap; item_off[V] = number of items
+  DevBuf<int> gi, si;        // [PAIR_ITEM * n_items_ub]
+  DevBuf<int> item_off;      // [V+1] first item (PAIR_ITEM rules) of every tap; item_off[V] = number of items
   DevBuf<int> blk_item;      // [V][n_blk+1] item holding tap k's first rule whose column is >= b*BLK_ROWS
   int n_blk = 0;
   long long n_items_ub = 0;  // host-side upper bound of item_off[V]
@@ -105,14 +106,12 @@ struct Level {
   // submanifold 3x3x3 neighbour table (output-stationary form of the reference's 27 rule lists)
   DevBuf<int> nbr;           // [27][n_pad], -1 = absent
   long long n_rules = -1;    // sum_k n_k, centre offset included
-  DevBuf<uint32_t> nbr_cm;   // [n_pad/32] per 32-row chunk: bit k set when offset k has a rule in the chunk
   PairList nbr_pairs;        // the same rules as 27 compacted (in, out) lists, built on first weight-gradient use
   // size-2/stride-2 link to the next coarser scale
   Level *coarse = nullptr;
   DevBuf<int> parent;        // [n]   coarse row of every fine row
   DevBuf<uint8_t> off8;      // [n]   (x&1)*4+(y&1)*2+(z&1)
   DevBuf<int> child;         // [8][coarse->n_pad] fine row or -1
-  DevBuf<uint32_t> child_cm; // [coarse->n_pad/32] same for the child table
   PairList child_pairs;      // 8 compacted (fine, coarse) lists
   DevBuf<int> up;            // [8][n_pad]  up[k][i] = parent[i] if off8[i]==k else -1 (one tap per fine row)
 };
@@ -144,7 +143,7 @@ void input_layer_bwd(Meta *m, const float *d_out, int C, float *d_feats, cudaStr
 void output_layer_fwd(Meta *m, const float *in, int C, float *out, cudaStream_t s);
 void output_layer_bwd(Meta *m, const float *d_out, int C, float *d_in, cudaStream_t s);
 
-// conv_simt.cu / conv_tc.cu ---------------------------------------------------------------------------
+// conv_simt.cu / conv_small.cu / conv_tma.cu ---------------------------------------------------------------------------
 // Generic "table convolution".  tbl is [V][stride] (row index or -1).
 //  GATHER : out[o,:]        = sum_k in[tbl[wk(k)][o],:] * Wk      for o in [0,n_rows)
 //  SCATTER: out[tbl[k][p],:] =        in[p,:]            * Wk      for p in [0,n_rows), tbl>=0
@@ -152,7 +151,8 @@ void output_layer_bwd(Meta *m, const float *d_out, int C, float *d_in, cudaStrea
 struct ConvArgs {
   const float *in = nullptr;
   const float *weight = nullptr;   // [V][c_in][c_out] as seen by THIS product (fp32 FMA kernels)
-  const float *weight_nk = nullptr;// [V][c_out][c_in] as seen by THIS product (tensor-core kernels: K-major B operand)
+  const void *weight_nk = nullptr; // [V][c_out][c_in] as seen by THIS product (tensor-core kernel: K-major B operand), fp32 or bf16
+  bool bf16 = false;               // tensor-core kernel: `in` and `weight_nk` are bf16 ([rows][c] uint16), fp32 accumulate and output
   const float *bias = nullptr;     // GATHER only
   float *out = nullptr;
   const int *tbl = nullptr;
@@ -168,13 +168,13 @@ struct ConvArgs {
 void conv_simt(const ConvArgs &a, cudaStream_t s);
 bool conv_small_supported(const ConvArgs &a);
 void conv_small(const ConvArgs &a, cudaStream_t s);   // c_in <= 4: one thread per output row (conv_small.cu)
-bool conv_tc_supported(const ConvArgs &a);
-void conv_tc(const ConvArgs &a, cudaStream_t s);       // cp.async producers (kept for A/B runs: SCN_TC_IMPL=cpasync)
-bool conv_tma_supported(const ConvArgs &a);
-void conv_tma(const ConvArgs &a, cudaStream_t s);      // TMA gather4 producers (default)
+bool conv_tma_supported(const ConvArgs &a);            // tcgen05 + TMA gather4 (conv_tma.cu); a.bf16 selects the operand type
+void conv_tma(const ConvArgs &a, cudaStream_t s);
 
 // weight preparation: dst[k][co][ci] = src[k][ci][co]   (per-tap transpose, used by every dgrad)
 void transpose_weight(const float *src, float *dst, int V, int c_in, int c_out, cudaStream_t s);
+// bf16 operand copies (round to nearest even): dst[i] = bf16(src[i]); n must be even
+void cast_bf16(const float *src, uint16_t *dst, long long n, cudaStream_t s);
 
 // dW[k] = sum_r A[ia(k,r),:]^T * B[ib(k,r),:]    A: [*,c_a], B: [*,c_b], dW: [V][c_a][c_b] (zeroed here)
 //   table_on_a:  ia = tbl[k][r], ib = r      (submanifold / strided conv: A = input, B = d_out)
@@ -191,8 +191,8 @@ struct WgradArgs {
   int c_a = 0, c_b = 0;
   long long n_rules = 0;
   int s_rows = 0;                  // rows of the other ("stationary") matrix
-  const uint32_t *chunk_mask = nullptr;  // [ceil(n_rows/32)] bit k: tap k has a rule inside the 32-row chunk (cp.async variant)
-  // compacted rule lists (TMA variant): see PairList
+  bool bf16 = false;               // a/b are bf16 copies ([rows][c] uint16) instead of fp32
+  // compacted rule lists (tensor-core kernel): see PairList
   const int *gi = nullptr, *si = nullptr, *blk_item = nullptr;
   int n_blk = 0, blk_rows = 0;
   bool table_on_a = true;
@@ -200,8 +200,6 @@ struct WgradArgs {
 void wgrad_simt(const WgradArgs &a, cudaStream_t s);
 bool wgrad_small_supported(const WgradArgs &a);
 void wgrad_small(const WgradArgs &a, cudaStream_t s);
-bool wgrad_tc_supported(const WgradArgs &a);
-void wgrad_tc(const WgradArgs &a, cudaStream_t s);
 bool wgrad_tma_supported(const WgradArgs &a);
 void wgrad_tma(const WgradArgs &a, cudaStream_t s);
 

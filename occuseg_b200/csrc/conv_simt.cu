@@ -258,6 +258,39 @@ void transpose_weight(const float *src, float *dst, int V, int c_in, int c_out, 
   SCN_LAUNCH_CHECK();
 }
 
+// fp32 -> bf16 (round to nearest even), 8 elements per thread
+__global__ void k_cast_bf16(const float *__restrict__ src, uint16_t *__restrict__ dst, long long n8, long long n) {
+  auto cvt2 = [](float lo, float hi) -> uint32_t {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  };
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(src) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(src) + 2 * i + 1);
+    uint4 o;
+    o.x = cvt2(a.x, a.y); o.y = cvt2(a.z, a.w); o.z = cvt2(b.x, b.y); o.w = cvt2(b.z, b.w);
+    reinterpret_cast<uint4 *>(dst)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < n - n8 * 8) {       // tail
+    const long long i = n8 * 8 + threadIdx.x;
+    uint32_t r = cvt2(src[i], 0.f);
+    dst[i] = (uint16_t)(r & 0xFFFFu);
+  }
+}
+
+void cast_bf16(const float *src, uint16_t *dst, long long n, cudaStream_t s) {
+  if (n == 0) return;
+  SCN_CHECK((uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0, "cast_bf16: unaligned buffers");
+  const long long n8 = n / 8;
+  long long g = (n8 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  k_cast_bf16<<<(int)g, 256, 0, s>>>(src, dst, n8, n);
+  SCN_LAUNCH_CHECK();
+}
+
 // -----------------------------------------------------------------------------------------------------
 // weight gradient  dW[k] = sum_r A[ia(k,r)]^T B[ib(k,r)]   (split over row chunks, fp32 atomics to merge)
 // -----------------------------------------------------------------------------------------------------

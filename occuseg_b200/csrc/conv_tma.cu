@@ -43,17 +43,18 @@ static EncodeFn encode_fn() {
   return fn;
 }
 
-// row-major fp32 matrix [rows, cols]; box = box_cols x box_rows elements
-static CUtensorMap make_map(const float *base, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows,
+// row-major fp32 or bf16 matrix [rows, cols]; box = box_cols x box_rows elements
+static CUtensorMap make_map(const void *base, bool bf16, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows,
                             CUtensorMapSwizzle sw) {
   EncodeFn fn = encode_fn();
   SCN_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   CUtensorMap m;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * sizeof(float)};
+  cuuint64_t strides[1] = {cols * (bf16 ? 2 : 4)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+  CUresult r = fn(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base),
+                  dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SCN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
@@ -64,7 +65,6 @@ static CUtensorMap make_map(const float *base, uint64_t cols, uint64_t rows, uin
 constexpr int TM = 128;
 constexpr int KCH = 32;
 constexpr int A_STAGE = TM * 128;
-constexpr int NTHREADS = 160;     // warp 0: TMEM owner + MMA issuer; warps 1-4: table set-up, TMA producers, epilogue (TMEM quarter = warp & 3)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -124,10 +124,36 @@ __device__ __forceinline__ uint64_t desc_mn32(uint32_t saddr, uint32_t lbo) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
 }
-// instruction descriptor (InstrDescriptor): kind::tf32, fp32 accumulate, M=128, N=n; majors: 0 = K, 1 = MN
-__device__ __forceinline__ uint32_t idesc_tf32(int n, uint32_t a_mn, uint32_t b_mn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+// MN-major SWIZZLE_128B (16-bit types): 64-channel blocks `lbo` bytes apart, 8-row K groups 1024 B apart
+__device__ __forceinline__ uint64_t desc_mn128(uint32_t saddr, uint32_t lbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (InstrDescriptor): fp32 accumulate, M=128, N=n; operand format 2 = tf32 (kind::tf32),
+// 1 = bf16 (kind::f16); majors: 0 = K, 1 = MN
+__device__ __forceinline__ uint32_t idesc_make(int n, uint32_t a_mn, uint32_t b_mn, bool bf16) {
+  const uint32_t fmt = bf16 ? 1u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_masked(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accum, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -190,216 +216,286 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 }
 
 // =====================================================================================================
-// forward / dgrad:  out[o,:] = sum_k in[tbl[k][o],:] * W[k]          (output stationary, 128 rows x TN per CTA)
+// forward / dgrad:  out[o,:] = sum_k in[tbl[k][o],:] * W[k]          (output stationary)
+//
+// Persistent CTAs (one per SM).  A tile group = MT consecutive 128-row tiles x TN output channels; its MT fp32
+// accumulators live in TMEM for the whole walk over the taps (double buffered: the epilogue of one group runs
+// under the main loop of the next).  A pipeline item = (group, tap, 32-channel K chunk): ONE [TN x 32] weight
+// tile shared by the MT row tiles, plus the rows each of them needs.  There is no set-up phase: the producer warp
+// that owns an item reads the tap's table row for the group straight from global memory (one coalesced 16-byte
+// load per lane = 128 rows, prefetched one item ahead), votes the present-row bits, and one lane issues the
+// copies.  The bits travel to the MMA thread in shared memory next to the stage and become tcgen05.mma's
+// disable-output-lane mask; taps with no row in the group are passed as empty items.
 // =====================================================================================================
+// warp 0: TMEM + MMA issuer; warps 1 .. nprod*ni: producers (item owner = (warp-1)/ni, share of the item's copies =
+// (warp-1)%ni); the last 4 warps: epilogue (TMEM quarter = warp & 3)
+constexpr int CONV_MAX_THREADS = 32 + 16 * 32 + 128;
+constexpr int MAX_MT = 4;
+
 struct ConvParams {
-  const float *in;
   const float *bias;
   float *out;
   const int *tbl;
-  int tbl_stride, n_rows, in_rows, V, c_in, c_out, mirror;
-  int TN, stages, nprod, b_stage, tmem_cols, prefetch;
-  long long *trace;     // SCN_TRACE=1: per-CTA clock64 breakdown of sampled tiles (debug only)
+  int tbl_stride, n_rows, V, c_in, c_out, mirror;
+  int TN, MT, stages, nprod, ni, b_stage, stage_bytes, tmem_cols, n_groups;
+  int bf16, kelems;            // operand type; elements per 128-byte K chunk (32 tf32 / 64 bf16)
+  unsigned long long *trace;   // SCN_TRACE=1: clock64 totals over all CTAs (debug only): see conv_tma()
 };
-#define TRACE_ON (p.trace != nullptr && (blockIdx.x & 127) == 5 && blockIdx.y == 0)
-#define TRACE_PUT(i, v) do { if (TRACE_ON) p.trace[(blockIdx.x >> 7) * 16 + (i)] = (v); } while (0)
 
-__global__ void __launch_bounds__(NTHREADS) k_conv_tma(const __grid_constant__ CUtensorMap map_x,
-                                                       const __grid_constant__ CUtensorMap map_w, ConvParams p) {
+__global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_constant__ CUtensorMap map_x,
+                                                              const __grid_constant__ CUtensorMap map_w, ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (base - raw);
-  const uint32_t a_base = base;
-  const uint32_t b_base = base + p.stages * A_STAGE;
-  int *s_idx = reinterpret_cast<int *>(smem + p.stages * (A_STAGE + p.b_stage));     // [V][TM] row to fetch
-  uint32_t *s_pm = reinterpret_cast<uint32_t *>(s_idx + p.V * TM);                    // [V][4] present-row bits
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_pm + p.V * 4);
+  uint4 *s_masks = reinterpret_cast<uint4 *>(smem + p.stages * p.stage_bytes);        // [stages][MAX_MT] present-row bits
+  int4 *s_rows = reinterpret_cast<int4 *>(s_masks + 8 * MAX_MT);                       // [16 producer warps][MT][32] rows to fetch
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_rows + 16 * p.MT * 32);
   const uint32_t full_bar = smem_u32(bars);
   const uint32_t empty_bar = full_bar + 8 * p.stages;
-  const uint32_t accum_bar = empty_bar + 8 * p.stages;
-  const uint32_t zero_bar = accum_bar + 8;
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 2);
-  uint32_t *s_mask = s_tmem + 1;
+  const uint32_t accf_bar = empty_bar + 8 * p.stages;       // [2] accumulator buffer complete
+  const uint32_t acce_bar = accf_bar + 16;                  // [2] accumulator buffer drained and zeroed
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 4);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler
-  const int row0 = blockIdx.x * TM;
   const int n0 = blockIdx.y * p.TN;
-  const int KC = p.c_in / KCH;
-  const long long t_entry = clock64();
+  const int KC = p.c_in / p.kelems;
+  const int ipg = p.V * KC;                                   // items per tile group
+  const int G = gridDim.x;
+  const int acc_cols = p.MT * p.TN;
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(full_bar + 8 * s, p.ni);       // every share of an item arrives: no producer warp can fall a phase behind
       mbar_init(empty_bar + 8 * s, 1);
     }
-    mbar_init(accum_bar, 1);
-    mbar_init(zero_bar, 4);
-    *s_mask = 0;
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accf_bar + 8 * b, 1);
+      mbar_init(acce_bar + 8 * b, 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (warp == 0) {
-    tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
-  } else {
-    // Rows to fetch for every tap.  An absent neighbour is never used by the MMA (its accumulator row is
-    // masked), so it is not fetched either: inside a 4-row gather group that has at least one present row the
-    // absent ones repeat a present row of the group (a cache hit), and groups with no present row are skipped.
-    const int e = tid - 32;
-    const int r = row0 + e;
-    const int pw = warp - 1;
-    const int gsh = lane & ~3;
-    uint32_t mine = 0;
-    // all V table entries of this row first (independent loads, one memory latency), then the warp votes
-    int tv[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k)
-      tv[k] = (k < p.V && r < p.n_rows) ? __ldg(&p.tbl[(long long)k * p.tbl_stride + r]) : -1;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      if (k < p.V) {
-        const int t = tv[k];
-        const uint32_t pm = __ballot_sync(0xffffffffu, t >= 0);
-        const uint32_t gm = (pm >> gsh) & 0xFu;
-        const int src = gsh + (gm ? __ffs(gm) - 1 : 0);
-        const int trep = __shfl_sync(0xffffffffu, t, src);
-        s_idx[k * TM + e] = t >= 0 ? t : (gm ? trep : 0);
-        if (lane == 0) s_pm[k * 4 + pw] = pm;
-        mine |= (pm ? 1u : 0u) << k;
-        if (t >= 0 && p.prefetch) {
-          const char *row = reinterpret_cast<const char *>(p.in + (long long)t * p.c_in);
-          for (int b = 0; b < p.c_in * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + b));
-        }
-      }
-    }
-    if (lane == 0 && mine) atomicOr(s_mask, mine);
-  }
+  if (warp == 0) tmem_alloc(s_tmem, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
-  const uint32_t tapmask = *s_mask;
-  if (tid == 0) { TRACE_PUT(0, t_entry); TRACE_PUT(1, clock64() - t_entry); TRACE_PUT(8, (long long)__popc(tapmask) * KC); }
 
   if (warp == 0) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
-      long long w_full = 0;
-      const uint32_t idesc = idesc_tf32(p.TN, 0, 0);
-      mbar_wait(zero_bar, 0);          // the accumulator starts as zeros (every MMA accumulates; rows can be masked from the first tap on)
-      tc_fence_after();
-      uint32_t remaining = tapmask;
-      int s = 0;
+      const uint32_t idesc = idesc_make(p.TN, 0, 0, p.bf16 != 0);
+      int s = 0, gi = 0;
       uint32_t ph = 0;
-      while (remaining) {
-        const int trow = __ffs(remaining) - 1;
-        remaining &= remaining - 1;
-        const uint4 pm = *reinterpret_cast<const uint4 *>(s_pm + trow * 4);
-        for (int kc = 0; kc < KC; ++kc) {
+      long long w_full = 0, w_acc = 0;
+      const long long t_begin = clock64();
+      for (int tg = blockIdx.x; tg < p.n_groups; tg += G, ++gi) {
+        const int buf = gi & 1;
+        const long long ta = clock64();
+        mbar_wait(acce_bar + 8 * buf, (uint32_t)(gi >> 1) & 1u);      // zeroed by the epilogue warps (or at start)
+        w_acc += clock64() - ta;
+        tc_fence_after();
+        const uint32_t acc = tmem + buf * acc_cols;
+        for (int j = 0; j < ipg; ++j) {
           const long long tw = clock64();
           mbar_wait(full_bar + 8 * s, ph);
           w_full += clock64() - tw;
           tc_fence_after();
-          const uint64_t ad = desc_k128(a_base + s * A_STAGE);
-          const uint64_t bd = desc_k128(b_base + s * p.b_stage);
+          const uint32_t st = base + s * p.stage_bytes;
+          const uint64_t bd = desc_k128(st + p.MT * A_STAGE);
+          for (int m = 0; m < p.MT; ++m) {
+            const uint4 pm = s_masks[s * MAX_MT + m];
+            if ((pm.x | pm.y | pm.z | pm.w) == 0u) continue;
+            const uint64_t ad = desc_k128(st + m * A_STAGE);
+            if (p.bf16) {
 #pragma unroll
-          for (int k = 0; k < KCH / 8; ++k)
-            mma_tf32_masked(tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, 1u, ~pm.x, ~pm.y, ~pm.z, ~pm.w);
+              for (int k = 0; k < 4; ++k)        // 4 x (K = 16 bf16 = 32 bytes of every row)
+                mma_bf16_masked(acc + m * p.TN, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, 1u, ~pm.x, ~pm.y, ~pm.z,
+                                ~pm.w);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)        // 4 x (K = 8 tf32 = 32 bytes of every row)
+                mma_tf32_masked(acc + m * p.TN, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, 1u, ~pm.x, ~pm.y, ~pm.z,
+                                ~pm.w);
+            }
+          }
           mma_commit(empty_bar + 8 * s);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
+        mma_commit(accf_bar + 8 * buf);
       }
-      mma_commit(accum_bar);
-      TRACE_PUT(2, w_full); TRACE_PUT(3, clock64() - t_entry);
+      if (p.trace) {
+        atomicAdd(p.trace + 0, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(p.trace + 1, (unsigned long long)w_full);
+        atomicAdd(p.trace + 2, (unsigned long long)w_acc);
+      }
     }
-  } else {
-    const int quarter = warp & 3;                     // TMEM lanes 32*quarter .. +31 belong to this warp
-    const uint32_t tq = tmem + ((uint32_t)(quarter * 32) << 16);
-    for (int c0 = 0; c0 < p.TN; c0 += 32) tmem_zero32(tq + c0);
-    tmem_wait_st();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(zero_bar);
+  } else if (warp <= p.nprod * p.ni) {
     // =========================== TMA producers, item-interleaved ===========================
-    // Producer pw owns items pw, pw+nprod, ... (stages % nprod == 0, so a stage always belongs to the same
-    // producer): it waits for the stage, posts the byte count and issues the weight tile and all gather4 copies
-    // of the item from one thread with the row indices already in registers.
-    const int pw = warp - 1;
-    if (pw < p.nprod && elect_one()) {
-      uint32_t remaining = tapmask;
-      int s = -1, turn = -1;
-      long long w_empty = 0, t_issue = 0;
-      uint32_t ph = 1;                 // parity to wait for on the empty barrier (first pass: already free)
-      while (remaining) {
-        const int trow = __ffs(remaining) - 1;
-        remaining &= remaining - 1;
-        const int wtap = p.mirror ? p.V - 1 - trow : trow;
-        for (int kc = 0; kc < KC; ++kc) {
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
-          if (++turn == p.nprod) turn = 0;
-          if (turn != pw) continue;
-          const uint4 pm = *reinterpret_cast<const uint4 *>(s_pm + trow * 4);
-          const uint32_t pmq[4] = {pm.x, pm.y, pm.z, pm.w};
-          uint32_t nz[4];
-          int groups = 0;
+    // Owner slot pw takes items pw, pw+nprod, ... (nprod <= stages, so a parity wait can never be two phases off);
+    // the ni warps of a slot split the item's copies between them because one thread cannot issue them fast
+    // enough (tools/ubench_pipe.cu); share 0 also posts the byte count, the masks and the weight tile.
+    const int pw = (warp - 1) / p.ni, part = (warp - 1) % p.ni;
+    {
+      int4 *my_rows = s_rows + (warp - 1) * p.MT * 32;
+      const int chunks = p.MT * 4 / p.ni;            // 8-group chunks of this share
+      const int chunk0 = part * chunks;
+      auto load_tbl = [&](int tg, int trow, int4 *dst) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            nz[q] = (pmq[q] | (pmq[q] >> 1) | (pmq[q] >> 2) | (pmq[q] >> 3)) & 0x11111111u;
-            groups += __popc(nz[q]);
+        for (int m = 0; m < MAX_MT; ++m) {
+          if (m < p.MT) {
+            const int row = (tg * p.MT + m) * TM + 4 * lane;
+            dst[m] = row < p.tbl_stride ? __ldg(reinterpret_cast<const int4 *>(p.tbl + (long long)trow * p.tbl_stride + row))
+                                        : make_int4(-1, -1, -1, -1);
           }
+        }
+      };
+      int tg = blockIdx.x, j = pw;
+      while (j >= ipg) { j -= ipg; tg += G; }
+      int s = pw;
+      uint32_t ph = 1;                   // parity to wait for on the empty barrier (first pass: already free)
+      long long w_empty = 0, t_issue = 0, n_items = 0, n_copies = 0;
+      const long long t_begin = clock64();
+      int4 cur[MAX_MT], nxt[MAX_MT];
+#pragma unroll
+      for (int m = 0; m < MAX_MT; ++m) cur[m] = nxt[m] = make_int4(-1, -1, -1, -1);
+      if (tg < p.n_groups) load_tbl(tg, j / KC, cur);
+      while (tg < p.n_groups) {
+        const int trow = j / KC, kc = j - trow * KC;
+        int tg2 = tg, j2 = j + p.nprod;
+        while (j2 >= ipg) { j2 -= ipg; tg2 += G; }
+        if (tg2 < p.n_groups) load_tbl(tg2, j2 / KC, nxt);
+        // present-row bits of every row tile; absent rows repeat a present row of their 4-row gather group
+        uint32_t gm[MAX_MT] = {0, 0, 0, 0}, any = 0;
+        uint4 pm[MAX_MT];
+#pragma unroll
+        for (int m = 0; m < MAX_MT; ++m) {
+          if (m < p.MT) {
+            int4 t = cur[m];
+            const uint32_t nib = (t.x >= 0 ? 1u : 0u) | (t.y >= 0 ? 2u : 0u) | (t.z >= 0 ? 4u : 0u) | (t.w >= 0 ? 8u : 0u);
+            gm[m] = __ballot_sync(0xffffffffu, nib != 0u);
+            const uint32_t sh = nib << (4 * (lane & 7));
+            pm[m].x = __reduce_or_sync(0xffffffffu, (lane >> 3) == 0 ? sh : 0u);
+            pm[m].y = __reduce_or_sync(0xffffffffu, (lane >> 3) == 1 ? sh : 0u);
+            pm[m].z = __reduce_or_sync(0xffffffffu, (lane >> 3) == 2 ? sh : 0u);
+            pm[m].w = __reduce_or_sync(0xffffffffu, (lane >> 3) == 3 ? sh : 0u);
+            const int rep = t.x >= 0 ? t.x : t.y >= 0 ? t.y : t.z >= 0 ? t.z : t.w;
+            t.x = t.x >= 0 ? t.x : rep;
+            t.y = t.y >= 0 ? t.y : rep;
+            t.z = t.z >= 0 ? t.z : rep;
+            t.w = t.w >= 0 ? t.w : rep;
+            my_rows[m * 32 + lane] = t;
+            any |= gm[m];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
           const long long tw = clock64();
           mbar_wait(empty_bar + 8 * s, ph);
           const long long ti = clock64();
           w_empty += ti - tw;
-          mbar_expect_tx(full_bar + 8 * s, (uint32_t)(p.b_stage + groups * 512));
-          tma_tile_2d(b_base + s * p.b_stage, &map_w, kc * KCH, wtap * p.c_out + n0, full_bar + 8 * s);
-          const uint32_t dst = a_base + s * A_STAGE;
-          const int4 *rows4 = reinterpret_cast<const int4 *>(s_idx + trow * TM);
+          ++n_items;
+          const uint32_t st = base + s * p.stage_bytes;
+          if (part == 0) {
+            int groups = 0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (!nz[q]) continue;
+            for (int m = 0; m < MAX_MT; ++m)
+              if (m < p.MT) {
+                s_masks[s * MAX_MT + m] = pm[m];
+                groups += __popc(gm[m]);
+              }
+            mbar_expect_tx(full_bar + 8 * s, any ? (uint32_t)(p.b_stage + groups * 512) : 0u);
+            if (any) {
+              const int wtap = p.mirror ? p.V - 1 - trow : trow;
+              tma_tile_2d(st + p.MT * A_STAGE, &map_w, kc * p.kelems, wtap * p.c_out + n0, full_bar + 8 * s);
+            }
+          }
+          for (int c = chunk0; c < chunk0 + chunks; ++c) {
+            const int m = c >> 2, q = c & 3;
+            uint32_t gmm = gm[0];
+#pragma unroll
+            for (int mm = 1; mm < MAX_MT; ++mm)
+              if (mm == m) gmm = gm[mm];
+            const uint32_t g8 = (gmm >> (8 * q)) & 0xFFu;
+            if (!g8) continue;
+            n_copies += __popc(g8);
             int4 r[8];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) r[g] = rows4[q * 8 + g];
+            for (int g = 0; g < 8; ++g) r[g] = my_rows[c * 8 + g];
 #pragma unroll
             for (int g = 0; g < 8; ++g)
-              if ((nz[q] >> (4 * g)) & 1u)
-                tma_gather4(dst + (q * 8 + g) * 512, &map_x, kc * KCH, r[g].x, r[g].y, r[g].z, r[g].w, full_bar + 8 * s);
+              if ((g8 >> g) & 1u)
+                tma_gather4(st + c * 8 * 512 + g * 512, &map_x, kc * p.kelems, r[g].x, r[g].y, r[g].z, r[g].w, full_bar + 8 * s);
           }
+          if (part != 0) mbar_arrive(full_bar + 8 * s);
           t_issue += clock64() - ti;
         }
-      }
-      if (pw == 0) { TRACE_PUT(4, w_empty); TRACE_PUT(5, clock64() - t_entry); TRACE_PUT(9, t_issue); }
-    }
-    __syncwarp();
-    // =========================== epilogue ===========================
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    if (tid == 32) TRACE_PUT(6, clock64() - t_entry);
-    const int r = row0 + quarter * 32 + lane;
-    float *orow = p.out + (long long)r * p.c_out + n0;
-    for (int c0 = 0; c0 < p.TN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tq + c0, v);
-      if (r < p.n_rows) {
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (p.bias) {
-            o.x += __ldg(&p.bias[n0 + c0 + j]);
-            o.y += __ldg(&p.bias[n0 + c0 + j + 1]);
-            o.z += __ldg(&p.bias[n0 + c0 + j + 2]);
-            o.w += __ldg(&p.bias[n0 + c0 + j + 3]);
+        for (int m = 0; m < MAX_MT; ++m) cur[m] = nxt[m];
+        tg = tg2;
+        j = j2;
+        s += p.nprod;
+        if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
+      }
+      if (p.trace && lane == 0 && pw == 0) {
+        unsigned long long *t = p.trace + 4 + 8 * part;
+        atomicAdd(t + 0, (unsigned long long)(clock64() - t_begin));
+        atomicAdd(t + 1, (unsigned long long)w_empty);
+        atomicAdd(t + 2, (unsigned long long)t_issue);
+        atomicAdd(t + 3, (unsigned long long)n_items);
+        atomicAdd(t + 4, (unsigned long long)n_copies);
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int quarter = warp & 3;                     // TMEM lanes 32*quarter .. +31 belong to this warp
+    const uint32_t tq = tmem + ((uint32_t)(quarter * 32) << 16);
+    for (int c = 0; c < 2 * acc_cols; c += 32) tmem_zero32(tq + c);
+    tmem_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(acce_bar);
+      mbar_arrive(acce_bar + 8);
+    }
+    int gi = 0;
+    for (int tg = blockIdx.x; tg < p.n_groups; tg += G, ++gi) {
+      const int buf = gi & 1;
+      mbar_wait(accf_bar + 8 * buf, (uint32_t)(gi >> 1) & 1u);
+      tc_fence_after();
+      for (int m = 0; m < p.MT; ++m) {
+        const int r = (tg * p.MT + m) * TM + quarter * 32 + lane;
+        float *orow = p.out + (long long)r * p.c_out + n0;
+        for (int c0 = 0; c0 < p.TN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tq + buf * acc_cols + m * p.TN + c0, v);
+          if (r < p.n_rows) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+              if (p.bias) {
+                o.x += __ldg(&p.bias[n0 + c0 + q]);
+                o.y += __ldg(&p.bias[n0 + c0 + q + 1]);
+                o.z += __ldg(&p.bias[n0 + c0 + q + 2]);
+                o.w += __ldg(&p.bias[n0 + c0 + q + 3]);
+              }
+              *reinterpret_cast<float4 *>(orow + c0 + q) = o;
+            }
           }
-          *reinterpret_cast<float4 *>(orow + c0 + j) = o;
         }
       }
+      for (int c = 0; c < acc_cols; c += 32) tmem_zero32(tq + buf * acc_cols + c);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce_bar + 8 * buf);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) TRACE_PUT(7, clock64() - t_entry);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
@@ -425,8 +521,8 @@ static int pick_tn(int c_out) {
 // Both operands are MN-major (the contraction runs over rules = rows), which tcgen05 accepts for tf32 only in
 // the SWIZZLE_128B_BASE32B layout: 32-channel atoms of [32 rules][128 B], 4-rule groups 512 B apart.
 // =====================================================================================================
-constexpr int KR = 32;            // rules (GEMM K) per pipeline item
-constexpr int SUB = KR * 128;     // bytes of one [KR rules x 32 channels] atom
+constexpr int KR = PAIR_ITEM;     // rules (GEMM K) per pipeline item (64)
+constexpr int SUB = KR * 128;     // bytes of one [KR rules x 128 B] channel block (32 tf32 or 64 bf16 channels)
 constexpr int WG_THREADS = 288;   // warp 0: TMEM + MMA; warps 1-4: producers; warps 5-8: epilogue (TMEM quarter = warp & 3)
 
 struct WgParams {
@@ -434,6 +530,7 @@ struct WgParams {
   const int *gi, *si, *blk_item;
   int V, Cg, Cs, transpose_out, n_blk, blk_per_range;
   int N, m_tiles, stages, nprod, stage_bytes, tmem_cols;
+  int bf16, cpb;                    // operand type; channels per 128-byte block (32 tf32 / 64 bf16)
 };
 
 __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tma(const __grid_constant__ CUtensorMap map_g,
@@ -442,8 +539,8 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tma(const __grid_constant_
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (base - raw);
-  int *s_pidx = reinterpret_cast<int *>(smem + p.stages * p.stage_bytes);     // [4 producers][64]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_pidx + 4 * 64);
+  int *s_pidx = reinterpret_cast<int *>(smem + p.stages * p.stage_bytes);     // [4 producers][2 * KR]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_pidx + 4 * 2 * KR);
   const uint32_t full_bar = smem_u32(bars);
   const uint32_t empty_bar = full_bar + 8 * p.stages;
   const uint32_t accum_bar = empty_bar + 8 * p.stages;
@@ -451,7 +548,8 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tma(const __grid_constant_
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int g_atoms = p.Cg >> 5, s_atoms = p.N >> 5;
+  const int g_atoms = p.Cg / p.cpb, s_atoms = p.N / p.cpb;
+  const int apm = 128 / p.cpb;                 // blocks per 128-channel accumulator tile
   const int tap = blockIdx.x;
   const int n0 = blockIdx.z * p.N;
   const int b0 = blockIdx.y * p.blk_per_range;
@@ -478,20 +576,31 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tma(const __grid_constant_
   if (warp == 0) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
-      const uint32_t idesc = idesc_tf32(p.N, 1, 1);
+      const uint32_t idesc = idesc_make(p.N, 1, 1, p.bf16 != 0);
       int s = 0;
       uint32_t ph = 0;
       for (int item = ib; item < ie; ++item) {
         mbar_wait(full_bar + 8 * s, ph);
         tc_fence_after();
         const uint32_t st = base + s * p.stage_bytes;
-        const uint64_t bd = desc_mn32(st + g_atoms * SUB, SUB);
-        for (int mt = 0; mt < p.m_tiles; ++mt) {
-          const uint64_t ad = desc_mn32(st + mt * 4 * SUB, SUB);
+        if (p.bf16) {
+          const uint64_t bd = desc_mn128(st + g_atoms * SUB, SUB);
+          for (int mt = 0; mt < p.m_tiles; ++mt) {
+            const uint64_t ad = desc_mn128(st + mt * apm * SUB, SUB);
 #pragma unroll
-          for (int kk = 0; kk < KR / 8; ++kk)    // K = 8 rules per MMA = two 512-byte K groups of every atom
-            mma_tf32(tmem + mt * p.N, ad + (uint64_t)(kk * 64), bd + (uint64_t)(kk * 64), idesc,
-                     (item > ib || kk) ? 1u : 0u);
+            for (int kk = 0; kk < KR / 16; ++kk)   // K = 16 rules per MMA = two 1024-byte K groups of every block
+              mma_bf16(tmem + mt * p.N, ad + (uint64_t)(kk * 128), bd + (uint64_t)(kk * 128), idesc,
+                       (item > ib || kk) ? 1u : 0u);
+          }
+        } else {
+          const uint64_t bd = desc_mn32(st + g_atoms * SUB, SUB);
+          for (int mt = 0; mt < p.m_tiles; ++mt) {
+            const uint64_t ad = desc_mn32(st + mt * apm * SUB, SUB);
+#pragma unroll
+            for (int kk = 0; kk < KR / 8; ++kk)    // K = 8 rules per MMA = two 512-byte K groups of every block
+              mma_tf32(tmem + mt * p.N, ad + (uint64_t)(kk * 64), bd + (uint64_t)(kk * 64), idesc,
+                       (item > ib || kk) ? 1u : 0u);
+          }
         }
         mma_commit(empty_bar + 8 * s);
         if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -504,43 +613,56 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tma(const __grid_constant_
     // lane 0 waits for the stage, posts the byte count and issues the item's copies.
     const int pw = warp - 1;
     if (pw < p.nprod) {
-      int *my = s_pidx + pw * 64;
+      int *my = s_pidx + pw * 2 * KR;
       int it = ib + pw;
-      int s = pw;                       // stage of item `it` (stages % nprod == 0: a producer cycles over its own stages)
+      int s = pw;                       // stage of item `it`
       uint32_t ph = 1;
-      int g_next = 0, s_next = 0;
+      int g_next[2] = {0, 0}, s_next[2] = {0, 0};
       if (it < ie) {
-        g_next = __ldg(&p.gi[(long long)it * KR + lane]);
-        s_next = __ldg(&p.si[(long long)it * KR + lane]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          g_next[h] = __ldg(&p.gi[(long long)it * KR + h * 32 + lane]);
+          s_next[h] = __ldg(&p.si[(long long)it * KR + h * 32 + lane]);
+        }
       }
       for (; it < ie; it += p.nprod) {
-        my[lane] = g_next;
-        my[32 + lane] = s_next;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          my[h * 32 + lane] = g_next[h];
+          my[KR + h * 32 + lane] = s_next[h];
+        }
         if (it + p.nprod < ie) {
-          g_next = __ldg(&p.gi[(long long)(it + p.nprod) * KR + lane]);
-          s_next = __ldg(&p.si[(long long)(it + p.nprod) * KR + lane]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            g_next[h] = __ldg(&p.gi[(long long)(it + p.nprod) * KR + h * 32 + lane]);
+            s_next[h] = __ldg(&p.si[(long long)(it + p.nprod) * KR + h * 32 + lane]);
+          }
         }
         __syncwarp();
         if (lane == 0) {
-          int4 rg[8], rs[8];
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            rg[g] = reinterpret_cast<const int4 *>(my)[g];
-            rs[g] = reinterpret_cast<const int4 *>(my + 32)[g];
-          }
           mbar_wait(empty_bar + 8 * s, ph);
           mbar_expect_tx(full_bar + 8 * s, (uint32_t)p.stage_bytes);
           const uint32_t dst = base + s * p.stage_bytes;
-          for (int a = 0; a < g_atoms; ++a) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              tma_gather4(dst + a * SUB + g * 512, &map_g, a * 32, rg[g].x, rg[g].y, rg[g].z, rg[g].w, full_bar + 8 * s);
-          }
-          for (int a = 0; a < s_atoms; ++a) {
+          for (int h = 0; h < 2; ++h) {            // 8 gather groups (32 rules) at a time
+            int4 rg[8], rs[8];
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              tma_gather4(dst + (g_atoms + a) * SUB + g * 512, &map_s, n0 + a * 32, rs[g].x, rs[g].y, rs[g].z, rs[g].w,
-                          full_bar + 8 * s);
+            for (int g = 0; g < 8; ++g) {
+              rg[g] = reinterpret_cast<const int4 *>(my)[h * 8 + g];
+              rs[g] = reinterpret_cast<const int4 *>(my + KR)[h * 8 + g];
+            }
+            for (int a = 0; a < g_atoms; ++a) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                tma_gather4(dst + a * SUB + (h * 8 + g) * 512, &map_g, a * p.cpb, rg[g].x, rg[g].y, rg[g].z, rg[g].w,
+                            full_bar + 8 * s);
+            }
+            for (int a = 0; a < s_atoms; ++a) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                tma_gather4(dst + (g_atoms + a) * SUB + (h * 8 + g) * 512, &map_s, n0 + a * p.cpb, rs[g].x, rs[g].y, rs[g].z,
+                            rs[g].w, full_bar + 8 * s);
+            }
           }
         }
         s += p.nprod;
@@ -590,7 +712,8 @@ static int env_int(const char *name, int dflt) {
 }
 
 bool conv_tma_supported(const ConvArgs &a) {
-  return !a.scatter && a.c_in >= 32 && a.c_in % 32 == 0 && a.c_out >= 32 && a.c_out % 32 == 0 && a.V <= 32 &&
+  const int kel = a.bf16 ? 64 : 32;
+  return !a.scatter && a.c_in >= kel && a.c_in % kel == 0 && a.c_out >= 32 && a.c_out % 32 == 0 && a.V <= 32 &&
          tma::pick_tn(a.c_out) > 0 && a.in_rows > 0 && ((uintptr_t)a.in % 16 == 0) && ((uintptr_t)a.out % 16 == 0);
 }
 
@@ -599,59 +722,80 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   SCN_CHECK(a.weight_nk != nullptr, "conv_tma needs the [V][Cout][Cin] weight layout");
   if (a.n_rows == 0) return;
   ConvParams p;
-  static const int prefetch = env_int("SCN_CONV_PREFETCH", 1);
-  p.prefetch = prefetch;
-  p.in = a.in; p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
-  p.in_rows = a.in_rows; p.V = a.V; p.c_in = a.c_in; p.c_out = a.c_out; p.mirror = a.mirror ? 1 : 0;
+  p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
+  p.V = a.V; p.c_in = a.c_in; p.c_out = a.c_out; p.mirror = a.mirror ? 1 : 0;
+  p.bf16 = a.bf16 ? 1 : 0;
+  p.kelems = a.bf16 ? 64 : 32;
   p.TN = pick_tn(a.c_out);
   p.b_stage = p.TN * 128;
-  const int stage = A_STAGE + p.b_stage;
-  const int fixed = 1024 + a.V * TM * (int)sizeof(int) + a.V * 16 + 8 * (2 * 8 + 2) + 64;
-  // two CTAs per SM (one's epilogue and table set-up overlap the other's main loop) when that leaves >= 3 stages
-  static const int force_ctas = env_int("SCN_CONV_CTAS", 0);
-  int budget = 113 * 1024;
-  if (force_ctas == 1 || (force_ctas == 0 && (budget - fixed) / stage < 3)) budget = 225 * 1024;
-  int st = (budget - fixed) / stage;
-  st = st >= 8 ? 8 : st >= 6 ? 6 : st >= 4 ? 4 : st >= 3 ? 3 : 2;
+  // row tiles per group: as many as two TMEM accumulator buffers allow (the weight tile of an item is shared by them)
+  static const int force_mt = env_int("SCN_CONV_MT", 0);
+  int mt = 512 / (2 * p.TN);
+  if (mt > 2) mt = 2;
+  if (force_mt > 0) mt = force_mt;
+  if (mt > MAX_MT) mt = MAX_MT;
+  while (mt > 1 && 2 * mt * p.TN > 512) --mt;
+  if (mt < 1) mt = 1;
+  const int tiles = (a.n_rows + TM - 1) / TM;
+  if (tiles < mt * sm_count()) mt = 1;                 // small levels: more, smaller groups keep every SM busy
+  p.MT = mt;
+  p.stage_bytes = p.MT * A_STAGE + p.b_stage;
+  const int fixed = 1024 + 8 * MAX_MT * 16 + 16 * p.MT * 32 * 16 + 8 * (2 * 8 + 4) + 64;
+  int st = (225 * 1024 - fixed) / p.stage_bytes;
+  if (st > 8) st = 8;
+  SCN_CHECK(st >= 2, "conv_tma: shared memory budget");
   p.stages = st;
-  p.nprod = st % 4 == 0 ? 4 : st % 3 == 0 ? 3 : 2;
+  p.nprod = st < 4 ? st : 4;
+  static const int force_ni = env_int("SCN_CONV_NI", 0);
+  p.ni = force_ni > 0 ? force_ni : 4;
+  while (p.ni > 1 && ((p.MT * 4) % p.ni != 0 || p.nprod * p.ni > 16)) p.ni >>= 1;
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.TN) p.tmem_cols <<= 1;
-  const size_t smem = (size_t)fixed + (size_t)p.stages * stage;
-  CUtensorMap mx = make_map(a.in, (uint64_t)a.c_in, (uint64_t)a.in_rows, KCH, 1, CU_TENSOR_MAP_SWIZZLE_128B);
-  CUtensorMap mw = make_map(a.weight_nk, (uint64_t)a.c_in, (uint64_t)a.V * a.c_out, KCH, (uint32_t)p.TN,
+  while (p.tmem_cols < 2 * p.MT * p.TN) p.tmem_cols <<= 1;
+  p.n_groups = (tiles + p.MT - 1) / p.MT;
+  const size_t smem = (size_t)fixed + (size_t)p.stages * p.stage_bytes;
+  CUtensorMap mx = make_map(a.in, a.bf16, (uint64_t)a.c_in, (uint64_t)a.in_rows, p.kelems, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap mw = make_map(a.weight_nk, a.bf16, (uint64_t)a.c_in, (uint64_t)a.V * a.c_out, p.kelems, (uint32_t)p.TN,
                             CU_TENSOR_MAP_SWIZZLE_128B);
   static size_t configured = 0;
   if (smem > configured) {
     SCN_CUDA(cudaFuncSetAttribute(k_conv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  dim3 grid((a.n_rows + TM - 1) / TM, a.c_out / p.TN);
+  const int n_tiles_n = a.c_out / p.TN;
+  int gx = sm_count() / n_tiles_n;
+  if (gx < 1) gx = 1;
+  if (gx > p.n_groups) gx = p.n_groups;
+  dim3 grid(gx, n_tiles_n);
   static const int trace = env_int("SCN_TRACE", 0);
   p.trace = nullptr;
-  const int n_tr = (int)(grid.x >> 7);
-  if (trace && n_tr > 0) {
-    SCN_CUDA(cudaMalloc((void **)&p.trace, sizeof(long long) * 16 * (n_tr + 1)));
-    SCN_CUDA(cudaMemset(p.trace, 0, sizeof(long long) * 16 * (n_tr + 1)));
+  if (trace) {
+    SCN_CUDA(cudaMalloc((void **)&p.trace, 8 * 64));
+    SCN_CUDA(cudaMemset(p.trace, 0, 8 * 64));
   }
-  k_conv_tma<<<grid, NTHREADS, smem, s>>>(mx, mw, p);
+  k_conv_tma<<<grid, 32 + 32 * p.nprod * p.ni + 128, smem, s>>>(mx, mw, p);
   SCN_LAUNCH_CHECK();
   if (p.trace) {
-    std::vector<long long> h(16 * (n_tr + 1));
+    unsigned long long h[64];
     SCN_CUDA(cudaStreamSynchronize(s));
-    SCN_CUDA(cudaMemcpy(h.data(), p.trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    SCN_CUDA(cudaMemcpy(h, p.trace, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(p.trace);
-    double m[16] = {0};
-    for (int i = 0; i < n_tr; ++i) for (int j = 1; j < 16; ++j) m[j] += (double)h[i * 16 + j] / n_tr;
-    fprintf(stderr, "[conv trace] rows %d C %d->%d TN %d stages %d nprod %d | tiles sampled %d: setup %.0f, items %.1f, "
-            "mma wait-full %.0f, mma done %.0f | prod0 wait-empty %.0f, issue %.0f, done %.0f | accum %.0f, end %.0f clk\n",
-            a.n_rows, a.c_in, a.c_out, p.TN, p.stages, p.nprod, n_tr, m[1], m[8], m[2], m[3], m[4], m[9], m[5], m[6], m[7]);
+    const double n = (double)grid.x * grid.y;
+    fprintf(stderr, "[conv trace] rows %d C %d->%d V %d TN %d MT %d stages %d nprod %d ni %d ctas %.0f | per CTA: mma loop %.0f clk, "
+            "wait-full %.0f, wait-acc %.0f |", a.n_rows, a.c_in, a.c_out, a.V, p.TN, p.MT, p.stages, p.nprod, p.ni, n, h[0] / n,
+            h[1] / n, h[2] / n);
+    for (int q = 0; q < p.ni; ++q) {
+      const unsigned long long *t = h + 4 + 8 * q;
+      fprintf(stderr, " share%d: loop %.0f wait-empty %.0f issue %.0f items %.0f copies %.0f |", q, t[0] / n, t[1] / n, t[2] / n,
+              t[3] / n, t[4] / n);
+    }
+    fprintf(stderr, "\n");
   }
 }
 
 bool wgrad_tma_supported(const WgradArgs &a) {
   const int cg = a.table_on_a ? a.c_a : a.c_b, cs = a.table_on_a ? a.c_b : a.c_a;
-  return a.gi != nullptr && a.g_rows > 0 && a.s_rows > 0 && cg >= 32 && cg % 32 == 0 && cs >= 32 && cs % 32 == 0 &&
+  const int cpb = a.bf16 ? 64 : 32;
+  return a.gi != nullptr && a.g_rows > 0 && a.s_rows > 0 && cg >= cpb && cg % cpb == 0 && cs >= cpb && cs % cpb == 0 &&
          a.V <= 32 && ((uintptr_t)a.a % 16 == 0) && ((uintptr_t)a.b % 16 == 0);
 }
 
@@ -662,29 +806,31 @@ void wgrad_tma(const WgradArgs &a, cudaStream_t s) {
   WgParams p;
   const float *G = a.table_on_a ? a.a : a.b;
   const float *S = a.table_on_a ? a.b : a.a;
+  p.bf16 = a.bf16 ? 1 : 0;
+  p.cpb = a.bf16 ? 64 : 32;
   p.Cg = a.table_on_a ? a.c_a : a.c_b;
   p.Cs = a.table_on_a ? a.c_b : a.c_a;
   p.transpose_out = a.table_on_a ? 0 : 1;
   p.dw = a.dw; p.gi = a.gi; p.si = a.si; p.blk_item = a.blk_item; p.V = a.V; p.n_blk = a.n_blk;
   p.m_tiles = (p.Cg + 127) / 128;
   p.N = 0;
-  for (int n = 256; n >= 32; n -= 32)
+  for (int n = 256; n >= p.cpb; n -= p.cpb)
     if (p.Cs % n == 0 && p.m_tiles * n <= 512) { p.N = n; break; }
   SCN_CHECK(p.N > 0, "wgrad_tma: no N tile");
   p.tmem_cols = 32;
   while (p.tmem_cols < p.m_tiles * p.N) p.tmem_cols <<= 1;
   // every stage holds the item's G atoms, then its S atoms; an accumulator tile always spans 4 G atoms, so the
   // last tile of a Cg that is not a multiple of 128 reads on into the S atoms (finite data; rows >= Cg are ignored)
-  p.stage_bytes = (p.Cg / 32 + p.N / 32) * SUB;
-  const int fixed = 1024 + 4 * 64 * 4 + 8 * (2 * 8 + 1) + 64;
-  const int tail = p.m_tiles * 128 > p.Cg ? 4 * SUB : 0;
+  p.stage_bytes = (p.Cg / p.cpb + p.N / p.cpb) * SUB;
+  const int fixed = 1024 + 4 * 2 * KR * 4 + 8 * (2 * 8 + 1) + 64;
+  const int tail = p.m_tiles * 128 > p.Cg ? (128 / p.cpb) * SUB : 0;
   int budget = 113 * 1024;
   if (512 / p.tmem_cols < 2 || (budget - fixed - tail) / p.stage_bytes < 3) budget = 225 * 1024;
   int st = (budget - fixed - tail) / p.stage_bytes;
   SCN_CHECK(st >= 2, "wgrad_tma: shared memory budget");
-  st = st >= 8 ? 8 : st >= 6 ? 6 : st >= 4 ? 4 : st >= 3 ? 3 : 2;
+  if (st > 8) st = 8;
   p.stages = st;
-  p.nprod = st % 4 == 0 ? 4 : st % 3 == 0 ? 3 : 2;
+  p.nprod = st < 4 ? st : 4;
   const size_t smem = (size_t)fixed + (size_t)p.stages * p.stage_bytes + tail;
   // row range per CTA: about 8 MB of G + S rows, so the ranges in flight (SMs x CTAs/SM / V of them) fit in L2
   static const int range_kb = env_int("SCN_WG_RANGE_KB", 8192);
@@ -693,8 +839,9 @@ void wgrad_tma(const WgradArgs &a, cudaStream_t s) {
   if (bpr < 1) bpr = 1;
   p.blk_per_range = bpr;
   const int ranges = (a.n_blk + bpr - 1) / bpr;
-  CUtensorMap mg = make_map(G, (uint64_t)p.Cg, (uint64_t)a.g_rows, 32, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  CUtensorMap ms = make_map(S, (uint64_t)p.Cs, (uint64_t)a.s_rows, 32, 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  const CUtensorMapSwizzle sw = a.bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  CUtensorMap mg = make_map(G, a.bf16, (uint64_t)p.Cg, (uint64_t)a.g_rows, p.cpb, 1, sw);
+  CUtensorMap ms = make_map(S, a.bf16, (uint64_t)p.Cs, (uint64_t)a.s_rows, p.cpb, 1, sw);
   static size_t configured = 0;
   if (smem > configured) {
     SCN_CUDA(cudaFuncSetAttribute(k_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -159,25 +159,12 @@ __global__ void k_neighbours(const uint64_t *__restrict__ keys, int n, int strid
   if (threadIdx.x == 0 && total) atomicAdd(n_rules, (unsigned long long)total);
 }
 
-// per 32-row chunk of a [V][stride] table: bit k <=> some row of the chunk has an entry at tap k
-__global__ void k_chunk_masks(const int *__restrict__ tbl, int stride, int V, int n_chunks, uint32_t *__restrict__ out) {
-  int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (chunk >= n_chunks) return;
-  int lane = threadIdx.x & 31;
-  uint32_t m = 0;
-  for (int k = 0; k < V; ++k) {
-    int t = tbl[(long long)k * stride + chunk * 32 + lane];
-    if (__any_sync(0xffffffffu, t >= 0)) m |= 1u << k;
-  }
-  if (lane == 0) out[chunk] = m;
-}
-
 // ---- per-tap compaction of a [V][stride] table into padded (entry, column) lists ------------------------------
 struct IsRule {
   __host__ __device__ int operator()(const int &t) const { return t >= 0 ? 1 : 0; }
 };
 // rank[i] = number of rules before flat position i.  One thread block: tap k owns rules rank[k*stride] ..
-// rank[(k+1)*stride]-1; its list starts at item_off[k] (32 rules per item, every tap rounded up).
+// rank[(k+1)*stride]-1; its list starts at item_off[k] (PAIR_ITEM rules per item, every tap rounded up).
 __global__ void k_pair_offsets(const int *__restrict__ tbl, const int *__restrict__ rank, int V, int stride,
                                int *__restrict__ item_off, int *__restrict__ rank_base) {
   if (threadIdx.x != 0) return;
@@ -189,7 +176,7 @@ __global__ void k_pair_offsets(const int *__restrict__ tbl, const int *__restric
     const int e = (k + 1 < V) ? rank[(long long)(k + 1) * stride] : total;
     item_off[k] = items;
     rank_base[k] = b;
-    items += (e - b + 31) / 32;
+    items += (e - b + PAIR_ITEM - 1) / PAIR_ITEM;
   }
   item_off[V] = items;
 }
@@ -201,7 +188,7 @@ __global__ void k_block_items(const int *__restrict__ rank, int V, int stride, i
   const int k = i / (n_blk + 1), b = i - k * (n_blk + 1);
   const long long col = (long long)b * blk_rows;
   blk_item[i] = (b == n_blk || col >= stride) ? item_off[k + 1]
-                                              : item_off[k] + (rank[(long long)k * stride + col] - rank_base[k]) / 32;
+                                              : item_off[k] + (rank[(long long)k * stride + col] - rank_base[k]) / PAIR_ITEM;
 }
 __global__ void k_scatter_pairs(const int *__restrict__ tbl, const int *__restrict__ rank, long long n_flat, int stride,
                                 const int *__restrict__ item_off, const int *__restrict__ rank_base,
@@ -212,7 +199,7 @@ __global__ void k_scatter_pairs(const int *__restrict__ tbl, const int *__restri
   if (t < 0) return;
   const int k = (int)(i / stride);
   const int col = (int)(i - (long long)k * stride);
-  const long long pos = (long long)item_off[k] * 32 + (rank[i] - rank_base[k]);
+  const long long pos = (long long)item_off[k] * PAIR_ITEM + (rank[i] - rank_base[k]);
   gi[pos] = t;
   si[pos] = col;
 }
@@ -281,9 +268,9 @@ void build_pair_list(PairList &out, const int *tbl, int V, int stride, long long
   if (out.item_off.p) return;
   const long long n_flat = (long long)V * stride;
   SCN_CHECK(n_flat > 0 && n_flat < (1ll << 31), "rule table too large for 32-bit ranks");
-  out.n_items_ub = (n_rules + 31ll * V) / 32 + 1;
-  out.gi.alloc((size_t)out.n_items_ub * 32, s);
-  out.si.alloc((size_t)out.n_items_ub * 32, s);
+  out.n_items_ub = (n_rules + (long long)(PAIR_ITEM - 1) * V) / PAIR_ITEM + 1;
+  out.gi.alloc((size_t)out.n_items_ub * PAIR_ITEM, s);
+  out.si.alloc((size_t)out.n_items_ub * PAIR_ITEM, s);
   out.item_off.alloc(V + 1, s);
   SCN_CUDA(cudaMemsetAsync(out.gi.p, 0x7F, sizeof(int) * out.gi.n, s));   // PAIR_PAD
   SCN_CUDA(cudaMemsetAsync(out.si.p, 0x7F, sizeof(int) * out.si.n, s));
@@ -409,9 +396,6 @@ void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
                                                      L->nbr.p, cnt.p);
     SCN_LAUNCH_CHECK();
   }
-  L->nbr_cm.alloc(L->n_pad / 32, s);
-  k_chunk_masks<<<grid_for(L->n_pad / 32, 8), 256, 0, s>>>(L->nbr.p, L->n_pad, 27, L->n_pad / 32, L->nbr_cm.p);
-  SCN_LAUNCH_CHECK();
   unsigned long long h = 0;
   SCN_CUDA(cudaMemcpyAsync(&h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, s));
   SCN_CUDA(cudaStreamSynchronize(s));   // once per scale per batch: the MAC count is part of the API
@@ -452,9 +436,6 @@ Level *ensure_coarse_level(Meta *m, Level *F, const int64_t coarse_size[3], cuda
   SCN_LAUNCH_CHECK();
   k_link_levels<<<grid_for(C->n, 256), 256, 0, s>>>(runs.ptr.p, runs.sorted_idx.p, F->keys.p, C->n, C->n_pad,
                                                     F->parent.p, F->off8.p, F->child.p, F->n_pad, F->up.p);
-  SCN_LAUNCH_CHECK();
-  F->child_cm.alloc(C->n_pad / 32, s);
-  k_chunk_masks<<<grid_for(C->n_pad / 32, 8), 256, 0, s>>>(F->child.p, C->n_pad, 8, C->n_pad / 32, F->child_cm.p);
   SCN_LAUNCH_CHECK();
   F->coarse = C;
   m->levels.push_back(C);

@@ -16,12 +16,13 @@ import torch
 
 from .. import _lib
 
-_PRECISIONS = {"fp32": _lib.FP32, "tf32": _lib.TF32}
-_precision = _PRECISIONS[os.environ.get("SCN_B200_PRECISION", "tf32").lower()]
+_PRECISIONS = {"fp32": _lib.FP32, "tf32": _lib.TF32, "bf16": _lib.BF16}
+_precision = _PRECISIONS[os.environ.get("SCN_B200_PRECISION", "bf16").lower()]
 
 
 def set_precision(name):
-    """'fp32' = exact FMA path everywhere; 'tf32' = tcgen05 tiles (fp32 accumulate) where channels allow."""
+    """'fp32' = exact FMA path everywhere; 'tf32' / 'bf16' = tcgen05 tiles (tf32 operands / bf16 copies of the
+    operands, fp32 accumulate and fp32 results) where the channel counts allow, exact fp32 elsewhere."""
     global _precision
     _precision = _PRECISIONS[name.lower()]
 
@@ -287,7 +288,7 @@ def BatchNormalization_backward(input_features, d_input_features, output_feature
 class _gemm_precision:
     def __enter__(self):
         self.prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = _precision == _lib.TF32
+        torch.backends.cuda.matmul.allow_tf32 = _precision != _lib.FP32
 
     def __exit__(self, *exc):
         torch.backends.cuda.matmul.allow_tf32 = self.prev

@@ -2,7 +2,7 @@
  (a) the committed golden vectors = outputs of the reference's own CPU code (tests/golden/make_golden.py),
  (b) the oracle on seeded scenes at sizes it finishes in seconds,
  (c) size-independent properties at BASELINE.json's full sizes.
-Tolerances (max-norm relative, conftest.rel_err): fp32 path 1e-5; tf32 tensor-core tiles 2e-2 (north_star).
+Tolerances (max-norm relative, conftest.rel_err): fp32 path 1e-5; tf32 / bf16 tensor-core tiles 2e-2 (north_star).
 Integer results (row order, rulebooks, MAC counts) must be bit-exact."""
 import numpy as np
 import pytest
@@ -131,7 +131,7 @@ def _subm(m, x, w, g, size=SIZE):
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_convolutions_match_reference_outputs(name, precision):
     g = load_golden(name)
     tol = FP32_TOL if precision == "fp32" else TF32_TOL
@@ -163,7 +163,7 @@ def test_convolutions_match_reference_outputs(name, precision):
         assert rel_err(dxd.cpu().numpy(), g["dxd"]) < tol
         assert rel_err(dwd.cpu().numpy(), g["dwd"]) < tol
     finally:
-        scn.set_precision("tf32")
+        scn.set_precision("bf16")
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
@@ -224,7 +224,8 @@ def test_io_layers_roundtrip_and_grads():
 
 # ---------------------------------------------------------------------------------------- config 1 + properties
 @pytest.mark.parametrize("precision,cin,cout", [("fp32", 16, 16), ("fp32", 3, 32), ("tf32", 32, 32), ("tf32", 64, 64),
-                                                ("tf32", 128, 64), ("tf32", 64, 96)])
+                                                ("tf32", 128, 64), ("tf32", 64, 96), ("bf16", 64, 64), ("bf16", 128, 64),
+                                                ("bf16", 64, 192), ("bf16", 320, 128), ("bf16", 64, 96)])
 def test_submanifold_on_scene_vs_oracle(precision, cin, cout):
     """BASELINE.json config 1 shape (100k-voxel scene, 3x3x3, 16->16) plus the tensor-core channel shapes."""
     tol = FP32_TOL if precision == "fp32" else TF32_TOL
@@ -242,13 +243,13 @@ def test_submanifold_on_scene_vs_oracle(precision, cin, cout):
         _lib.profile(True)
         y, macs, dx, dw = _subm(m, cu(x), cu(w), cu(go))
     finally:
-        scn.set_precision("tf32")
+        scn.set_precision("bf16")
     y0, macs0 = arith.rule_conv_forward(x, w, rules, N)
     dx0, dw0 = arith.rule_conv_backward(x, go, w, rules)
     assert macs == macs0
     prof = _lib.profile_read()
     _lib.profile(False)
-    if precision == "tf32":      # the tcgen05 kernels really ran (forward + dgrad), no silent fp32 substitute
+    if precision != "fp32":      # the tcgen05 kernels really ran (forward + dgrad), no silent fp32 substitute
         assert prof["conv_tc"]["launches"] >= 2 and prof["conv_fp32"]["launches"] == 0, prof
         assert prof["wgrad_tc"]["launches"] >= 1 and prof["wgrad_fp32"]["launches"] == 0, prof
     else:
@@ -272,7 +273,11 @@ def test_full_size_properties():
     x = torch.randn(N, C, device="cuda", generator=gen)
     g = torch.randn(N, C, device="cuda", generator=gen)
     w = torch.randn(27, C, C, device="cuda", generator=gen) * 0.05
-    for precision, tol in (("fp32", 1e-4), ("tf32", TF32_TOL)):
+    for precision, tol, C in (("fp32", 1e-4, 32), ("tf32", TF32_TOL, 32), ("bf16", TF32_TOL, 64)):
+        if x.shape[1] != C:
+            x = torch.randn(N, C, device="cuda", generator=gen)
+            g = torch.randn(N, C, device="cuda", generator=gen)
+            w = torch.randn(27, C, C, device="cuda", generator=gen) * 0.05
         scn.set_precision(precision)
         try:
             y, macs, dx, dw = _subm(m, x, w, g)
@@ -282,12 +287,14 @@ def test_full_size_properties():
             wc[13] = w[13]
             yc = _subm(m, x, wc, g)[0]
             assert rel_err(yc.cpu().numpy(), (x @ w[13]).cpu().numpy()) < max(tol, 2e-3)  # torch.mm may use tf32
+            if precision == "bf16":
+                assert rel_err(y2.cpu().numpy(), (2 * y).cpu().numpy()) == 0.0
             a = (y.double() * g.double()).sum().item()
             b = (x.double() * dx.double()).sum().item()
             c = (w.double() * dw.double()).sum().item()
             assert abs(a - b) / abs(a) < tol and abs(a - c) / abs(a) < tol
         finally:
-            scn.set_precision("tf32")
+            scn.set_precision("bf16")
     nbr, n_rules = m.submanifoldNeighbourTable(lt(SIZE))
     nbr = nbr.numpy()
     # symmetry of the rule relation: nbr[26-k][nbr[k][o]] == o

@@ -195,6 +195,66 @@ __global__ void k_gather_il(const __grid_constant__ CUtensorMap map, const int *
   if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
 }
 
+// ---------------------------------------------------------------------------------------------- 4. tcgen05.mma issue / execution rate
+// one thread issues `n` MMAs (M=128, N=n_cols, one K step of 32 bytes per row) from shared memory, commit every 4, waits at the end
+__device__ __forceinline__ uint64_t desc_k128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+template <int KIND>   // 0 tf32, 1 bf16
+__global__ void k_mma_rate(int n, int n_cols, int masked, int n_cta_stages, long long *out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t s_tmem;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < 48 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem_raw + (base - raw))[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+  long long t0 = 0, t1 = 0, t2 = 0;
+  if (threadIdx.x == 0) {
+    // idesc: c fp32 (1<<4); a/b format: tf32 = 2, bf16 = 1 at bits 7 and 10; N>>3 at 17; M>>4 at 24
+    const uint32_t fmt = KIND == 0 ? 2u : 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t mk = masked ? 0x0F0F0F0Fu : 0u;
+    t0 = clock64();
+    for (int i = 0; i < n; ++i) {
+      const uint32_t st = base + (i % n_cta_stages) * 0;     // same stage: execution rate, not data movement
+      const uint64_t ad = desc_k128(st) + (uint64_t)((i & 3) * 2);
+      const uint64_t bd = desc_k128(st + 16384) + (uint64_t)((i & 3) * 2);
+      if (KIND == 0)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                     ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(1u), "r"(mk) : "memory");
+      else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                     ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(1u), "r"(mk) : "memory");
+      if ((i & 3) == 3) mma_commit(smem_u32(&bar) + 0 * 8);
+    }
+    t1 = clock64();
+  }
+  __syncthreads();
+  // drain: wait until the tensor pipe is idle (commit phases completed = n/4; just spin on time via a final commit)
+  if (threadIdx.x == 0) {
+    // parity of the (n/4)-th completion
+    mbar_wait(smem_u32(&bar), ((n / 4) - 1) & 1);
+    t2 = clock64();
+    out[blockIdx.x * 2] = t1 - t0;
+    out[blockIdx.x * 2 + 1] = t2 - t0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -211,6 +271,26 @@ int main() {
       CK(cudaMemcpy(h.data(), d_out, 148 * 8, cudaMemcpyDeviceToHost));
       printf("mode %s stages %d: %.1f clk/item\n", mode ? "tcgen05.commit" : "arrive", stages, (double)h[0] / items);
     }
+
+  {
+    long long *d2; CK(cudaMalloc(&d2, 148 * 16));
+    std::vector<long long> h2(296);
+    CK(cudaFuncSetAttribute(k_mma_rate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(k_mma_rate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    printf("== tcgen05.mma SS, M=128, K step = 32 B/row, 148 CTAs: clk per MMA (issue loop / until complete)\n");
+    for (int kind = 0; kind < 2; ++kind)
+      for (int ncols : {64, 128, 256})
+        for (int masked = 0; masked < 2; ++masked) {
+          const int n = 4096;
+          if (kind == 0) k_mma_rate<0><<<148, 128, 50 * 1024>>>(n, ncols, masked, 1, d2);
+          else k_mma_rate<1><<<148, 128, 50 * 1024>>>(n, ncols, masked, 1, d2);
+          CK(cudaDeviceSynchronize());
+          CK(cudaMemcpy(h2.data(), d2, 148 * 16, cudaMemcpyDeviceToHost));
+          printf("  %s N=%3d %s: issue %.1f clk/MMA, complete %.1f clk/MMA\n", kind ? "bf16" : "tf32", ncols,
+                 masked ? "masked  " : "unmasked", (double)h2[0] / n, (double)h2[1] / n);
+        }
+  }
+  if (getenv("UBENCH_MMA_ONLY")) return 0;
 
   // ---- gather4
   void *fn = nullptr; cudaDriverEntryPointQueryResult q;
