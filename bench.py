@@ -213,15 +213,19 @@ def run_ours(args):
         dist.all_reduce(vox)
     total_voxels = float(vox.item())
 
-    # ---- timed region 1: inputs resident in HBM
+    # ---- timed region 1: inputs resident in HBM (no per-launch instrumentation inside)
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = _lib.launch_count()
-    _lib.profile(True)
     ms = timed(lambda: step(coords_dev, feats_dev), args.steps)
-    prof = _lib.profile_read()
-    _lib.profile(False)
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
+
+    # ---- the same steps again with CUDA events around every library launch: per-kernel-family times for the
+    # roofline line (the events cost a few ms per step, which is why this pass is not the one that is reported)
+    _lib.profile(True)
+    ms_prof = timed(lambda: step(coords_dev, feats_dev), args.steps)
+    prof = _lib.profile_read()
+    _lib.profile(False)
 
     # ---- timed region 2: end to end from pinned host buffers, loss read back every step
     def e2e_step():
@@ -257,7 +261,7 @@ def run_ours(args):
                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "launches": t["launches"], "avg_launch_ms": per_launch_ms,
                     "algorithmic_bytes_per_launch": t["bytes"] / t["launches"],
-                    "share_of_step": t["ms"] / ms,
+                    "share_of_step": t["ms"] / ms_prof, "instrumented_ms_per_step": ms_prof / args.steps,
                     "tensor_tflops": t["flops"] / (t["ms"] * 1e-3) / 1e12 if t["flops"] else None,
                     "tensor_peak_tflops": tc_peak if args.precision == "bf16" else tc_peak / 2,
                     "by_kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in kinds.items()}}

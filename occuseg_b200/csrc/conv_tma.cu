@@ -24,6 +24,12 @@
 #include <cuda.h>
 #include <cstdlib>
 #include <cstdio>
+// -DSCN_TRACE_BUILD compiles clock64 accounting into k_conv_tma (SCN_TRACE=1 prints it); off in normal builds
+#ifdef SCN_TRACE_BUILD
+#define TRC(x) x
+#else
+#define TRC(x)
+#endif
 
 namespace scn {
 namespace tma {
@@ -84,6 +90,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n\t"
       "}" ::"r"(bar), "r"(parity)
       : "memory");
+}
+// long waits (epilogue warps): one lane polls with a back-off, the rest of the warp sleeps at the warp barrier
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
+  if (lane == 0) {
+    uint32_t done = 0;
+    while (true) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+      if (done) break;
+      __nanosleep(256);
+    }
+  }
+  __syncwarp();
 }
 __device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -230,7 +253,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 // warp 0: TMEM + MMA issuer; warps 1 .. nprod*ni: producers (item owner = (warp-1)/ni, share of the item's copies =
 // (warp-1)%ni); the last 4 warps: epilogue (TMEM quarter = warp & 3)
 constexpr int CONV_MAX_THREADS = 32 + 16 * 32 + 128;
-constexpr int MAX_MT = 4;
+constexpr int MAX_MT = 2;
 
 struct ConvParams {
   const float *bias;
@@ -239,6 +262,7 @@ struct ConvParams {
   int tbl_stride, n_rows, V, c_in, c_out, mirror;
   int TN, MT, stages, nprod, ni, b_stage, stage_bytes, tmem_cols, n_groups;
   int bf16, kelems;            // operand type; elements per 128-byte K chunk (32 tf32 / 64 bf16)
+  const void *in;              // base of the gathered matrix (L2 prefetch of upcoming rows)
   unsigned long long *trace;   // SCN_TRACE=1: clock64 totals over all CTAs (debug only): see conv_tma()
 };
 
@@ -289,19 +313,18 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
       const uint32_t idesc = idesc_make(p.TN, 0, 0, p.bf16 != 0);
       int s = 0, gi = 0;
       uint32_t ph = 0;
-      long long w_full = 0, w_acc = 0;
-      const long long t_begin = clock64();
+      TRC(long long w_full = 0; long long w_acc = 0; const long long t_begin = clock64();)
       for (int tg = blockIdx.x; tg < p.n_groups; tg += G, ++gi) {
         const int buf = gi & 1;
-        const long long ta = clock64();
+        TRC(const long long ta = clock64();)
         mbar_wait(acce_bar + 8 * buf, (uint32_t)(gi >> 1) & 1u);      // zeroed by the epilogue warps (or at start)
-        w_acc += clock64() - ta;
+        TRC(w_acc += clock64() - ta;)
         tc_fence_after();
         const uint32_t acc = tmem + buf * acc_cols;
         for (int j = 0; j < ipg; ++j) {
-          const long long tw = clock64();
+          TRC(const long long tw = clock64();)
           mbar_wait(full_bar + 8 * s, ph);
-          w_full += clock64() - tw;
+          TRC(w_full += clock64() - tw;)
           tc_fence_after();
           const uint32_t st = base + s * p.stage_bytes;
           const uint64_t bd = desc_k128(st + p.MT * A_STAGE);
@@ -326,11 +349,11 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
         }
         mma_commit(accf_bar + 8 * buf);
       }
-      if (p.trace) {
+      TRC(if (p.trace) {
         atomicAdd(p.trace + 0, (unsigned long long)(clock64() - t_begin));
         atomicAdd(p.trace + 1, (unsigned long long)w_full);
         atomicAdd(p.trace + 2, (unsigned long long)w_acc);
-      }
+      })
     }
   } else if (warp <= p.nprod * p.ni) {
     // =========================== TMA producers, item-interleaved ===========================
@@ -342,45 +365,78 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
       int4 *my_rows = s_rows + (warp - 1) * p.MT * 32;
       const int chunks = p.MT * 4 / p.ni;            // 8-group chunks of this share
       const int chunk0 = part * chunks;
+      // share 0 needs every row tile of the item (it publishes the masks and the byte count); the others only the
+      // row tile(s) their copies come from
+      const int m_lo = part == 0 ? 0 : chunk0 >> 2, m_hi = part == 0 ? p.MT - 1 : (chunk0 + chunks - 1) >> 2;
       auto load_tbl = [&](int tg, int trow, int4 *dst) {
 #pragma unroll
         for (int m = 0; m < MAX_MT; ++m) {
-          if (m < p.MT) {
+          if (m >= m_lo && m <= m_hi) {
             const int row = (tg * p.MT + m) * TM + 4 * lane;
             dst[m] = row < p.tbl_stride ? __ldg(reinterpret_cast<const int4 *>(p.tbl + (long long)trow * p.tbl_stride + row))
                                         : make_int4(-1, -1, -1, -1);
           }
         }
       };
+      // item i -> (tile group, index inside the group); this slot's items are i = pw, pw + nprod, ...
+      auto advance = [&](int &tg_, int &j_) {
+        j_ += p.nprod;
+        while (j_ >= ipg) { j_ -= ipg; tg_ += G; }
+      };
       int tg = blockIdx.x, j = pw;
       while (j >= ipg) { j -= ipg; tg += G; }
       int s = pw;
       uint32_t ph = 1;                   // parity to wait for on the empty barrier (first pass: already free)
-      long long w_empty = 0, t_issue = 0, n_items = 0, n_copies = 0;
-      const long long t_begin = clock64();
-      int4 cur[MAX_MT], nxt[MAX_MT];
+      TRC(long long w_empty = 0; long long t_issue = 0; long long n_items = 0; long long n_copies = 0; long long t_pre = 0;
+          long long t_b = 0; const long long t_begin = clock64();)
+      // Table rows are fetched TWO items ahead (they stream from HBM once per kernel), and the feature rows of the
+      // NEXT item are pulled towards L2 while the current one is issued: a gather that misses L2 holds a TMA
+      // request slot for a full HBM round trip, and the slots, not the bandwidth, are what runs out.
+      int4 cur[MAX_MT], nxt[MAX_MT], far[MAX_MT];
 #pragma unroll
-      for (int m = 0; m < MAX_MT; ++m) cur[m] = nxt[m] = make_int4(-1, -1, -1, -1);
+      for (int m = 0; m < MAX_MT; ++m) cur[m] = nxt[m] = far[m] = make_int4(-1, -1, -1, -1);
+      int tg1 = tg, j1 = j;
+      advance(tg1, j1);
       if (tg < p.n_groups) load_tbl(tg, j / KC, cur);
+      if (tg1 < p.n_groups) load_tbl(tg1, j1 / KC, nxt);
+      const char *in_bytes = reinterpret_cast<const char *>(p.in);
+      const long long row_bytes = (long long)p.c_in * (p.bf16 ? 2 : 4);
       while (tg < p.n_groups) {
+        TRC(const long long t_top = clock64();)
         const int trow = j / KC, kc = j - trow * KC;
-        int tg2 = tg, j2 = j + p.nprod;
-        while (j2 >= ipg) { j2 -= ipg; tg2 += G; }
-        if (tg2 < p.n_groups) load_tbl(tg2, j2 / KC, nxt);
+        int tg2 = tg1, j2 = j1;
+        advance(tg2, j2);
+        if (tg2 < p.n_groups) load_tbl(tg2, j2 / KC, far);
+        if (tg1 < p.n_groups) {
+          const long long off = (long long)(j1 - (j1 / KC) * KC) * 128;
+#pragma unroll
+          for (int m = 0; m < MAX_MT; ++m) {
+            const int c = m * 4 + (lane >> 3);          // this lane's 8-group chunk: only the share that will issue it prefetches
+            if (m < p.MT && c >= chunk0 && c < chunk0 + chunks) {
+              const int4 t = nxt[m];
+              if (t.x >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_bytes + t.x * row_bytes + off));
+              if (t.y >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_bytes + t.y * row_bytes + off));
+              if (t.z >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_bytes + t.z * row_bytes + off));
+              if (t.w >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_bytes + t.w * row_bytes + off));
+            }
+          }
+        }
         // present-row bits of every row tile; absent rows repeat a present row of their 4-row gather group
-        uint32_t gm[MAX_MT] = {0, 0, 0, 0}, any = 0;
+        uint32_t gm[MAX_MT] = {0, 0}, any = 0;
         uint4 pm[MAX_MT];
 #pragma unroll
         for (int m = 0; m < MAX_MT; ++m) {
-          if (m < p.MT) {
+          if (m >= m_lo && m <= m_hi) {
             int4 t = cur[m];
             const uint32_t nib = (t.x >= 0 ? 1u : 0u) | (t.y >= 0 ? 2u : 0u) | (t.z >= 0 ? 4u : 0u) | (t.w >= 0 ? 8u : 0u);
             gm[m] = __ballot_sync(0xffffffffu, nib != 0u);
-            const uint32_t sh = nib << (4 * (lane & 7));
-            pm[m].x = __reduce_or_sync(0xffffffffu, (lane >> 3) == 0 ? sh : 0u);
-            pm[m].y = __reduce_or_sync(0xffffffffu, (lane >> 3) == 1 ? sh : 0u);
-            pm[m].z = __reduce_or_sync(0xffffffffu, (lane >> 3) == 2 ? sh : 0u);
-            pm[m].w = __reduce_or_sync(0xffffffffu, (lane >> 3) == 3 ? sh : 0u);
+            if (part == 0) {
+              const uint32_t sh = nib << (4 * (lane & 7));
+              pm[m].x = __reduce_or_sync(0xffffffffu, (lane >> 3) == 0 ? sh : 0u);
+              pm[m].y = __reduce_or_sync(0xffffffffu, (lane >> 3) == 1 ? sh : 0u);
+              pm[m].z = __reduce_or_sync(0xffffffffu, (lane >> 3) == 2 ? sh : 0u);
+              pm[m].w = __reduce_or_sync(0xffffffffu, (lane >> 3) == 3 ? sh : 0u);
+            }
             const int rep = t.x >= 0 ? t.x : t.y >= 0 ? t.y : t.z >= 0 ? t.z : t.w;
             t.x = t.x >= 0 ? t.x : rep;
             t.y = t.y >= 0 ? t.y : rep;
@@ -392,11 +448,9 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
         }
         __syncwarp();
         if (lane == 0) {
-          const long long tw = clock64();
+          TRC(const long long tw = clock64(); t_pre += tw - t_top;)
           mbar_wait(empty_bar + 8 * s, ph);
-          const long long ti = clock64();
-          w_empty += ti - tw;
-          ++n_items;
+          TRC(const long long ti = clock64(); w_empty += ti - tw; ++n_items;)
           const uint32_t st = base + s * p.stage_bytes;
           if (part == 0) {
             int groups = 0;
@@ -411,6 +465,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
               const int wtap = p.mirror ? p.V - 1 - trow : trow;
               tma_tile_2d(st + p.MT * A_STAGE, &map_w, kc * p.kelems, wtap * p.c_out + n0, full_bar + 8 * s);
             }
+            TRC(t_b += clock64() - ti;)
           }
           for (int c = chunk0; c < chunk0 + chunks; ++c) {
             const int m = c >> 2, q = c & 3;
@@ -420,7 +475,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
               if (mm == m) gmm = gm[mm];
             const uint32_t g8 = (gmm >> (8 * q)) & 0xFFu;
             if (!g8) continue;
-            n_copies += __popc(g8);
+            TRC(n_copies += __popc(g8);)
             int4 r[8];
 #pragma unroll
             for (int g = 0; g < 8; ++g) r[g] = my_rows[c * 8 + g];
@@ -430,24 +485,29 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
                 tma_gather4(st + c * 8 * 512 + g * 512, &map_x, kc * p.kelems, r[g].x, r[g].y, r[g].z, r[g].w, full_bar + 8 * s);
           }
           if (part != 0) mbar_arrive(full_bar + 8 * s);
-          t_issue += clock64() - ti;
+          TRC(t_issue += clock64() - ti;)
         }
         __syncwarp();
 #pragma unroll
-        for (int m = 0; m < MAX_MT; ++m) cur[m] = nxt[m];
-        tg = tg2;
-        j = j2;
+        for (int m = 0; m < MAX_MT; ++m) {
+          cur[m] = nxt[m];
+          nxt[m] = far[m];
+        }
+        tg = tg1; j = j1;
+        tg1 = tg2; j1 = j2;
         s += p.nprod;
         if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
       }
-      if (p.trace && lane == 0 && pw == 0) {
+      TRC(if (p.trace && lane == 0 && pw == 0) {
         unsigned long long *t = p.trace + 4 + 8 * part;
         atomicAdd(t + 0, (unsigned long long)(clock64() - t_begin));
         atomicAdd(t + 1, (unsigned long long)w_empty);
         atomicAdd(t + 2, (unsigned long long)t_issue);
         atomicAdd(t + 3, (unsigned long long)n_items);
         atomicAdd(t + 4, (unsigned long long)n_copies);
-      }
+        atomicAdd(t + 5, (unsigned long long)t_pre);
+        atomicAdd(t + 6, (unsigned long long)t_b);
+      })
     }
   } else {
     // =========================== epilogue warps ===========================
@@ -464,7 +524,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
     int gi = 0;
     for (int tg = blockIdx.x; tg < p.n_groups; tg += G, ++gi) {
       const int buf = gi & 1;
-      mbar_wait(accf_bar + 8 * buf, (uint32_t)(gi >> 1) & 1u);
+      mbar_wait_warp(accf_bar + 8 * buf, (uint32_t)(gi >> 1) & 1u, lane);
       tc_fence_after();
       for (int m = 0; m < p.MT; ++m) {
         const int r = (tg * p.MT + m) * TM + quarter * 32 + lane;
@@ -673,7 +733,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tma(const __grid_constant_
   } else {
     // =========================== epilogue: TMEM -> fp32 reductions into dW ===========================
     const int quarter = warp & 3;
-    mbar_wait(accum_bar, 0);
+    mbar_wait_warp(accum_bar, 0, lane);
     tc_fence_after();
     const uint32_t acc = tmem + ((uint32_t)(quarter * 32) << 16);
     for (int mt = 0; mt < p.m_tiles; ++mt) {
@@ -722,7 +782,7 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   SCN_CHECK(a.weight_nk != nullptr, "conv_tma needs the [V][Cout][Cin] weight layout");
   if (a.n_rows == 0) return;
   ConvParams p;
-  p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
+  p.in = a.in; p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
   p.V = a.V; p.c_in = a.c_in; p.c_out = a.c_out; p.mirror = a.mirror ? 1 : 0;
   p.bf16 = a.bf16 ? 1 : 0;
   p.kelems = a.bf16 ? 64 : 32;
@@ -768,10 +828,14 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   dim3 grid(gx, n_tiles_n);
   static const int trace = env_int("SCN_TRACE", 0);
   p.trace = nullptr;
+#ifndef SCN_TRACE_BUILD
+  if (trace) fprintf(stderr, "[conv trace] rebuild with -DSCN_TRACE_BUILD to collect the clock64 breakdown\n");
+#else
   if (trace) {
     SCN_CUDA(cudaMalloc((void **)&p.trace, 8 * 64));
     SCN_CUDA(cudaMemset(p.trace, 0, 8 * 64));
   }
+#endif
   k_conv_tma<<<grid, 32 + 32 * p.nprod * p.ni + 128, smem, s>>>(mx, mw, p);
   SCN_LAUNCH_CHECK();
   if (p.trace) {
@@ -785,8 +849,8 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
             h[1] / n, h[2] / n);
     for (int q = 0; q < p.ni; ++q) {
       const unsigned long long *t = h + 4 + 8 * q;
-      fprintf(stderr, " share%d: loop %.0f wait-empty %.0f issue %.0f items %.0f copies %.0f |", q, t[0] / n, t[1] / n, t[2] / n,
-              t[3] / n, t[4] / n);
+      fprintf(stderr, " share%d: loop %.0f pre %.0f wait-empty %.0f issue %.0f (masks+B %.0f) items %.0f copies %.0f |", q, t[0] / n,
+              t[5] / n, t[1] / n, t[2] / n, t[6] / n, t[3] / n, t[4] / n);
     }
     fprintf(stderr, "\n");
   }
@@ -813,20 +877,28 @@ void wgrad_tma(const WgradArgs &a, cudaStream_t s) {
   p.transpose_out = a.table_on_a ? 0 : 1;
   p.dw = a.dw; p.gi = a.gi; p.si = a.si; p.blk_item = a.blk_item; p.V = a.V; p.n_blk = a.n_blk;
   p.m_tiles = (p.Cg + 127) / 128;
-  p.N = 0;
-  for (int n = 256; n >= p.cpb; n -= p.cpb)
-    if (p.Cs % n == 0 && p.m_tiles * n <= 512) { p.N = n; break; }
-  SCN_CHECK(p.N > 0, "wgrad_tma: no N tile");
-  p.tmem_cols = 32;
-  while (p.tmem_cols < p.m_tiles * p.N) p.tmem_cols <<= 1;
-  // every stage holds the item's G atoms, then its S atoms; an accumulator tile always spans 4 G atoms, so the
-  // last tile of a Cg that is not a multiple of 128 reads on into the S atoms (finite data; rows >= Cg are ignored)
-  p.stage_bytes = (p.Cg / p.cpb + p.N / p.cpb) * SUB;
+  // every stage holds the item's G blocks, then its S blocks; an accumulator tile always spans 128 channels of G, so the
+  // last tile of a Cg that is not a multiple of 128 reads on into the S blocks (finite data; rows >= Cg are ignored)
   const int fixed = 1024 + 4 * 2 * KR * 4 + 8 * (2 * 8 + 1) + 64;
   const int tail = p.m_tiles * 128 > p.Cg ? (128 / p.cpb) * SUB : 0;
-  int budget = 113 * 1024;
+  // column tile: the widest multiple of a block that divides Cs, fits TMEM and leaves at least 3 pipeline stages
+  p.N = 0;
+  int budget = 225 * 1024, st = 0;
+  for (int pass = 0; pass < 2 && p.N == 0; ++pass)
+    for (int n = 256; n >= p.cpb; n -= p.cpb) {
+      if (p.Cs % n != 0 || p.m_tiles * n > 512) continue;
+      const int sb = (p.Cg / p.cpb + n / p.cpb) * SUB;
+      if ((225 * 1024 - fixed - tail) / sb < (pass == 0 ? 3 : 2)) continue;
+      p.N = n;
+      break;
+    }
+  SCN_CHECK(p.N > 0, "wgrad_tma: no column tile fits shared memory");
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.m_tiles * p.N) p.tmem_cols <<= 1;
+  p.stage_bytes = (p.Cg / p.cpb + p.N / p.cpb) * SUB;
+  budget = 113 * 1024;                               // two CTAs per SM when TMEM and >= 3 stages allow
   if (512 / p.tmem_cols < 2 || (budget - fixed - tail) / p.stage_bytes < 3) budget = 225 * 1024;
-  int st = (budget - fixed - tail) / p.stage_bytes;
+  st = (budget - fixed - tail) / p.stage_bytes;
   SCN_CHECK(st >= 2, "wgrad_tma: shared memory budget");
   if (st > 8) st = 8;
   p.stages = st;

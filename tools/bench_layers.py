@@ -5,10 +5,11 @@ from occuseg_b200.sparseconvnet import SCN
 from occuseg_b200 import _lib, scenes
 def lt(v): return torch.LongTensor([v,v,v])
 nsc=int(sys.argv[1]) if len(sys.argv)>1 else 8
+prec=sys.argv[2] if len(sys.argv)>2 else 'bf16'
 coords,feats=scenes.make_batch("S250k",tuple(range(nsc)))
 m=SCN.Metadata_3(); out=torch.empty(0,device='cuda')
 SCN.InputLayer_updateOutput(m, lt(4096), torch.from_numpy(coords), torch.from_numpy(feats).cuda(), out, nsc, 4, None)
-scn.set_precision('tf32')
+scn.set_precision(prec); print('precision', prec)
 size=4096
 def ev(fn, reps=3):
     fn(); torch.cuda.synchronize()

@@ -10,7 +10,7 @@ nsc = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 coords, feats = scenes.make_batch("S250k", tuple(range(nsc)))
 m = SCN.Metadata_3(); out = torch.empty(0, device='cuda')
 SCN.InputLayer_updateOutput(m, lt(4096), torch.from_numpy(coords), torch.from_numpy(feats).cuda(), out, nsc, 4, None)
-scn.set_precision('tf32')
+scn.set_precision(sys.argv[3] if len(sys.argv) > 3 else 'bf16')
 N = m.getNActive(lt(4096))
 x = torch.randn(N, C, device='cuda'); g = torch.randn(N, C, device='cuda'); w = torch.randn(27, C, C, device='cuda') * 0.05
 y = torch.empty(0, device='cuda'); dx = torch.empty(0, device='cuda'); dw = torch.zeros_like(w)
