@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
           }
         }
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {          // elect.sync, not lane == 0: ptxas then keeps the copy operands in uniform registers (no vote loops)
           TRC(const long long tw = clock64(); t_pre += tw - t_top;)
           mbar_wait(empty_bar + 8 * s, ph);
           TRC(const long long ti = clock64(); w_empty += ti - tw; ++n_items;)
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tma(const __grid_constant_
           }
         }
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_wait(empty_bar + 8 * s, ph);
           mbar_expect_tx(full_bar + 8 * s, (uint32_t)p.stage_bytes);
           const uint32_t dst = base + s * p.stage_bytes;
