@@ -262,12 +262,38 @@ void scn_meta_destroy(scn_meta *h) {
   delete h;
 }
 
+// Depth of the scale hierarchy the previous batches ended up with.  Every scale costs two host synchronisations
+// (row count, rule count); done lazily they sit between the layers of the forward pass and drain the launch queue
+// right before the small deep levels, which then run launch-bound.  So once the depth is known, the whole chain of
+// rulebooks is built (and all its synchronisations paid) inside the InputLayer call, and the rest of the step is
+// enqueued without a single host wait.  A batch that needs fewer scales wastes a few tiny kernels; one that needs
+// more builds the extra scales lazily, as before, and raises the hint.
+static std::atomic<int> g_depth_hint{0};
+
+static void prebuild_scales(Meta *m, cudaStream_t s) {
+  const int depth = g_depth_hint.load();
+  for (int i = 0; i + 1 <= depth; ++i) {
+    Level *L = m->levels.back();
+    ensure_neighbour_table(m, L, s);
+    if (i + 1 == depth) break;
+    int64_t coarse[3];
+    bool ok = L->n > 0;
+    for (int d = 0; d < 3; ++d) {
+      ok = ok && L->size[d] % 2 == 0 && L->size[d] >= 2;
+      coarse[d] = L->size[d] / 2;
+    }
+    if (!ok) break;
+    ensure_coarse_level(m, L, coarse, s);
+  }
+}
+
 int scn_input_layer_build(scn_meta *h, const int64_t size[3], const int64_t *coords, int on_device, int64_t P,
                           int batch, int mode, void *stream, int64_t *n_active) {
   SCN_TRY
   SCN_CHECK(h && coords && n_active, "null argument");
   build_input_level(&h->m, size, coords, on_device != 0, P, batch, mode, (cudaStream_t)stream);
   *n_active = h->m.levels[0]->n;
+  prebuild_scales(&h->m, (cudaStream_t)stream);
   SCN_CATCH
 }
 
@@ -331,10 +357,16 @@ int scn_subm_neighbour_table(scn_meta *h, const int64_t size[3], int32_t *out) {
   SCN_CATCH
 }
 
+static void note_depth(Meta *m) {
+  int d = (int)m->levels.size(), cur = g_depth_hint.load();
+  while (d > cur && !g_depth_hint.compare_exchange_weak(cur, d)) {}
+}
+
 int scn_strided_rulebook(scn_meta *h, const int64_t fine[3], const int64_t coarse[3], void *stream, int64_t *n_coarse) {
   SCN_TRY
   Level *F = need_level(&h->m, fine, "Convolution");
   Level *C = ensure_coarse_level(&h->m, F, coarse, (cudaStream_t)stream);
+  note_depth(&h->m);
   if (n_coarse) *n_coarse = C->n;
   SCN_CATCH
 }
@@ -399,6 +431,7 @@ int scn_conv_fwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   check_channels(c_in, c_out);
   Level *F = need_level(&h->m, in_size, "Convolution");
   Level *C = ensure_coarse_level(&h->m, F, out_size, s);
+  note_depth(&h->m);
   // out[p] = sum_k in[child[k][p]] * W[k]
   ConvArgs a;
   a.in = in; a.bias = bias; a.out = out;
