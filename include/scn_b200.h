@@ -90,6 +90,17 @@ int scn_strided_rulebook(scn_meta *m, const int64_t fine_size[3], const int64_t 
 /* copy to HOST: parent int32 [Nfine] (coarse row of each fine row) and offset uint8 [Nfine] (0..7) */
 int scn_strided_table(scn_meta *m, const int64_t fine_size[3], int32_t *parent_host, uint8_t *offset_host);
 
+/* ---- SCN_BF16 operand copies ----------------------------------------------------------------------
+ * The SCN_BF16 kernels read bf16 COPIES of the fp32 feature matrices.  By default every entry makes (and drops) the
+ * copies it needs.  A caller that keeps them saves those passes: scn_bf16_operand registers `bf16` ([rows, c] bf16,
+ * caller-owned) as the copy of the fp32 matrix at `fp32` for the NEXT convolution entry on this handle whose `in`
+ * argument is that pointer.  ready = 1: already filled (e.g. by scn_bn_fwd's out_bf16, or by an earlier forward
+ * call); ready = 0: the entry fills it.  Forward entries use it as the gathered operand, backward entries as the
+ * `in` operand of the weight gradient.  scn_bf16_plan: bit 0 = the forward product of a [c_in -> c_out] layer reads a
+ * bf16 `in`, bit 1 = its weight gradient does (0 unless precision is SCN_BF16 and the widths allow). */
+int scn_bf16_operand(scn_meta *m, const float *fp32, void *bf16, int ready);
+int scn_bf16_plan(int c_in, int c_out, int precision);
+
 /* ---- SubmanifoldConvolution_updateOutput / _backward (sparseconvnet.h:50-61; drivers
  * CUDA/Convolution.cpp:104-210; kernels CUDA/Convolution.cu:447-534,695-753,1059-1152) ----------
  * out[N,Cout] = sum_k in[nbr_k(o)] * W[k];  *macs = sum_k n_k*Cin*Cout (the reference's return value) */
@@ -119,13 +130,17 @@ int scn_deconv_bwd(scn_meta *m, const int64_t in_size[3], const int64_t out_size
  * (sparseconvnet.h:21-33, CUDA/BatchNormalization.cpp:21-71, BatchNormalization.cu:14-199) --------
  * train: batch statistics, running = momentum*running + (1-momentum)*batch (unbiased var);
  * y = leaky(gamma*(x-mean)*invstd + beta); leakiness 0 = ReLU, 1 = identity.  gamma/beta may be NULL. */
-int scn_bn_fwd(const float *in, float *out, float *save_mean, float *save_invstd, float *running_mean,
+/* out_bf16: optional second output, the bf16 copy of `out` ([n_rows, channels], channels % 4 == 0) for the SCN_BF16
+ * convolution that consumes it (see scn_bf16_operand); NULL = none */
+int scn_bn_fwd(const float *in, float *out, void *out_bf16, float *save_mean, float *save_invstd, float *running_mean,
                float *running_var, const float *gamma, const float *beta, int64_t n_rows, int channels, float eps,
                float momentum, int train, float leakiness, void *stream);
-/* d_out is NOT modified (the reference masks it in place, BatchNormalization.cu:151-153; no caller observes it) */
+/* d_out is NOT modified (the reference masks it in place, BatchNormalization.cu:151-153; no caller observes it).
+ * `out` (the forward output) is accepted for symmetry with the reference entry but never read: the activation mask is
+ * recomputed from `in`, gamma and beta exactly as the forward pass computed it, so `out` may be NULL. */
 int scn_bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
-               const float *gamma, float *d_in, float *d_gamma, float *d_beta, int64_t n_rows, int channels,
-               float leakiness, void *stream);
+               const float *gamma, const float *beta, float *d_in, float *d_gamma, float *d_beta, int64_t n_rows,
+               int channels, float leakiness, void *stream);
 
 #ifdef __cplusplus
 }

@@ -4,7 +4,7 @@
 // The reference walks all N rows with at most 16 CTAs (grid = min(16, C/NTX)) and accumulates the
 // statistics as fp32 running sums.  Here the reduction is spread over 4 CTAs per SM, partial sums are
 // short fp32 chains merged in fp64, and the normalise pass is a 128-bit streaming kernel.
-// HBM-bound: forward 3*N*C*4 bytes (read x twice, write y), backward 5*N*C*4.
+// HBM-bound: forward 3*N*C*4 bytes (read x twice, write y), backward 5*N*C*4 (x and d_out twice, d_in once).
 #include "common.cuh"
 
 namespace scn {
@@ -18,17 +18,29 @@ constexpr int ROWS_PER_FLUSH = 64;      // rows a thread folds in fp32 before ad
 // C (the block uses cv * floor(256/cv) threads) and a warp reads whole contiguous rows.  Four independent rows
 // are in flight per thread.  fp32 chains of <= 64 rows are merged in fp64 (registers -> shared -> one fp64
 // atomic per column per CTA).
+// The backward passes do not read the forward output: the ReLU mask y > 0 is recomputed from x with the very
+// expression the forward pass used (fmaf(w, x, b), w = invstd*gamma, b = beta - mean*w), which saves one of the three
+// [N, C] reads of each backward kernel.
 template <int VEC, int MODE>
-__global__ void __launch_bounds__(RED_THREADS) k_bn_reduce(const float *__restrict__ x, const float *__restrict__ y,
+__global__ void __launch_bounds__(RED_THREADS) k_bn_reduce(const float *__restrict__ x, const float *__restrict__ invstd,
                                                           const float *__restrict__ d, const float *__restrict__ mean,
+                                                          const float *__restrict__ gamma, const float *__restrict__ beta,
                                                           long long n, int C, float leak, double *__restrict__ acc) {
   const int cv = C / VEC;
   const int row_lanes = blockDim.x / cv;
   const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
   extern __shared__ double red[];          // [2][row_lanes][C]
-  float m[VEC];
+  float m[VEC], wv[VEC], bv[VEC];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) m[j] = MODE == 1 ? __ldg(&mean[cg * VEC + j]) : 0.f;
+  for (int j = 0; j < VEC; ++j) {
+    m[j] = wv[j] = bv[j] = 0.f;
+    if (MODE == 1) {
+      const int c = cg * VEC + j;
+      m[j] = __ldg(&mean[c]);
+      wv[j] = __ldg(&invstd[c]) * (gamma ? __ldg(&gamma[c]) : 1.f);
+      bv[j] = -m[j] * wv[j] + (beta ? __ldg(&beta[c]) : 0.f);
+    }
+  }
   double t0[VEC], t1[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) t0[j] = t1[j] = 0.0;
@@ -36,19 +48,17 @@ __global__ void __launch_bounds__(RED_THREADS) k_bn_reduce(const float *__restri
   const long long r_begin = blockIdx.x * rows_per_cta;
   const long long r_end = r_begin + rows_per_cta < n ? r_begin + rows_per_cta : n;
   auto fold = [&](long long r, float *s0, float *s1) {
-    float xv[VEC], yv[VEC], dv[VEC];
+    float xv[VEC], dv[VEC];
     if (VEC == 4) {
       float4 t = __ldg(reinterpret_cast<const float4 *>(x + r * C) + cg);
       xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
       if (MODE == 1) {
-        float4 u = __ldg(reinterpret_cast<const float4 *>(y + r * C) + cg);
         float4 w = __ldg(reinterpret_cast<const float4 *>(d + r * C) + cg);
-        yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
         dv[0] = w.x; dv[1] = w.y; dv[2] = w.z; dv[3] = w.w;
       }
     } else {
       xv[0] = __ldg(x + r * C + cg);
-      if (MODE == 1) { yv[0] = __ldg(y + r * C + cg); dv[0] = __ldg(d + r * C + cg); }
+      if (MODE == 1) dv[0] = __ldg(d + r * C + cg);
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -56,7 +66,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_bn_reduce(const float *__restri
         s0[j] += xv[j];
         s1[j] = fmaf(xv[j], xv[j], s1[j]);
       } else {
-        float dd = yv[j] > 0.f ? dv[j] : dv[j] * leak;
+        float dd = fmaf(wv[j], xv[j], bv[j]) > 0.f ? dv[j] : dv[j] * leak;
         s0[j] += dd;
         s1[j] = fmaf(xv[j] - m[j], dd, s1[j]);
       }
@@ -133,7 +143,7 @@ __global__ void k_bn_finalize_fwd(const double *__restrict__ acc, long long n, i
 
 template <int VEC>
 __global__ void __launch_bounds__(256) k_bn_apply_fwd(const float *__restrict__ x, float *__restrict__ y,
-                                                      const float *__restrict__ save_mean,
+                                                      uint16_t *__restrict__ y16, const float *__restrict__ save_mean,
                                                       const float *__restrict__ save_invstd,
                                                       const float *__restrict__ gamma, const float *__restrict__ beta,
                                                       long long n, int C, float leak) {
@@ -157,6 +167,12 @@ __global__ void __launch_bounds__(256) k_bn_apply_fwd(const float *__restrict__ 
       o.x = o.x > 0.f ? o.x : o.x * leak; o.y = o.y > 0.f ? o.y : o.y * leak;
       o.z = o.z > 0.f ? o.z : o.z * leak; o.w = o.w > 0.f ? o.w : o.w * leak;
       reinterpret_cast<float4 *>(y)[e] = o;
+      if (y16) {      // bf16 copy for the tensor-core convolution that consumes y (saves that layer's cast pass)
+        uint2 h;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(o.y), "f"(o.x));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(o.w), "f"(o.z));
+        reinterpret_cast<uint2 *>(y16)[e] = h;
+      }
     } else {
       float o = fmaf(wb[cg], __ldg(x + e), wb[C + cg]);
       y[e] = o > 0.f ? o : o * leak;
@@ -179,39 +195,39 @@ __global__ void k_bn_finalize_bwd(const double *__restrict__ acc, long long n, i
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ x, const float *__restrict__ y,
+__global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ x, const float *__restrict__ beta,
                                                       const float *__restrict__ d, float *__restrict__ dx,
                                                       const float *__restrict__ save_mean,
                                                       const float *__restrict__ save_invstd,
                                                       const float *__restrict__ gamma, const float *__restrict__ coef,
                                                       long long n, int C, float leak) {
-  extern __shared__ float sm[];   // [4][C]: mean, gradMean, k, invstd*gamma
+  extern __shared__ float sm[];   // [5][C]: mean, gradMean, k, w = invstd*gamma, b = beta - mean*w
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float w = save_invstd[c] * (gamma ? gamma[c] : 1.f);
     sm[c] = save_mean[c];
     sm[C + c] = coef[c];
     sm[2 * C + c] = coef[C + c];
-    sm[3 * C + c] = save_invstd[c] * (gamma ? gamma[c] : 1.f);
+    sm[3 * C + c] = w;
+    sm[4 * C + c] = -save_mean[c] * w + (beta ? beta[c] : 0.f);
   }
   __syncthreads();
   const int cv = C / VEC;
   const long long total = n * cv;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     int c0 = (int)(e % cv) * VEC;
-    float xv[VEC], yv[VEC], dv[VEC], ov[VEC];
+    float xv[VEC], dv[VEC], ov[VEC];
     if (VEC == 4) {
       float4 t = __ldg(reinterpret_cast<const float4 *>(x) + e);
-      float4 u = __ldg(reinterpret_cast<const float4 *>(y) + e);
       float4 w = __ldg(reinterpret_cast<const float4 *>(d) + e);
       xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
-      yv[0] = u.x; yv[1] = u.y; yv[2] = u.z; yv[3] = u.w;
       dv[0] = w.x; dv[1] = w.y; dv[2] = w.z; dv[3] = w.w;
     } else {
-      xv[0] = __ldg(x + e); yv[0] = __ldg(y + e); dv[0] = __ldg(d + e);
+      xv[0] = __ldg(x + e); dv[0] = __ldg(d + e);
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       int c = c0 + j;
-      float dd = yv[j] > 0.f ? dv[j] : dv[j] * leak;
+      float dd = fmaf(sm[3 * C + c], xv[j], sm[4 * C + c]) > 0.f ? dv[j] : dv[j] * leak;
       ov[j] = (dd - sm[C + c] - (xv[j] - sm[c]) * sm[2 * C + c]) * sm[3 * C + c];
     }
     if (VEC == 4) reinterpret_cast<float4 *>(dx)[e] = make_float4(ov[0], ov[1], ov[2], ov[3]);
@@ -226,9 +242,9 @@ static int stream_grid(long long work_items, int block) {
   return (int)(g < 1 ? 1 : g);
 }
 
-void bn_fwd(const float *in, float *out, float *save_mean, float *save_invstd, float *running_mean, float *running_var,
-            const float *gamma, const float *beta, long long n, int C, float eps, float momentum, bool train,
-            float leakiness, cudaStream_t s) {
+void bn_fwd(const float *in, float *out, uint16_t *out_bf16, float *save_mean, float *save_invstd, float *running_mean,
+            float *running_var, const float *gamma, const float *beta, long long n, int C, float eps, float momentum,
+            bool train, float leakiness, cudaStream_t s) {
   SCN_CHECK(C > 0 && C <= 4096, "BatchNorm: channel count out of range");
   if (n == 0) return;
   bool v4 = (C % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
@@ -240,22 +256,23 @@ void bn_fwd(const float *in, float *out, float *save_mean, float *save_invstd, f
     const bool r4 = v4 && C / 4 <= RED_THREADS;
     SCN_CHECK(r4 || C <= RED_THREADS, "BatchNorm: more than 256 channels need 16-byte aligned rows");
     const RedCfg rc = reduce_cfg(n, C, r4 ? 4 : 1);
-    if (r4) k_bn_reduce<4, 0><<<rc.grid, rc.threads, rc.smem, s>>>(in, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
-    else k_bn_reduce<1, 0><<<rc.grid, rc.threads, rc.smem, s>>>(in, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
+    if (r4) k_bn_reduce<4, 0><<<rc.grid, rc.threads, rc.smem, s>>>(in, nullptr, nullptr, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
+    else k_bn_reduce<1, 0><<<rc.grid, rc.threads, rc.smem, s>>>(in, nullptr, nullptr, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
     SCN_LAUNCH_CHECK();
   }
   k_bn_finalize_fwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, eps, momentum, train, save_mean, save_invstd,
                                                     running_mean, running_var);
   SCN_LAUNCH_CHECK();
   size_t smem = sizeof(float) * 2 * C;
-  if (v4) k_bn_apply_fwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, out, save_mean, save_invstd, gamma, beta, n, C, leakiness);
-  else k_bn_apply_fwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, out, save_mean, save_invstd, gamma, beta, n, C, leakiness);
+  SCN_CHECK(!out_bf16 || (v4 && (uintptr_t)out_bf16 % 8 == 0), "BatchNorm: the bf16 copy needs C % 4 == 0 and aligned buffers");
+  if (v4) k_bn_apply_fwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, out, out_bf16, save_mean, save_invstd, gamma, beta, n, C, leakiness);
+  else k_bn_apply_fwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, out, nullptr, save_mean, save_invstd, gamma, beta, n, C, leakiness);
   SCN_LAUNCH_CHECK();
   acc.release(s);
 }
 
 void bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
-            const float *gamma, float *d_in, float *d_gamma, float *d_beta, long long n, int C, float leakiness,
+            const float *gamma, const float *beta, float *d_in, float *d_gamma, float *d_beta, long long n, int C, float leakiness,
             cudaStream_t s) {
   SCN_CHECK(C > 0 && C <= 4096, "BatchNorm: channel count out of range");
   if (n == 0) return;
@@ -269,14 +286,14 @@ void bn_bwd(const float *in, const float *out, const float *d_out, const float *
   const bool r4 = v4 && C / 4 <= RED_THREADS;
   SCN_CHECK(r4 || C <= RED_THREADS, "BatchNorm: more than 256 channels need 16-byte aligned rows");
   const RedCfg rc = reduce_cfg(n, C, r4 ? 4 : 1);
-  if (r4) k_bn_reduce<4, 1><<<rc.grid, rc.threads, rc.smem, s>>>(in, out, d_out, save_mean, n, C, leakiness, acc.p);
-  else k_bn_reduce<1, 1><<<rc.grid, rc.threads, rc.smem, s>>>(in, out, d_out, save_mean, n, C, leakiness, acc.p);
+  if (r4) k_bn_reduce<4, 1><<<rc.grid, rc.threads, rc.smem, s>>>(in, save_invstd, d_out, save_mean, gamma, beta, n, C, leakiness, acc.p);
+  else k_bn_reduce<1, 1><<<rc.grid, rc.threads, rc.smem, s>>>(in, save_invstd, d_out, save_mean, gamma, beta, n, C, leakiness, acc.p);
   SCN_LAUNCH_CHECK();
   k_bn_finalize_bwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, save_invstd, d_gamma, d_beta, coef.p);
   SCN_LAUNCH_CHECK();
-  size_t smem = sizeof(float) * 4 * C;
-  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, out, d_out, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness);
-  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, out, d_out, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness);
+  size_t smem = sizeof(float) * 5 * C;
+  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, beta, d_out, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness);
+  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, beta, d_out, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness);
   SCN_LAUNCH_CHECK();
   acc.release(s);
   coef.release(s);

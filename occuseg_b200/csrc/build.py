@@ -15,7 +15,7 @@ HEADERS = ["common.cuh", os.path.join("..", "..", "include", "scn_b200.h")]
 LIB = os.path.join(HERE, "libscn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-         "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("SCN_NVCC_EXTRA", "").split()
 
 
 def _stale(target, deps):

@@ -219,6 +219,19 @@ struct scn_meta {
   Meta m;
 };
 
+// the bf16 copy registered for `src` (filled here if the caller only supplied the buffer), or NULL; one use only
+static const uint16_t *take_bf16_hint(Meta *m, const float *src, long long n, cudaStream_t s) {
+  if (!m->hint_bf16 || m->hint_src != src) return nullptr;
+  uint16_t *p = (uint16_t *)m->hint_bf16;
+  if (!m->hint_ready) {
+    ProfScope ps(PK_CAST, 6.0 * (double)n, 0.0, s);
+    cast_bf16(src, p, n, s);
+  }
+  m->hint_bf16 = nullptr;
+  m->hint_src = nullptr;
+  return p;
+}
+
 static void check_channels(int c_in, int c_out) {
   SCN_CHECK(c_in > 0 && c_out > 0 && c_in <= 4096 && c_out <= 4096, "channel counts out of range");
 }
@@ -391,7 +404,7 @@ int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   ConvArgs a;
   a.in = in; a.bias = bias; a.out = out;
   a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_in; a.c_out = c_out; a.n_rules = L->n_rules; a.in_rows = L->n;
-  run_conv(a, weight, true, precision, s);
+  run_conv(a, weight, true, precision, s, take_bf16_hint(&h->m, in, (long long)L->n * c_in, s));
   if (macs) *macs = (double)L->n_rules * c_in * c_out;   // flops += nRules*ip*op, CPU/Convolution.cpp:134
   SCN_CATCH
 }
@@ -408,7 +421,9 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   const bool dgrad16 = d_in && bf16_conv_shape(c_out, c_in, precision), wgrad16 = bf16_wgrad_shape(c_in, c_out, precision);
   Bf16Copy g16, x16;
   const uint16_t *pg = (dgrad16 || wgrad16) ? g16.make(d_out, (long long)L->n * c_out, s) : nullptr;
-  const uint16_t *px = wgrad16 ? x16.make(in, (long long)L->n * c_in, s) : nullptr;
+  const uint16_t *px = take_bf16_hint(&h->m, in, (long long)L->n * c_in, s);
+  if (!wgrad16) px = nullptr;
+  else if (!px) px = x16.make(in, (long long)L->n * c_in, s);
   ConvArgs a;
   a.in = d_out; a.out = d_in;
   a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_out; a.c_out = c_in; a.mirror = true; a.n_rules = L->n_rules; a.in_rows = L->n;
@@ -436,7 +451,7 @@ int scn_conv_fwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   ConvArgs a;
   a.in = in; a.bias = bias; a.out = out;
   a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_in; a.c_out = c_out; a.n_rules = F->n; a.in_rows = F->n;
-  run_conv(a, weight, true, precision, s);
+  run_conv(a, weight, true, precision, s, take_bf16_hint(&h->m, in, (long long)F->n * c_in, s));
   if (macs) *macs = (double)F->n * c_in * c_out;   // every fine row has exactly one rule
   SCN_CATCH
 }
@@ -454,7 +469,7 @@ int scn_conv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
   w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = F->n; w.g_rows = F->n; w.s_rows = C->n;
-  run_wgrad(w, F->child_pairs, precision, s);
+  run_wgrad(w, F->child_pairs, precision, s, take_bf16_hint(&h->m, in, (long long)F->n * c_in, s));
   if (d_bias) bias_grad(d_out, d_bias, C->n, c_out, s);
   SCN_CATCH
 }
@@ -472,7 +487,7 @@ int scn_deconv_fwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
   Level *C = F->coarse;
   SCN_CHECK(bias == nullptr, "Deconvolution: bias is not supported on this path (the UNet uses bias=False)");
   // out[child[k][p]] = in[p] * W[k]
-  run_up(F, C, in, weight, true, out, c_in, c_out, precision, s);
+  run_up(F, C, in, weight, true, out, c_in, c_out, precision, s, take_bf16_hint(&h->m, in, (long long)C->n * c_in, s));
   if (macs) *macs = (double)F->n * c_in * c_out;
   SCN_CATCH
 }
@@ -496,28 +511,41 @@ int scn_deconv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
   w.c_a = c_in; w.c_b = c_out; w.table_on_a = false; w.n_rules = F->n; w.g_rows = F->n; w.s_rows = C->n;
-  run_wgrad(w, F->child_pairs, precision, s);
+  run_wgrad(w, F->child_pairs, precision, s, take_bf16_hint(&h->m, in, (long long)C->n * c_in, s));
   if (d_bias) bias_grad(d_out, d_bias, F->n, c_out, s);
   SCN_CATCH
 }
 
 // ---- batch norm ---------------------------------------------------------------------------------------
-int scn_bn_fwd(const float *in, float *out, float *save_mean, float *save_invstd, float *running_mean,
+int scn_bf16_operand(scn_meta *h, const float *fp32, void *bf16, int ready) {
+  SCN_TRY
+  SCN_CHECK(h, "null handle");
+  h->m.hint_src = fp32;
+  h->m.hint_bf16 = bf16;
+  h->m.hint_ready = ready;
+  SCN_CATCH
+}
+
+int scn_bf16_plan(int c_in, int c_out, int precision) {
+  return (bf16_conv_shape(c_in, c_out, precision) ? 1 : 0) | (bf16_wgrad_shape(c_in, c_out, precision) ? 2 : 0);
+}
+
+int scn_bn_fwd(const float *in, float *out, void *out_bf16, float *save_mean, float *save_invstd, float *running_mean,
                float *running_var, const float *gamma, const float *beta, int64_t n, int C, float eps, float momentum,
                int train, float leakiness, void *stream) {
   SCN_TRY
-  ProfScope ps(PK_BN, 3.0 * 4.0 * (double)n * C, 0.0, (cudaStream_t)stream);
-  bn_fwd(in, out, save_mean, save_invstd, running_mean, running_var, gamma, beta, n, C, eps, momentum, train != 0,
+  ProfScope ps(PK_BN, (out_bf16 ? 3.5 : 3.0) * 4.0 * (double)n * C, 0.0, (cudaStream_t)stream);
+  bn_fwd(in, out, (uint16_t *)out_bf16, save_mean, save_invstd, running_mean, running_var, gamma, beta, n, C, eps, momentum, train != 0,
          leakiness, (cudaStream_t)stream);
   SCN_CATCH
 }
 
 int scn_bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
-               const float *gamma, float *d_in, float *d_gamma, float *d_beta, int64_t n, int C, float leakiness,
-               void *stream) {
+               const float *gamma, const float *beta, float *d_in, float *d_gamma, float *d_beta, int64_t n, int C,
+               float leakiness, void *stream) {
   SCN_TRY
   ProfScope ps(PK_BN, 5.0 * 4.0 * (double)n * C, 0.0, (cudaStream_t)stream);
-  bn_bwd(in, out, d_out, save_mean, save_invstd, gamma, d_in, d_gamma, d_beta, n, C, leakiness, (cudaStream_t)stream);
+  bn_bwd(in, out, d_out, save_mean, save_invstd, gamma, beta, d_in, d_gamma, d_beta, n, C, leakiness, (cudaStream_t)stream);
   SCN_CATCH
 }
 

@@ -126,6 +126,10 @@ struct Meta {
   DevBuf<int> row_of_point;  // [P]
   DevBuf<int> rule_ptr;      // [N+1]
   DevBuf<int> rule_pts;      // [P] point ids grouped by row, original order inside a row
+  // scn_bf16_operand(): a caller-owned bf16 copy of the fp32 matrix at hint_src, for the next convolution entry
+  const float *hint_src = nullptr;
+  void *hint_bf16 = nullptr;
+  int hint_ready = 0;
   ~Meta();
 };
 
@@ -206,11 +210,11 @@ void wgrad_tma(const WgradArgs &a, cudaStream_t s);
 void bias_grad(const float *d_out, float *d_bias, long long n_rows, int C, cudaStream_t s);
 
 // bn.cu
-void bn_fwd(const float *in, float *out, float *save_mean, float *save_invstd, float *running_mean, float *running_var,
-            const float *gamma, const float *beta, long long n, int C, float eps, float momentum, bool train,
-            float leakiness, cudaStream_t s);
+void bn_fwd(const float *in, float *out, uint16_t *out_bf16, float *save_mean, float *save_invstd, float *running_mean,
+            float *running_var, const float *gamma, const float *beta, long long n, int C, float eps, float momentum,
+            bool train, float leakiness, cudaStream_t s);
 void bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
-            const float *gamma, float *d_in, float *d_gamma, float *d_beta, long long n, int C, float leakiness,
+            const float *gamma, const float *beta, float *d_in, float *d_gamma, float *d_beta, long long n, int C, float leakiness,
             cudaStream_t s);
 
 }  // namespace scn

@@ -35,6 +35,38 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# ---- bf16 operand copies (precision 'bf16') ---------------------------------------------------------------------
+# A producer (BatchNormReLU) may attach the bf16 copy of its output to the tensor; a convolution that finds a valid
+# copy (same storage, unchanged version counter) hands it to the library instead of paying for a cast pass, and
+# keeps it for the weight gradient.  Purely an optimisation: without a copy the library makes its own.
+def wants_bf16(channels):
+    return _precision == _lib.BF16 and channels % 64 == 0
+
+
+def attach_bf16(t, copy):
+    t._scn_bf16 = (t._version, t.data_ptr(), copy)
+
+
+def bf16_operand(m, x, c_in, c_out):
+    """Register the bf16 copy of `x` for the next convolution entry on handle m.  Returns the copy (kept by the
+    caller for the backward pass) or None when this layer does not run on bf16 tiles."""
+    if not _lib.lib().scn_bf16_plan(int(c_in), int(c_out), _precision) or x.numel() == 0:
+        return None
+    held = getattr(x, "_scn_bf16", None)
+    if held is not None and held[0] == x._version and held[1] == x.data_ptr() and held[2].shape == x.shape:
+        copy, ready = held[2], 1
+    else:
+        copy, ready = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device), 0
+    _lib.check(_lib.lib().scn_bf16_operand(m._handle(), _ptr(x), _ptr(copy), ready))
+    return copy
+
+
+def bf16_operand_again(m, x, copy):
+    """Backward pass: `copy` was filled during the forward call."""
+    if copy is not None:
+        _lib.check(_lib.lib().scn_bf16_operand(m._handle(), _ptr(x), _ptr(copy), 1))
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else C.c_void_p(0)
 
@@ -263,11 +295,15 @@ def Deconvolution_backward(in_size, out_size, filter_size, filter_stride, m, inp
 
 # ---- batch norm (sparseconvnet.h:21-33) ------------------------------------------------------------------
 def BatchNormalization_updateOutput(input_features, output_features, saveMean, saveInvStd, runningMean, runningVar,
-                                    weight, bias, eps, momentum, train, leakiness):
+                                    weight, bias, eps, momentum, train, leakiness, output_bf16=None):
+    """output_bf16 (extension): an EMPTY bfloat16 tensor that receives the bf16 copy of the output for the
+    tensor-core convolution that follows (see attach_bf16 / bf16_operand)."""
     x = _cuda_f32(input_features, "input")
     with torch.cuda.device(x.device):
         output_features.resize_(x.size(0), x.size(1))
-        _lib.check(_lib.lib().scn_bn_fwd(_ptr(x), _ptr(output_features), _ptr(saveMean), _ptr(saveInvStd),
+        if output_bf16 is not None:
+            output_bf16.resize_(x.size(0), x.size(1))
+        _lib.check(_lib.lib().scn_bn_fwd(_ptr(x), _ptr(output_features), _ptr(output_bf16), _ptr(saveMean), _ptr(saveInvStd),
                                          _ptr(runningMean), _ptr(runningVar), _ptr(_opt(weight)), _ptr(_opt(bias)),
                                          x.size(0), x.size(1), float(eps), float(momentum), int(bool(train)),
                                          float(leakiness), _stream()))
@@ -279,7 +315,7 @@ def BatchNormalization_backward(input_features, d_input_features, output_feature
     with torch.cuda.device(x.device):
         d_input_features.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_bn_bwd(_ptr(x), _ptr(output_features), _ptr(g), _ptr(saveMean), _ptr(saveInvStd),
-                                         _ptr(_opt(weight)), _ptr(d_input_features), _ptr(_opt(d_weight)),
+                                         _ptr(_opt(weight)), _ptr(_opt(bias)), _ptr(d_input_features), _ptr(_opt(d_weight)),
                                          _ptr(_opt(d_bias)), x.size(0), x.size(1), float(leakiness), _stream()))
 
 

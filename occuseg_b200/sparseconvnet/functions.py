@@ -26,6 +26,7 @@ class SubmanifoldConvolutionFunction(Function):
         ctx.scn_meta, ctx.dilated_rate = metadata, dilated_rate
         ctx.save_for_backward(x, spatial_size, weight, bias, filter_size)
         out = x.new_empty(0)
+        ctx.x16 = SCN.bf16_operand(metadata, x, weight.size(1), weight.size(2))
         _count(SCN.SubmanifoldConvolution_updateOutput(spatial_size, filter_size, metadata, x, out, weight, bias,
                                                        dilated_rate), out)
         return out
@@ -36,9 +37,10 @@ class SubmanifoldConvolutionFunction(Function):
         gw, gb = torch.zeros_like(weight), torch.zeros_like(bias)
         # the layer behind the InputLayer has no use for d_input (point features are data): skip that product
         gx = grad_out.new_empty(0) if ctx.needs_input_grad[0] else None
+        SCN.bf16_operand_again(ctx.scn_meta, x, ctx.x16)
         SCN.SubmanifoldConvolution_backward(spatial_size, filter_size, ctx.scn_meta, x, gx, grad_out.contiguous(),
                                             weight, gw, gb, ctx.dilated_rate)
-        del ctx.scn_meta
+        del ctx.scn_meta, ctx.x16
         return gx, gw, optionalTensorReturn(gb), None, None, None, None, None
 
 
@@ -51,6 +53,7 @@ class _StridedFunction(Function):
         ctx.scn_meta = metadata
         ctx.save_for_backward(x, in_size, weight, bias, out_size, filter_size, filter_stride)
         out = x.new_empty(0)
+        ctx.x16 = SCN.bf16_operand(metadata, x, weight.size(1), weight.size(2))
         _count(cls.fwd(in_size, out_size, filter_size, filter_stride, metadata, x, out, weight, bias), out)
         return out
 
@@ -58,8 +61,9 @@ class _StridedFunction(Function):
     def _backward(cls, ctx, grad_out):
         x, in_size, weight, bias, out_size, filter_size, filter_stride = ctx.saved_tensors
         gx, gw, gb = grad_out.new_empty(0), torch.zeros_like(weight), torch.zeros_like(bias)
+        SCN.bf16_operand_again(ctx.scn_meta, x, ctx.x16)
         cls.bwd(in_size, out_size, filter_size, filter_stride, ctx.scn_meta, x, gx, grad_out.contiguous(), weight, gw, gb)
-        del ctx.scn_meta
+        del ctx.scn_meta, ctx.x16
         return gx, gw, optionalTensorReturn(gb), None, None, None, None, None, None
 
 
@@ -94,17 +98,22 @@ class BatchNormalizationFunction(Function):
         n_planes = running_mean.shape[0]
         out = x.new_empty(0)
         save_mean, save_invstd = x.new_empty(n_planes), x.new_empty(n_planes)
+        # second, non-differentiable output: the bf16 copy of `out` for the tensor-core convolution that follows
+        out16 = torch.empty(0, dtype=torch.bfloat16, device=x.device)
         SCN.BatchNormalization_updateOutput(x, out, save_mean, save_invstd, running_mean, running_var, weight, bias,
-                                            eps, momentum, train, leakiness)
-        ctx.save_for_backward(x, out, weight, bias, running_mean, running_var, save_mean, save_invstd)
-        return out
+                                            eps, momentum, train, leakiness,
+                                            out16 if SCN.wants_bf16(n_planes) and x.is_cuda else None)
+        # the backward pass recomputes the activation mask from x, so `out` is not kept alive for it
+        ctx.save_for_backward(x, weight, bias, running_mean, running_var, save_mean, save_invstd)
+        ctx.mark_non_differentiable(out16)
+        return out, out16
 
     @staticmethod
-    def backward(ctx, grad_out):
-        x, out, weight, bias, running_mean, running_var, save_mean, save_invstd = ctx.saved_tensors
+    def backward(ctx, grad_out, _grad_out16=None):
+        x, weight, bias, running_mean, running_var, save_mean, save_invstd = ctx.saved_tensors
         assert ctx.train, "BatchNormalization backward is only defined in training mode (as in the reference)"
         gx, gw, gb = grad_out.new_empty(0), torch.zeros_like(weight), torch.zeros_like(bias)
-        SCN.BatchNormalization_backward(x, gx, out, grad_out.contiguous(), save_mean, save_invstd, running_mean,
+        SCN.BatchNormalization_backward(x, gx, None, grad_out.contiguous(), save_mean, save_invstd, running_mean,
                                         running_var, weight, bias, gw, gb, ctx.leakiness)
         return gx, optionalTensorReturn(gw), optionalTensorReturn(gb), None, None, None, None, None, None
 

@@ -13,6 +13,7 @@ Parameter names, shapes and initialisation (normal(0, sqrt(2/(nIn*volume)))) fol
 import torch
 from torch.nn import Module, Parameter
 
+from . import SCN
 from . import functions as F
 from .SCN import Metadata_3
 from .tensor import SparseConvNetTensor
@@ -238,9 +239,12 @@ class BatchNormalization(Module):
     def forward(self, input):
         assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes, \
             (self.nPlanes, input.features.shape)
-        feats = F.BatchNormalizationFunction.apply(input.features, optionalTensor(self, "weight"),
-                                                   optionalTensor(self, "bias"), self.running_mean, self.running_var,
-                                                   self.eps, self.momentum, self.training, self.leakiness)
+        feats, feats16 = F.BatchNormalizationFunction.apply(input.features, optionalTensor(self, "weight"),
+                                                            optionalTensor(self, "bias"), self.running_mean,
+                                                            self.running_var, self.eps, self.momentum, self.training,
+                                                            self.leakiness)
+        if feats16.numel():
+            SCN.attach_bf16(feats, feats16)
         return _same(input, feats)
 
     def input_spatial_size(self, out_size):

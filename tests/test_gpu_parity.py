@@ -302,3 +302,33 @@ def test_full_size_properties():
         o = np.flatnonzero(nbr[k] >= 0)
         assert np.array_equal(nbr[26 - k][nbr[k][o]], o)
     assert n_rules == int((nbr >= 0).sum())
+
+
+def test_bf16_operand_copies_are_equivalent():
+    """precision 'bf16': the copy BatchNormReLU attaches to its output, and the copy a convolution keeps for its
+    weight gradient, must give bit-identical results to the copies the library makes on its own."""
+    coords, _ = scenes.make_batch("small", (0, 1))
+    scn.set_precision("bf16")
+    torch.manual_seed(3)
+    inp = scn.InputLayer(3, SIZE, mode=4)
+    x0 = [torch.from_numpy(coords).float(), torch.randn(len(coords), 64, device="cuda"), None, 2]
+    bn = scn.BatchNormReLU(64).cuda()
+    conv = scn.SubmanifoldConvolution(3, 64, 64, 3, False).cuda()
+    t = bn(inp(x0))
+    held = t.features._scn_bf16
+    assert torch.equal(held[2], t.features.to(torch.bfloat16))           # round-to-nearest-even, like torch
+    y_a = conv(t).features
+    y_a.square().sum().backward()
+    g_a = conv.weight.grad.clone()
+    conv.weight.grad = None
+    del t.features._scn_bf16                                             # library makes its own copies
+    t2 = scn.SparseConvNetTensor(t.features.detach().clone().requires_grad_(True), t.metadata, t.spatial_size)
+    y_b = conv(t2).features
+    y_b.square().sum().backward()
+    assert torch.equal(y_a, y_b) and torch.equal(g_a, conv.weight.grad)
+    # an in-place change invalidates the attached copy (version counter)
+    t3 = bn(inp(x0))
+    with torch.no_grad():
+        t3.features.mul_(2.0)
+    y_c = conv(t3).features
+    assert rel_err(y_c.detach().cpu().numpy(), (2 * y_a).detach().cpu().numpy()) < 1e-6
