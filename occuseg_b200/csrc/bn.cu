@@ -72,23 +72,27 @@ __global__ void __launch_bounds__(RED_THREADS) k_bn_reduce(const float *__restri
       }
     }
   };
+  constexpr int U = MODE == 0 ? 8 : 4;      // independent rows in flight per thread (8 x 16-byte loads either way)
   for (long long rb = r_begin + rl; rb < r_end; rb += (long long)row_lanes * ROWS_PER_FLUSH) {
-    float s0[4][VEC], s1[4][VEC];
+    float s0[U][VEC], s1[U][VEC];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int j = 0; j < VEC; ++j) s0[u][j] = s1[u][j] = 0.f;
     long long r = rb;
     const long long stop = rb + (long long)row_lanes * ROWS_PER_FLUSH < r_end ? rb + (long long)row_lanes * ROWS_PER_FLUSH : r_end;
-    for (; r + 3ll * row_lanes < stop; r += 4ll * row_lanes) {
+    for (; r + (long long)(U - 1) * row_lanes < stop; r += (long long)U * row_lanes) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) fold(r + (long long)u * row_lanes, s0[u], s1[u]);
+      for (int u = 0; u < U; ++u) fold(r + (long long)u * row_lanes, s0[u], s1[u]);
     }
     for (; r < stop; r += row_lanes) fold(r, s0[0], s1[0]);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      t0[j] += (double)((s0[0][j] + s0[1][j]) + (s0[2][j] + s0[3][j]));
-      t1[j] += (double)((s1[0][j] + s1[1][j]) + (s1[2][j] + s1[3][j]));
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) { a0 += s0[u][j]; a1 += s1[u][j]; }
+      t0[j] += (double)a0;
+      t1[j] += (double)a1;
     }
   }
   if (threadIdx.x < cv * row_lanes) {
