@@ -113,18 +113,19 @@ static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, 
   DevBuf<uint16_t> w16;
   Bf16Copy x16;
   const float *use = w;
-  const size_t wn = (size_t)a.V * a.c_in * a.c_out;
+  const int wv = a.n_taps ? a.n_taps : a.V;        // weight taps (the one-tap-per-row form has V = 1 table row, n_taps weights)
+  const size_t wn = (size_t)wv * a.c_in * a.c_out;
   if (want_kn != native_kn) {
     tmp.alloc(wn, s);
     // source rows/cols: native_kn -> [c_in][c_out], else [c_out][c_in]
-    if (native_kn) transpose_weight(w, tmp.p, a.V, a.c_in, a.c_out, s);
-    else transpose_weight(w, tmp.p, a.V, a.c_out, a.c_in, s);
+    if (native_kn) transpose_weight(w, tmp.p, wv, a.c_in, a.c_out, s);
+    else transpose_weight(w, tmp.p, wv, a.c_out, a.c_in, s);
     use = tmp.p;
   }
   const double es = a.bf16 ? 2.0 : 4.0;      // bytes per gathered element
   // algorithmic work (gather/scatter model): R*Cin*s + N*Cout*4 + 4*R + V*Cin*Cout*s
   const double bytes = es * (double)a.n_rules * a.c_in + 4.0 * (double)(a.scatter ? a.n_rules : a.n_rows) * a.c_out +
-                       4.0 * (double)a.n_rules + es * (double)a.V * a.c_in * a.c_out;
+                       4.0 * (double)a.n_rules + es * (double)wv * a.c_in * a.c_out;
   const double flops = 2.0 * (double)a.n_rules * a.c_in * a.c_out;
   if (a.bf16) {
     w16.alloc(wn, s);
@@ -150,13 +151,26 @@ static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, 
 
 // One-rule-per-fine-row products (Deconvolution forward, strided-Convolution dgrad):
 //   out[i] = in[parent[i]] * Wk(off[i]).   fp32: input-stationary scatter over the child table;
-//   tensor cores: gather over the `up` table (exactly one live tap per row, absent taps are skipped per tile).
+//   tensor cores: the fine rows regrouped by tap (see below).
 static void run_up(Level *F, Level *C, const float *in, const float *w, bool native_kn, float *out, int c_in, int c_out,
                    int precision, cudaStream_t s, const uint16_t *in16 = nullptr) {
+  // tensor cores: the fine rows grouped by tap (whole 256-row tile groups per tap), one gathered row and one weight tap
+  // per row -- no work is spent on the 7 taps a row does not have
   ConvArgs g;
-  g.in = in; g.out = out; g.tbl = F->up.p; g.tbl_stride = F->n_pad; g.n_rows = F->n; g.V = 8;
-  g.c_in = c_in; g.c_out = c_out; g.n_rules = F->n; g.in_rows = C->n;
+  g.in = in; g.out = out; g.V = 1; g.c_in = c_in; g.c_out = c_out; g.n_rules = F->n; g.in_rows = C->n;
+  g.n_rows = 1;   // placeholder for the support check; set below
+  g.bf16 = bf16_conv_shape(c_in, c_out, precision);
   if (precision != SCN_FP32 && conv_tma_supported(g)) {
+    build_pair_list(F->up_pairs, F->child.p, 8, C->n_pad, F->n, 256, 0xFF, s);
+    PairList &P = F->up_pairs;
+    g.tbl = P.si.p;                     // gathered (coarse) row of every rule
+    g.tbl_stride = (int)(P.n_items_ub * 256);
+    g.n_rows = (int)(P.n_items_ub * 256);
+    g.out_rows = P.gi.p;                // fine row every result goes to
+    g.item_off = P.item_off.p;
+    g.rows_per_item = 256;
+    g.n_taps = 8;
+    g.out_limit = F->n;
     run_conv(g, w, native_kn, precision, s, in16);
     return;
   }
@@ -172,7 +186,7 @@ static void run_wgrad(WgradArgs a, PairList &pairs, int precision, cudaStream_t 
   const int cg = a.table_on_a ? a.c_a : a.c_b, cs = a.table_on_a ? a.c_b : a.c_a;
   a.bf16 = bf16_wgrad_shape(cg, cs, precision);
   if (precision != SCN_FP32) {
-    build_pair_list(pairs, a.tbl, a.V, a.tbl_stride, a.n_rules, s);
+    build_pair_list(pairs, a.tbl, a.V, a.tbl_stride, a.n_rules, PAIR_ITEM, 0x7F, s);
     a.gi = pairs.gi.p; a.si = pairs.si.p; a.blk_item = pairs.blk_item.p; a.n_blk = pairs.n_blk; a.blk_rows = BLK_ROWS;
   }
   const bool tcore = precision != SCN_FP32 && wgrad_tma_supported(a);

@@ -88,10 +88,12 @@ struct PairList {
   DevBuf<int> item_off;      // [V+1] first item (PAIR_ITEM rules) of every tap; item_off[V] = number of items
   DevBuf<int> blk_item;      // [V][n_blk+1] item holding tap k's first rule whose column is >= b*BLK_ROWS
   int n_blk = 0;
+  int unit = PAIR_ITEM;      // rules per item (64 for the weight gradient, 256 = one tile group for the "up" products)
   long long n_items_ub = 0;  // host-side upper bound of item_off[V]
 };
 constexpr int BLK_ROWS = 512;
-void build_pair_list(PairList &out, const int *tbl, int V, int stride, long long n_rules, cudaStream_t s);
+void build_pair_list(PairList &out, const int *tbl, int V, int stride, long long n_rules, int unit, int pad_byte,
+                     cudaStream_t s);
 
 // ---- one scale of one batch -------------------------------------------------------------------------
 struct Level {
@@ -113,7 +115,7 @@ struct Level {
   DevBuf<uint8_t> off8;      // [n]   (x&1)*4+(y&1)*2+(z&1)
   DevBuf<int> child;         // [8][coarse->n_pad] fine row or -1
   PairList child_pairs;      // 8 compacted (fine, coarse) lists
-  DevBuf<int> up;            // [8][n_pad]  up[k][i] = parent[i] if off8[i]==k else -1 (one tap per fine row)
+  PairList up_pairs;         // the same lists padded to whole 256-row tile groups (-1), for the one-tap-per-row products
 };
 
 struct Meta {
@@ -167,6 +169,12 @@ struct ConvArgs {
   int c_in = 0, c_out = 0;
   long long n_rules = 0;           // live table entries (for the algorithmic-bytes model only)
   bool mirror = false;             // GATHER: use table row V-1-k for weight tap k (dgrad of a submanifold conv)
+  // tensor-core kernel, one-tap-per-row products (deconvolution forward, strided dgrad): V = 1, tbl = the gathered row of
+  // every rule, rules grouped by tap in items of `rows_per_item` rows (item_off[k] = first item of weight tap k, n_taps + 1
+  // entries), result row j goes to out_rows[j] (< 0 or >= out_limit: padding)
+  const int *out_rows = nullptr;
+  const int *item_off = nullptr;
+  int rows_per_item = 0, n_taps = 0, out_limit = 0;
   bool scatter = false;
 };
 void conv_simt(const ConvArgs &a, cudaStream_t s);

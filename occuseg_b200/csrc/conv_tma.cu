@@ -263,6 +263,9 @@ struct ConvParams {
   int TN, MT, stages, nprod, ni, b_stage, stage_bytes, tmem_cols, n_groups;
   int bf16, kelems;            // operand type; elements per 128-byte K chunk (32 tf32 / 64 bf16)
   const void *in;              // base of the gathered matrix (L2 prefetch of upcoming rows)
+  // one-tap-per-row form (see ConvArgs): weight tap of a tile group from item_off, result rows scattered through out_rows
+  const int *out_rows, *item_off;
+  int rows_per_item, n_taps, out_limit;
   unsigned long long *trace;   // SCN_TRACE=1: clock64 totals over all CTAs (debug only): see conv_tma()
 };
 
@@ -462,7 +465,12 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
               }
             mbar_expect_tx(full_bar + 8 * s, any ? (uint32_t)(p.b_stage + groups * 512) : 0u);
             if (any) {
-              const int wtap = p.mirror ? p.V - 1 - trow : trow;
+              int wtap = p.mirror ? p.V - 1 - trow : trow;
+              if (p.item_off) {           // tile groups are tap-pure: the tap whose item range holds this group
+                const int item = (tg * p.MT * TM) / p.rows_per_item;
+                wtap = 0;
+                for (int k = 1; k < p.n_taps; ++k) wtap += (__ldg(&p.item_off[k]) <= item) ? 1 : 0;
+              }
               tma_tile_2d(st + p.MT * A_STAGE, &map_w, kc * p.kelems, wtap * p.c_out + n0, full_bar + 8 * s);
             }
             TRC(t_b += clock64() - ti;)
@@ -527,12 +535,17 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
       mbar_wait_warp(accf_bar + 8 * buf, (uint32_t)(gi >> 1) & 1u, lane);
       tc_fence_after();
       for (int m = 0; m < p.MT; ++m) {
-        const int r = (tg * p.MT + m) * TM + quarter * 32 + lane;
+        int r = (tg * p.MT + m) * TM + quarter * 32 + lane;
+        bool live = r < p.n_rows;
+        if (p.out_rows) {                 // scattered result rows (each written exactly once)
+          r = live ? __ldg(&p.out_rows[r]) : -1;
+          live = r >= 0 && r < p.out_limit;
+        }
         float *orow = p.out + (long long)r * p.c_out + n0;
         for (int c0 = 0; c0 < p.TN; c0 += 32) {
           float v[32];
           tmem_ld32(tq + buf * acc_cols + m * p.TN + c0, v);
-          if (r < p.n_rows) {
+          if (live) {
 #pragma unroll
             for (int q = 0; q < 32; q += 4) {
               float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
@@ -782,6 +795,8 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   SCN_CHECK(a.weight_nk != nullptr, "conv_tma needs the [V][Cout][Cin] weight layout");
   if (a.n_rows == 0) return;
   ConvParams p;
+  p.out_rows = a.out_rows; p.item_off = a.item_off; p.rows_per_item = a.rows_per_item; p.n_taps = a.n_taps;
+  p.out_limit = a.out_limit;
   p.in = a.in; p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
   p.V = a.V; p.c_in = a.c_in; p.c_out = a.c_out; p.mirror = a.mirror ? 1 : 0;
   p.bf16 = a.bf16 ? 1 : 0;
@@ -814,7 +829,7 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   p.n_groups = (tiles + p.MT - 1) / p.MT;
   const size_t smem = (size_t)fixed + (size_t)p.stages * p.stage_bytes;
   CUtensorMap mx = make_map(a.in, a.bf16, (uint64_t)a.c_in, (uint64_t)a.in_rows, p.kelems, 1, CU_TENSOR_MAP_SWIZZLE_128B);
-  CUtensorMap mw = make_map(a.weight_nk, a.bf16, (uint64_t)a.c_in, (uint64_t)a.V * a.c_out, p.kelems, (uint32_t)p.TN,
+  CUtensorMap mw = make_map(a.weight_nk, a.bf16, (uint64_t)a.c_in, (uint64_t)(a.n_taps ? a.n_taps : a.V) * a.c_out, p.kelems, (uint32_t)p.TN,
                             CU_TENSOR_MAP_SWIZZLE_128B);
   static size_t configured = 0;
   if (smem > configured) {

@@ -63,8 +63,7 @@ __global__ void k_rows_of_points(const int *__restrict__ run_ptr, const int *__r
 // stride-2 link: parent / offset of every fine row, child table of every coarse row
 __global__ void k_link_levels(const int *__restrict__ run_ptr, const int *__restrict__ sorted_idx,
                               const uint64_t *__restrict__ fine_keys, int n_runs, int child_stride,
-                              int *__restrict__ parent, uint8_t *__restrict__ off8, int *__restrict__ child,
-                              int up_stride, int *__restrict__ up) {
+                              int *__restrict__ parent, uint8_t *__restrict__ off8, int *__restrict__ child) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_runs) return;
   for (int j = run_ptr[r]; j < run_ptr[r + 1]; ++j) {
@@ -75,7 +74,6 @@ __global__ void k_link_levels(const int *__restrict__ run_ptr, const int *__rest
     parent[i] = r;
     off8[i] = (uint8_t)off;
     child[off * child_stride + r] = i;
-    up[off * up_stride + i] = r;
   }
 }
 
@@ -165,7 +163,7 @@ struct IsRule {
 };
 // rank[i] = number of rules before flat position i.  One thread block: tap k owns rules rank[k*stride] ..
 // rank[(k+1)*stride]-1; its list starts at item_off[k] (PAIR_ITEM rules per item, every tap rounded up).
-__global__ void k_pair_offsets(const int *__restrict__ tbl, const int *__restrict__ rank, int V, int stride,
+__global__ void k_pair_offsets(const int *__restrict__ tbl, const int *__restrict__ rank, int V, int stride, int unit,
                                int *__restrict__ item_off, int *__restrict__ rank_base) {
   if (threadIdx.x != 0) return;
   const long long last = (long long)V * stride - 1;
@@ -176,11 +174,11 @@ __global__ void k_pair_offsets(const int *__restrict__ tbl, const int *__restric
     const int e = (k + 1 < V) ? rank[(long long)(k + 1) * stride] : total;
     item_off[k] = items;
     rank_base[k] = b;
-    items += (e - b + PAIR_ITEM - 1) / PAIR_ITEM;
+    items += (e - b + unit - 1) / unit;
   }
   item_off[V] = items;
 }
-__global__ void k_block_items(const int *__restrict__ rank, int V, int stride, int n_blk, int blk_rows,
+__global__ void k_block_items(const int *__restrict__ rank, int V, int stride, int n_blk, int blk_rows, int unit,
                               const int *__restrict__ item_off, const int *__restrict__ rank_base,
                               int *__restrict__ blk_item) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -188,10 +186,10 @@ __global__ void k_block_items(const int *__restrict__ rank, int V, int stride, i
   const int k = i / (n_blk + 1), b = i - k * (n_blk + 1);
   const long long col = (long long)b * blk_rows;
   blk_item[i] = (b == n_blk || col >= stride) ? item_off[k + 1]
-                                              : item_off[k] + (rank[(long long)k * stride + col] - rank_base[k]) / PAIR_ITEM;
+                                              : item_off[k] + (rank[(long long)k * stride + col] - rank_base[k]) / unit;
 }
 __global__ void k_scatter_pairs(const int *__restrict__ tbl, const int *__restrict__ rank, long long n_flat, int stride,
-                                const int *__restrict__ item_off, const int *__restrict__ rank_base,
+                                int unit, const int *__restrict__ item_off, const int *__restrict__ rank_base,
                                 int *__restrict__ gi, int *__restrict__ si) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n_flat) return;
@@ -199,7 +197,7 @@ __global__ void k_scatter_pairs(const int *__restrict__ tbl, const int *__restri
   if (t < 0) return;
   const int k = (int)(i / stride);
   const int col = (int)(i - (long long)k * stride);
-  const long long pos = (long long)item_off[k] * PAIR_ITEM + (rank[i] - rank_base[k]);
+  const long long pos = (long long)item_off[k] * unit + (rank[i] - rank_base[k]);
   gi[pos] = t;
   si[pos] = col;
 }
@@ -264,16 +262,18 @@ static void sort_and_group(DevBuf<uint64_t> &keys, DevBuf<int> &idx, long long n
   tmp.release(s);
 }
 
-void build_pair_list(PairList &out, const int *tbl, int V, int stride, long long n_rules, cudaStream_t s) {
+void build_pair_list(PairList &out, const int *tbl, int V, int stride, long long n_rules, int unit, int pad_byte,
+                     cudaStream_t s) {
   if (out.item_off.p) return;
+  out.unit = unit;
   const long long n_flat = (long long)V * stride;
   SCN_CHECK(n_flat > 0 && n_flat < (1ll << 31), "rule table too large for 32-bit ranks");
-  out.n_items_ub = (n_rules + (long long)(PAIR_ITEM - 1) * V) / PAIR_ITEM + 1;
-  out.gi.alloc((size_t)out.n_items_ub * PAIR_ITEM, s);
-  out.si.alloc((size_t)out.n_items_ub * PAIR_ITEM, s);
+  out.n_items_ub = (n_rules + (long long)(unit - 1) * V) / unit + 1;
+  out.gi.alloc((size_t)out.n_items_ub * unit, s);
+  out.si.alloc((size_t)out.n_items_ub * unit, s);
   out.item_off.alloc(V + 1, s);
-  SCN_CUDA(cudaMemsetAsync(out.gi.p, 0x7F, sizeof(int) * out.gi.n, s));   // PAIR_PAD
-  SCN_CUDA(cudaMemsetAsync(out.si.p, 0x7F, sizeof(int) * out.si.n, s));
+  SCN_CUDA(cudaMemsetAsync(out.gi.p, pad_byte, sizeof(int) * out.gi.n, s));   // 0x7F -> PAIR_PAD, 0xFF -> -1
+  SCN_CUDA(cudaMemsetAsync(out.si.p, pad_byte, sizeof(int) * out.si.n, s));
   DevBuf<int> rank, rank_base;
   rank.alloc((size_t)n_flat, s);
   rank_base.alloc(V, s);
@@ -284,14 +284,14 @@ void build_pair_list(PairList &out, const int *tbl, int V, int stride, long long
   tmp.alloc(tb, s);
   SCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags, rank.p, (int)n_flat, s));
   count_launch(2);
-  k_pair_offsets<<<1, 32, 0, s>>>(tbl, rank.p, V, stride, out.item_off.p, rank_base.p);
+  k_pair_offsets<<<1, 32, 0, s>>>(tbl, rank.p, V, stride, unit, out.item_off.p, rank_base.p);
   SCN_LAUNCH_CHECK();
-  k_scatter_pairs<<<grid_for(n_flat, 256), 256, 0, s>>>(tbl, rank.p, n_flat, stride, out.item_off.p, rank_base.p,
+  k_scatter_pairs<<<grid_for(n_flat, 256), 256, 0, s>>>(tbl, rank.p, n_flat, stride, unit, out.item_off.p, rank_base.p,
                                                          out.gi.p, out.si.p);
   SCN_LAUNCH_CHECK();
   out.n_blk = (stride + BLK_ROWS - 1) / BLK_ROWS;
   out.blk_item.alloc((size_t)V * (out.n_blk + 1), s);
-  k_block_items<<<grid_for((long long)V * (out.n_blk + 1), 256), 256, 0, s>>>(rank.p, V, stride, out.n_blk, BLK_ROWS,
+  k_block_items<<<grid_for((long long)V * (out.n_blk + 1), 256), 256, 0, s>>>(rank.p, V, stride, out.n_blk, BLK_ROWS, unit,
                                                                              out.item_off.p, rank_base.p, out.blk_item.p);
   SCN_LAUNCH_CHECK();
   rank.release(s);
@@ -386,11 +386,9 @@ void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
   DevBuf<unsigned long long> cnt;
   cnt.alloc(1, s);
   SCN_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long), s));
-  if (L->n_pad != L->n) {
-    // padding rows read as "absent" so tile kernels need no tail checks on the table
-    k_fill_int<<<grid_for((long long)27 * L->n_pad, 256), 256, 0, s>>>(L->nbr.p, (long long)27 * L->n_pad, -1);
-    SCN_LAUNCH_CHECK();
-  }
+  if (L->n_pad != L->n)   // padding rows read as "absent" so tile kernels need no tail checks on the table
+    for (int k = 0; k < 27; ++k)
+      SCN_CUDA(cudaMemsetAsync(L->nbr.p + (size_t)k * L->n_pad + L->n, 0xFF, sizeof(int) * (size_t)(L->n_pad - L->n), s));
   if (L->n) {
     k_neighbours<<<grid_for(L->n, 256), 256, 0, s>>>(L->keys.p, L->n, L->n_pad, L->hkeys.p, L->hvals.p, L->hmask,
                                                      L->nbr.p, cnt.p);
@@ -429,13 +427,9 @@ Level *ensure_coarse_level(Meta *m, Level *F, const int64_t coarse_size[3], cuda
   F->parent.alloc(F->n, s);
   F->off8.alloc(F->n, s);
   F->child.alloc((size_t)8 * C->n_pad, s);
-  k_fill_int<<<grid_for((long long)8 * C->n_pad, 256), 256, 0, s>>>(F->child.p, (long long)8 * C->n_pad, -1);
-  SCN_LAUNCH_CHECK();
-  F->up.alloc((size_t)8 * F->n_pad, s);
-  k_fill_int<<<grid_for((long long)8 * F->n_pad, 256), 256, 0, s>>>(F->up.p, (long long)8 * F->n_pad, -1);
-  SCN_LAUNCH_CHECK();
+  SCN_CUDA(cudaMemsetAsync(F->child.p, 0xFF, sizeof(int) * (size_t)8 * C->n_pad, s));      // -1 = no child at this offset
   k_link_levels<<<grid_for(C->n, 256), 256, 0, s>>>(runs.ptr.p, runs.sorted_idx.p, F->keys.p, C->n, C->n_pad,
-                                                    F->parent.p, F->off8.p, F->child.p, F->n_pad, F->up.p);
+                                                    F->parent.p, F->off8.p, F->child.p);
   SCN_LAUNCH_CHECK();
   F->coarse = C;
   m->levels.push_back(C);
