@@ -1,13 +1,16 @@
-// TMA-fed tcgen05 table convolutions for sm_100a (SCN_TF32 path, default).
+// tcgen05 + TMA table convolutions for sm_100a: the SCN_BF16 (default) and SCN_TF32 paths.
 //
-// Same math and tiling as conv_tc.cu, but the operands are moved by the Tensor Memory Accelerator instead
-// of by per-thread cp.async:
-//   * gathered rows:  cp.async.bulk.tensor.2d ... tile::gather4 -- ONE instruction fetches four arbitrary
-//     rows (128 bytes each) of the feature matrix into four consecutive swizzled shared-memory rows; an
-//     absent neighbour is requested as the out-of-bounds row index `rows`, which TMA zero-fills;
-//   * weights / stationary rows: ordinary 2-D tile loads.
-// Completion is counted in bytes on an mbarrier (expect_tx); the MMA thread consumes the stage and frees it
-// with tcgen05.commit.
+//   k_conv_tma  : forward / dgrad / strided / deconvolution as an output-stationary gather-GEMM
+//   k_wgrad_tma : weight gradients over per-tap compacted rule lists
+//
+// Operands are moved by the Tensor Memory Accelerator:
+//   * gathered rows:  cp.async.bulk.tensor.2d ... tile::gather4 -- ONE instruction fetches four arbitrary rows
+//     (128 bytes each = 64 bf16 or 32 tf32 channels) of a feature matrix into four consecutive swizzled
+//     shared-memory rows;
+//   * weights: ordinary 2-D tile loads.
+// Completion is counted in bytes on an mbarrier (expect_tx); one elected thread issues tcgen05.mma (fp32
+// accumulators in TMEM) and frees the stage with tcgen05.commit.  Replaces the reference's scalar shared-memory FMA
+// kernels with global atomics (CUDA/Convolution.cu:447-534,695-753,1059-1152; CUDA/Deconvolution.cu:9-554).
 //
 // What the micro-benchmarks (tools/ubench_pipe.cu, profiles/r01_ubench.md) say about this machine, and what the
 // kernels do about it:
