@@ -282,7 +282,13 @@ def run_ours(args):
                     "share_of_step": t["ms"] / ms_prof, "instrumented_ms_per_step": ms_prof / args.steps,
                     "tensor_tflops": t["flops"] / (t["ms"] * 1e-3) / 1e12 if t["flops"] else None,
                     "tensor_peak_tflops": tc_peak if args.precision == "bf16" else tc_peak / 2,
-                    "by_kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in kinds.items()}}
+                    "by_kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in kinds.items()},
+                    # the same algorithmic-bytes / CUDA-event-time ratio for every kernel family of the library
+                    "families": {k: {"achieved_gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None,
+                                     "frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm_peak if v["ms"] else None,
+                                     "launches_per_step": v["launches"] / args.steps,
+                                     "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["flops"] and v["ms"] else None}
+                                 for k, v in kinds.items()}}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
