@@ -105,7 +105,11 @@ int scn_bf16_plan(int c_in, int c_out, int precision);
  * CUDA/Convolution.cpp:104-210; kernels CUDA/Convolution.cu:447-534,695-753,1059-1152) ----------
  * out[N,Cout] = sum_k in[nbr_k(o)] * W[k];  *macs = sum_k n_k*Cin*Cout (the reference's return value) */
 int scn_subm_fwd(scn_meta *m, const int64_t spatial_size[3], const float *in, const float *weight, const float *bias,
-                 float *out, int c_in, int c_out, int precision, void *stream, double *macs);
+                 const float *residual, float *out, int c_in, int c_out, int precision, void *stream, double *macs);
+/* residual (extension, may be NULL): [N,Cout] fp32 added to the result in the kernel epilogue -- the shortcut of a
+ * residual block (networkArchitectures.py:225-240) without a separate add pass.  Only the tensor-core kernels take it:
+ * scn_fuses_residual(c_in, c_out, precision) says whether this layer shape does. */
+int scn_fuses_residual(int c_in, int c_out, int precision);
 /* d_in[N,Cin] (NULL: the input gradient is not needed and is skipped), d_weight[27,Cin,Cout], d_bias[Cout] (NULL when no bias) */
 int scn_subm_bwd(scn_meta *m, const int64_t spatial_size[3], const float *in, const float *d_out, const float *weight,
                  float *d_in, float *d_weight, float *d_bias, int c_in, int c_out, int precision, void *stream);
@@ -139,8 +143,10 @@ int scn_bn_fwd(const float *in, float *out, void *out_bf16, float *save_mean, fl
  * `out` (the forward output) is accepted for symmetry with the reference entry but never read: the activation mask is
  * recomputed from `in`, gamma and beta exactly as the forward pass computed it, so `out` may be NULL. */
 int scn_bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
-               const float *gamma, const float *beta, float *d_in, float *d_gamma, float *d_beta, int64_t n_rows,
-               int channels, float leakiness, void *stream);
+               const float *gamma, const float *beta, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta,
+               int64_t n_rows, int channels, float leakiness, void *stream);
+/* d_in_add (extension, may be NULL): [n_rows, channels] fp32 added to d_in in the same pass -- the gradient that
+ * reaches the same input through a residual shortcut, instead of a separate accumulation pass. */
 
 #ifdef __cplusplus
 }

@@ -200,7 +200,8 @@ __global__ void k_bn_finalize_bwd(const double *__restrict__ acc, long long n, i
 
 template <int VEC>
 __global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ x, const float *__restrict__ beta,
-                                                      const float *__restrict__ d, float *__restrict__ dx,
+                                                      const float *__restrict__ d, const float *__restrict__ add,
+                                                      float *__restrict__ dx,
                                                       const float *__restrict__ save_mean,
                                                       const float *__restrict__ save_invstd,
                                                       const float *__restrict__ gamma, const float *__restrict__ coef,
@@ -233,6 +234,14 @@ __global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ 
       int c = c0 + j;
       float dd = fmaf(sm[3 * C + c], xv[j], sm[4 * C + c]) > 0.f ? dv[j] : dv[j] * leak;
       ov[j] = (dd - sm[C + c] - (xv[j] - sm[c]) * sm[2 * C + c]) * sm[3 * C + c];
+    }
+    if (add) {          // gradient arriving through the residual shortcut of the same input: accumulated here
+      if (VEC == 4) {
+        const float4 av = __ldg(reinterpret_cast<const float4 *>(add) + e);
+        ov[0] += av.x; ov[1] += av.y; ov[2] += av.z; ov[3] += av.w;
+      } else {
+        ov[0] += __ldg(add + e);
+      }
     }
     if (VEC == 4) reinterpret_cast<float4 *>(dx)[e] = make_float4(ov[0], ov[1], ov[2], ov[3]);
     else dx[e] = ov[0];
@@ -276,12 +285,12 @@ void bn_fwd(const float *in, float *out, uint16_t *out_bf16, float *save_mean, f
 }
 
 void bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
-            const float *gamma, const float *beta, float *d_in, float *d_gamma, float *d_beta, long long n, int C, float leakiness,
+            const float *gamma, const float *beta, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta, long long n, int C, float leakiness,
             cudaStream_t s) {
   SCN_CHECK(C > 0 && C <= 4096, "BatchNorm: channel count out of range");
   if (n == 0) return;
-  bool v4 = (C % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)d_out % 16 == 0) &&
-            ((uintptr_t)d_in % 16 == 0);
+  bool v4 = (C % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)d_out % 16 == 0) && ((uintptr_t)d_in % 16 == 0) &&
+            ((uintptr_t)d_in_add % 16 == 0);
   DevBuf<double> acc;
   DevBuf<float> coef;
   acc.alloc(2 * (size_t)C, s);
@@ -296,8 +305,8 @@ void bn_bwd(const float *in, const float *out, const float *d_out, const float *
   k_bn_finalize_bwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, save_invstd, d_gamma, d_beta, coef.p);
   SCN_LAUNCH_CHECK();
   size_t smem = sizeof(float) * 5 * C;
-  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, beta, d_out, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness);
-  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, beta, d_out, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness);
+  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness);
+  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness);
   SCN_LAUNCH_CHECK();
   acc.release(s);
   coef.release(s);

@@ -408,8 +408,8 @@ int scn_strided_table(scn_meta *h, const int64_t fine[3], int32_t *parent, uint8
 }
 
 // ---- submanifold ------------------------------------------------------------------------------------
-int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const float *weight, const float *bias, float *out,
-                 int c_in, int c_out, int precision, void *stream, double *macs) {
+int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const float *weight, const float *bias,
+                 const float *residual, float *out, int c_in, int c_out, int precision, void *stream, double *macs) {
   SCN_TRY
   cudaStream_t s = (cudaStream_t)stream;
   check_channels(c_in, c_out);
@@ -418,6 +418,13 @@ int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   ConvArgs a;
   a.in = in; a.bias = bias; a.out = out;
   a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_in; a.c_out = c_out; a.n_rules = L->n_rules; a.in_rows = L->n;
+  a.residual = residual;
+  if (residual) {
+    ConvArgs probe = a;
+    probe.bf16 = bf16_conv_shape(c_in, c_out, precision);
+    SCN_CHECK(precision != SCN_FP32 && conv_tma_supported(probe) && (uintptr_t)residual % 16 == 0,
+              "SubmanifoldConvolution: a fused residual needs the tensor-core path (see scn_fuses_residual)");
+  }
   run_conv(a, weight, true, precision, s, take_bf16_hint(&h->m, in, (long long)L->n * c_in, s));
   if (macs) *macs = (double)L->n_rules * c_in * c_out;   // flops += nRules*ip*op, CPU/Convolution.cpp:134
   SCN_CATCH
@@ -540,6 +547,11 @@ int scn_bf16_operand(scn_meta *h, const float *fp32, void *bf16, int ready) {
   SCN_CATCH
 }
 
+int scn_fuses_residual(int c_in, int c_out, int precision) {
+  const int kel = bf16_conv_shape(c_in, c_out, precision) ? 64 : 32;
+  return precision != SCN_FP32 && c_in >= kel && c_in % kel == 0 && c_out >= 32 && c_out % 32 == 0;
+}
+
 int scn_bf16_plan(int c_in, int c_out, int precision) {
   return (bf16_conv_shape(c_in, c_out, precision) ? 1 : 0) | (bf16_wgrad_shape(c_in, c_out, precision) ? 2 : 0);
 }
@@ -555,11 +567,12 @@ int scn_bn_fwd(const float *in, float *out, void *out_bf16, float *save_mean, fl
 }
 
 int scn_bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
-               const float *gamma, const float *beta, float *d_in, float *d_gamma, float *d_beta, int64_t n, int C,
-               float leakiness, void *stream) {
+               const float *gamma, const float *beta, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta,
+               int64_t n, int C, float leakiness, void *stream) {
   SCN_TRY
-  ProfScope ps(PK_BN, 5.0 * 4.0 * (double)n * C, 0.0, (cudaStream_t)stream);
-  bn_bwd(in, out, d_out, save_mean, save_invstd, gamma, beta, d_in, d_gamma, d_beta, n, C, leakiness, (cudaStream_t)stream);
+  ProfScope ps(PK_BN, (d_in_add ? 6.0 : 5.0) * 4.0 * (double)n * C, 0.0, (cudaStream_t)stream);
+  bn_bwd(in, out, d_out, save_mean, save_invstd, gamma, beta, d_in_add, d_in, d_gamma, d_beta, n, C, leakiness,
+         (cudaStream_t)stream);
   SCN_CATCH
 }
 

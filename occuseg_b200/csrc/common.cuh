@@ -160,6 +160,7 @@ struct ConvArgs {
   const void *weight_nk = nullptr; // [V][c_out][c_in] as seen by THIS product (tensor-core kernel: K-major B operand), fp32 or bf16
   bool bf16 = false;               // tensor-core kernel: `in` and `weight_nk` are bf16 ([rows][c] uint16), fp32 accumulate and output
   const float *bias = nullptr;     // GATHER only
+  const float *residual = nullptr; // tensor-core kernel only: [n_rows, c_out] fp32 added to the result
   float *out = nullptr;
   const int *tbl = nullptr;
   int tbl_stride = 0;
@@ -222,7 +223,7 @@ void bn_fwd(const float *in, float *out, uint16_t *out_bf16, float *save_mean, f
             float *running_var, const float *gamma, const float *beta, long long n, int C, float eps, float momentum,
             bool train, float leakiness, cudaStream_t s);
 void bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
-            const float *gamma, const float *beta, float *d_in, float *d_gamma, float *d_beta, long long n, int C, float leakiness,
+            const float *gamma, const float *beta, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta, long long n, int C, float leakiness,
             cudaStream_t s);
 
 }  // namespace scn

@@ -260,6 +260,7 @@ constexpr int MAX_MT = 2;
 
 struct ConvParams {
   const float *bias;
+  const float *residual;       // optional [n_rows, c_out] fp32 added to the result (residual shortcut fused into the epilogue)
   float *out;
   const int *tbl;
   int tbl_stride, n_rows, V, c_in, c_out, mirror;
@@ -558,6 +559,10 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
                 o.z += __ldg(&p.bias[n0 + c0 + q + 2]);
                 o.w += __ldg(&p.bias[n0 + c0 + q + 3]);
               }
+              if (p.residual) {
+                const float4 rv = __ldg(reinterpret_cast<const float4 *>(p.residual + (long long)r * p.c_out + n0 + c0 + q));
+                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+              }
               *reinterpret_cast<float4 *>(orow + c0 + q) = o;
             }
           }
@@ -800,6 +805,7 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   ConvParams p;
   p.out_rows = a.out_rows; p.item_off = a.item_off; p.rows_per_item = a.rows_per_item; p.n_taps = a.n_taps;
   p.out_limit = a.out_limit;
+  p.residual = a.residual;
   p.in = a.in; p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
   p.V = a.V; p.c_in = a.c_in; p.c_out = a.c_out; p.mirror = a.mirror ? 1 : 0;
   p.bf16 = a.bf16 ? 1 : 0;

@@ -39,6 +39,11 @@ def _stream():
 # A producer (BatchNormReLU) may attach the bf16 copy of its output to the tensor; a convolution that finds a valid
 # copy (same storage, unchanged version counter) hands it to the library instead of paying for a cast pass, and
 # keeps it for the weight gradient.  Purely an optimisation: without a copy the library makes its own.
+def fuses_residual(c_in, c_out):
+    """True when SubmanifoldConvolution_updateOutput(nIn=c_in, nOut=c_out) can add a residual in its epilogue."""
+    return bool(_lib.lib().scn_fuses_residual(int(c_in), int(c_out), _precision))
+
+
 def wants_bf16(channels):
     return _precision == _lib.BF16 and channels % 64 == 0
 
@@ -209,10 +214,15 @@ def _check_weight(weight, v):
 
 
 def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_features, output_features, weight, bias,
-                                        dilated_rate=1):
+                                        dilated_rate=1, residual=None):
+    """residual (extension): [N, nOut] tensor added to the result inside the kernel (see fuses_residual)."""
     if int(dilated_rate) != 1 or any(int(f) != 3 for f in filter_size.tolist()):
         raise NotImplementedError("SubmanifoldConvolution: only 3x3x3, dilation 1 is on this path")
     x, w, b = _cuda_f32(input_features, "input"), _check_weight(weight, 27), _opt(bias)
+    if residual is not None:
+        residual = _cuda_f32(residual, "residual")
+        if residual.shape != (x.size(0), w.size(2)):
+            raise ValueError(f"SubmanifoldConvolution: residual is {tuple(residual.shape)}")
     macs = C.c_double(0.0)
     with torch.cuda.device(x.device):
         n = m.getNActive(spatial_size)
@@ -220,8 +230,8 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
             raise ValueError(f"SubmanifoldConvolution: input is {tuple(x.shape)}, scale has {n} rows, nIn={w.size(1)}")
         output_features.resize_(n, w.size(2))
         _lib.check(_lib.lib().scn_subm_fwd(m._handle(), _lib.size3(spatial_size), _ptr(x), _ptr(w), _ptr(b),
-                                           _ptr(output_features), w.size(1), w.size(2), _precision, _stream(),
-                                           C.byref(macs)))
+                                           _ptr(residual), _ptr(output_features), w.size(1), w.size(2), _precision,
+                                           _stream(), C.byref(macs)))
     return macs.value
 
 
@@ -310,12 +320,18 @@ def BatchNormalization_updateOutput(input_features, output_features, saveMean, s
 
 
 def BatchNormalization_backward(input_features, d_input_features, output_features, d_output_features, saveMean,
-                                saveInvStd, runningMean, runningVar, weight, bias, d_weight, d_bias, leakiness):
+                                saveInvStd, runningMean, runningVar, weight, bias, d_weight, d_bias, leakiness,
+                                d_input_add=None):
+    """d_input_add (extension): a gradient of the same input that arrived through a residual shortcut; it is added to
+    d_input in the same pass."""
     x, g = _cuda_f32(input_features, "input"), _cuda_f32(d_output_features, "grad")
+    if d_input_add is not None:
+        d_input_add = _cuda_f32(d_input_add, "d_input_add")
     with torch.cuda.device(x.device):
         d_input_features.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_bn_bwd(_ptr(x), _ptr(output_features), _ptr(g), _ptr(saveMean), _ptr(saveInvStd),
-                                         _ptr(_opt(weight)), _ptr(_opt(bias)), _ptr(d_input_features), _ptr(_opt(d_weight)),
+                                         _ptr(_opt(weight)), _ptr(_opt(bias)), _ptr(d_input_add), _ptr(d_input_features),
+                                         _ptr(_opt(d_weight)),
                                          _ptr(_opt(d_bias)), x.size(0), x.size(1), float(leakiness), _stream()))
 
 

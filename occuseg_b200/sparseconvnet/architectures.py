@@ -14,7 +14,7 @@ def _block(seq, dimension, a, b, residual, leakiness):
         for m in bn_conv(a, b) + bn_conv(b, b):
             body.add(m)
         shortcut = L.Identity() if a == b else L.NetworkInNetwork(a, b, False)
-        seq.add(L.ConcatTable().add(shortcut).add(body)).add(L.AddTable())
+        seq.add(L.ResidualConcatTable().add(shortcut).add(body)).add(L.AddTable())
     else:
         body = L.Sequential()
         for m in bn_conv(a, b):

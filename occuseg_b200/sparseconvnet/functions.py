@@ -22,13 +22,14 @@ def _count(macs, out):
 
 class SubmanifoldConvolutionFunction(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, metadata, spatial_size, dimension, filter_size, dilated_rate=1):
+    def forward(ctx, x, weight, bias, metadata, spatial_size, dimension, filter_size, dilated_rate=1, residual=None):
+        """residual (extension): added to the result in the kernel epilogue; its gradient is grad_out itself."""
         ctx.scn_meta, ctx.dilated_rate = metadata, dilated_rate
         ctx.save_for_backward(x, spatial_size, weight, bias, filter_size)
         out = x.new_empty(0)
         ctx.x16 = SCN.bf16_operand(metadata, x, weight.size(1), weight.size(2))
         _count(SCN.SubmanifoldConvolution_updateOutput(spatial_size, filter_size, metadata, x, out, weight, bias,
-                                                       dilated_rate), out)
+                                                       dilated_rate, residual), out)
         return out
 
     @staticmethod
@@ -41,7 +42,7 @@ class SubmanifoldConvolutionFunction(Function):
         SCN.SubmanifoldConvolution_backward(spatial_size, filter_size, ctx.scn_meta, x, gx, grad_out.contiguous(),
                                             weight, gw, gb, ctx.dilated_rate)
         del ctx.scn_meta, ctx.x16
-        return gx, gw, optionalTensorReturn(gb), None, None, None, None, None
+        return gx, gw, optionalTensorReturn(gb), None, None, None, None, None, (grad_out if ctx.needs_input_grad[8] else None)
 
 
 class _StridedFunction(Function):
@@ -93,7 +94,10 @@ class DeconvolutionFunction(_StridedFunction):
 
 class BatchNormalizationFunction(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, train, leakiness):
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, train, leakiness, with_alias=False):
+        """Returns (out, out16, alias).  out16: bf16 copy of out (or empty).  alias (with_alias): a view of x for the
+        shortcut branch of a residual block -- whatever gradient comes back through it is added to d_x inside the
+        backward kernel instead of by a separate accumulation pass."""
         ctx.train, ctx.leakiness = train, leakiness
         n_planes = running_mean.shape[0]
         out = x.new_empty(0)
@@ -106,16 +110,17 @@ class BatchNormalizationFunction(Function):
         # the backward pass recomputes the activation mask from x, so `out` is not kept alive for it
         ctx.save_for_backward(x, weight, bias, running_mean, running_var, save_mean, save_invstd)
         ctx.mark_non_differentiable(out16)
-        return out, out16
+        return out, out16, (x.view_as(x) if with_alias else x.new_empty(0))
 
     @staticmethod
-    def backward(ctx, grad_out, _grad_out16=None):
+    def backward(ctx, grad_out, _grad_out16=None, grad_alias=None):
         x, weight, bias, running_mean, running_var, save_mean, save_invstd = ctx.saved_tensors
         assert ctx.train, "BatchNormalization backward is only defined in training mode (as in the reference)"
         gx, gw, gb = grad_out.new_empty(0), torch.zeros_like(weight), torch.zeros_like(bias)
+        add = grad_alias.contiguous() if grad_alias is not None and grad_alias.numel() == x.numel() else None
         SCN.BatchNormalization_backward(x, gx, None, grad_out.contiguous(), save_mean, save_invstd, running_mean,
-                                        running_var, weight, bias, gw, gb, ctx.leakiness)
-        return gx, optionalTensorReturn(gw), optionalTensorReturn(gb), None, None, None, None, None, None
+                                        running_var, weight, bias, gw, gb, ctx.leakiness, add)
+        return gx, optionalTensorReturn(gw), optionalTensorReturn(gb), None, None, None, None, None, None, None
 
 
 class NetworkInNetworkFunction(Function):

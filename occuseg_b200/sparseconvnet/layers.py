@@ -60,6 +60,29 @@ class ConcatTable(torch.nn.Sequential):
         return self._modules["0"].input_spatial_size(out_size)
 
 
+class ResidualConcatTable(ConcatTable):
+    """ConcatTable([shortcut, Sequential(BN, SubmConv, BN, SubmConv)]) of a residual block -- same children, hence the
+    same state_dict keys as the reference (networkArchitectures.py:225-240) -- whose forward fuses the two elementwise
+    passes of the block into its kernels: the shortcut is added in the epilogue of the last convolution, and the
+    gradient that returns through the shortcut is added inside the first BatchNorm's backward kernel.  Returns a
+    one-element list, so the AddTable that follows passes it through."""
+
+    def forward(self, input):
+        shortcut, body = self._modules["0"], self._modules["1"]
+        mods = list(body._modules.values())
+        last = mods[-1]
+        fusable = (torch.is_grad_enabled() and len(mods) == 4 and isinstance(mods[0], BatchNormalization)
+                   and isinstance(last, SubmanifoldConvolution) and input.features.is_cuda
+                   and SCN.fuses_residual(last.nIn, last.nOut) and mods[0].training)
+        if not fusable:
+            return [shortcut(input), body(input)]
+        t, alias = mods[0](input, with_alias=True)
+        s = shortcut(alias)
+        for m in mods[1:-1]:
+            t = m(t)
+        return [last(t, residual=s.features)]
+
+
 class AddTable(torch.nn.Sequential):
     def forward(self, input):
         total = input[0].features
@@ -141,11 +164,12 @@ class SubmanifoldConvolution(_ConvBase):
         self._init_weight(dimension, nIn, nOut, filter_size, bias)
         self.dilated_rate = dilated_rate
 
-    def forward(self, input):
+    def forward(self, input, residual=None):
+        """residual (extension): features of the shortcut branch, added inside the kernel (SCN.fuses_residual)."""
         self._check(input)
         feats = F.SubmanifoldConvolutionFunction.apply(input.features, self.weight, optionalTensor(self, "bias"),
                                                        input.metadata, input.spatial_size, self.dimension,
-                                                       self.filter_size, self.dilated_rate)
+                                                       self.filter_size, self.dilated_rate, residual)
         return _same(input, feats)
 
     def input_spatial_size(self, out_size):
@@ -236,15 +260,18 @@ class BatchNormalization(Module):
             self.weight = Parameter(torch.ones(nPlanes))
             self.bias = Parameter(torch.zeros(nPlanes))
 
-    def forward(self, input):
+    def forward(self, input, with_alias=False):
+        """with_alias (extension): also return the input re-issued as a view whose gradient is folded into this
+        layer's backward kernel (used for the shortcut of a residual block)."""
         assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes, \
             (self.nPlanes, input.features.shape)
-        feats, feats16 = F.BatchNormalizationFunction.apply(input.features, optionalTensor(self, "weight"),
-                                                            optionalTensor(self, "bias"), self.running_mean,
-                                                            self.running_var, self.eps, self.momentum, self.training,
-                                                            self.leakiness)
+        feats, feats16, alias = F.BatchNormalizationFunction.apply(
+            input.features, optionalTensor(self, "weight"), optionalTensor(self, "bias"), self.running_mean,
+            self.running_var, self.eps, self.momentum, self.training, self.leakiness, with_alias)
         if feats16.numel():
             SCN.attach_bf16(feats, feats16)
+        if with_alias:
+            return _same(input, feats), _same(input, alias)
         return _same(input, feats)
 
     def input_spatial_size(self, out_size):

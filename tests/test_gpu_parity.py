@@ -385,3 +385,28 @@ def test_prebuilt_scale_chain_equals_lazy_build():
         assert np.array_equal(a, b)
     assert tabs[0][3:6] == tabs[1][3:6]
     assert np.array_equal(tabs[0][6], tabs[1][6])
+
+
+def test_fused_residual_block_equals_unfused():
+    """ResidualConcatTable folds the shortcut add into the last convolution's epilogue and the shortcut's gradient into
+    the first BatchNorm's backward kernel.  Same single fp32 additions as the AddTable / autograd accumulation they
+    replace, so the outputs must be bit-identical; the gradients are compared at 1e-5 because weight gradients are
+    merged with floating-point atomics whose order differs from run to run.  Covers both shortcuts (identity, NiN)."""
+    from occuseg_b200.sparseconvnet import SCN as scn_SCN
+    coords, _ = scenes.make_batch("small", (0, 1))
+    feats = torch.randn(len(coords), 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    x = [torch.from_numpy(coords).float(), feats, None, 2]
+    res = []
+    real = scn_SCN.fuses_residual
+    for fused in (True, False):
+        scn_SCN.fuses_residual = real if fused else (lambda a, b: False)
+        try:
+            net = _small_unet()
+            out = net(x)
+            out.square().mean().backward()
+            res.append((out.detach().clone(), [p.grad.detach().clone() for p in net.parameters()]))
+        finally:
+            scn_SCN.fuses_residual = real
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
