@@ -105,7 +105,11 @@ int scn_bf16_plan(int c_in, int c_out, int precision);
  * CUDA/Convolution.cpp:104-210; kernels CUDA/Convolution.cu:447-534,695-753,1059-1152) ----------
  * out[N,Cout] = sum_k in[nbr_k(o)] * W[k];  *macs = sum_k n_k*Cin*Cout (the reference's return value) */
 int scn_subm_fwd(scn_meta *m, const int64_t spatial_size[3], const float *in, const float *weight, const float *bias,
-                 const float *residual, float *out, int c_in, int c_out, int precision, void *stream, double *macs);
+                 const float *residual, double *stats, float *out, int c_in, int c_out, int precision, void *stream,
+                 double *macs);
+/* stats (extension, may be NULL): [2][Cout] fp64, receives the column sums and sums of squares of the result
+ * (accumulated in the kernel epilogue) for the BatchNorm that consumes it: pass it to scn_bn_fwd as stats_in and that
+ * call skips its reduction pass.  Same availability as residual. */
 /* residual (extension, may be NULL): [N,Cout] fp32 added to the result in the kernel epilogue -- the shortcut of a
  * residual block (networkArchitectures.py:225-240) without a separate add pass.  Only the tensor-core kernels take it:
  * scn_fuses_residual(c_in, c_out, precision) says whether this layer shape does. */
@@ -136,7 +140,10 @@ int scn_deconv_bwd(scn_meta *m, const int64_t in_size[3], const int64_t out_size
  * y = leaky(gamma*(x-mean)*invstd + beta); leakiness 0 = ReLU, 1 = identity.  gamma/beta may be NULL. */
 /* out_bf16: optional second output, the bf16 copy of `out` ([n_rows, channels], channels % 4 == 0) for the SCN_BF16
  * convolution that consumes it (see scn_bf16_operand); NULL = none */
-int scn_bn_fwd(const float *in, float *out, void *out_bf16, float *save_mean, float *save_invstd, float *running_mean,
+/* stats_in: optional [2][channels] fp64 column sums / sums of squares of `in` made by the kernel that produced it
+ * (scn_subm_fwd's stats); used in training mode instead of a reduction pass over `in`; NULL = compute here */
+int scn_bn_fwd(const float *in, float *out, void *out_bf16, const double *stats_in, float *save_mean, float *save_invstd,
+               float *running_mean,
                float *running_var, const float *gamma, const float *beta, int64_t n_rows, int channels, float eps,
                float momentum, int train, float leakiness, void *stream);
 /* d_out is NOT modified (the reference masks it in place, BatchNormalization.cu:151-153; no caller observes it).

@@ -35,14 +35,14 @@ PROTOTYPES = {
     "scn_subm_neighbour_table": (C.c_int, [_vp, _i64p, _vp]),
     "scn_strided_rulebook": (C.c_int, [_vp, _i64p, _i64p, _vp, _i64p]),
     "scn_strided_table": (C.c_int, [_vp, _i64p, _vp, _vp]),
-    "scn_subm_fwd": (C.c_int, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
+    "scn_subm_fwd": (C.c_int, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
     "scn_fuses_residual": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "scn_subm_bwd": (C.c_int, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "scn_conv_fwd": (C.c_int, [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
     "scn_conv_bwd": (C.c_int, [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "scn_deconv_fwd": (C.c_int, [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
     "scn_deconv_bwd": (C.c_int, [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
-    "scn_bn_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, _vp]),
+    "scn_bn_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, _vp]),
     "scn_bf16_operand": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "scn_bf16_plan": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "scn_bn_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, _vp]),

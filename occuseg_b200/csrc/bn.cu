@@ -255,7 +255,8 @@ static int stream_grid(long long work_items, int block) {
   return (int)(g < 1 ? 1 : g);
 }
 
-void bn_fwd(const float *in, float *out, uint16_t *out_bf16, float *save_mean, float *save_invstd, float *running_mean,
+void bn_fwd(const float *in, float *out, uint16_t *out_bf16, const double *stats_in, float *save_mean, float *save_invstd,
+            float *running_mean,
             float *running_var, const float *gamma, const float *beta, long long n, int C, float eps, float momentum,
             bool train, float leakiness, cudaStream_t s) {
   SCN_CHECK(C > 0 && C <= 4096, "BatchNorm: channel count out of range");
@@ -263,7 +264,10 @@ void bn_fwd(const float *in, float *out, uint16_t *out_bf16, float *save_mean, f
   bool v4 = (C % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
   DevBuf<double> acc;
   acc.alloc(2 * (size_t)C, s);
-  if (train) {
+  const double *acc_use = acc.p;
+  if (train && stats_in) {
+    acc_use = stats_in;          // column sums already accumulated by the kernel that produced `in`
+  } else if (train) {
     SCN_CHECK(n > 1, "BatchNorm (train): needs at least two active rows");
     SCN_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * 2 * C, s));
     const bool r4 = v4 && C / 4 <= RED_THREADS;
@@ -273,7 +277,7 @@ void bn_fwd(const float *in, float *out, uint16_t *out_bf16, float *save_mean, f
     else k_bn_reduce<1, 0><<<rc.grid, rc.threads, rc.smem, s>>>(in, nullptr, nullptr, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
     SCN_LAUNCH_CHECK();
   }
-  k_bn_finalize_fwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, eps, momentum, train, save_mean, save_invstd,
+  k_bn_finalize_fwd<<<(C + 127) / 128, 128, 0, s>>>(acc_use, n, C, eps, momentum, train, save_mean, save_invstd,
                                                     running_mean, running_var);
   SCN_LAUNCH_CHECK();
   size_t smem = sizeof(float) * 2 * C;

@@ -409,7 +409,8 @@ int scn_strided_table(scn_meta *h, const int64_t fine[3], int32_t *parent, uint8
 
 // ---- submanifold ------------------------------------------------------------------------------------
 int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const float *weight, const float *bias,
-                 const float *residual, float *out, int c_in, int c_out, int precision, void *stream, double *macs) {
+                 const float *residual, double *stats, float *out, int c_in, int c_out, int precision, void *stream,
+                 double *macs) {
   SCN_TRY
   cudaStream_t s = (cudaStream_t)stream;
   check_channels(c_in, c_out);
@@ -419,11 +420,12 @@ int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   a.in = in; a.bias = bias; a.out = out;
   a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_in; a.c_out = c_out; a.n_rules = L->n_rules; a.in_rows = L->n;
   a.residual = residual;
-  if (residual) {
+  a.stats = stats;
+  if (residual || stats) {
     ConvArgs probe = a;
     probe.bf16 = bf16_conv_shape(c_in, c_out, precision);
     SCN_CHECK(precision != SCN_FP32 && conv_tma_supported(probe) && (uintptr_t)residual % 16 == 0,
-              "SubmanifoldConvolution: a fused residual needs the tensor-core path (see scn_fuses_residual)");
+              "SubmanifoldConvolution: fused residual / statistics need the tensor-core path (see scn_fuses_residual)");
   }
   run_conv(a, weight, true, precision, s, take_bf16_hint(&h->m, in, (long long)L->n * c_in, s));
   if (macs) *macs = (double)L->n_rules * c_in * c_out;   // flops += nRules*ip*op, CPU/Convolution.cpp:134
@@ -556,12 +558,13 @@ int scn_bf16_plan(int c_in, int c_out, int precision) {
   return (bf16_conv_shape(c_in, c_out, precision) ? 1 : 0) | (bf16_wgrad_shape(c_in, c_out, precision) ? 2 : 0);
 }
 
-int scn_bn_fwd(const float *in, float *out, void *out_bf16, float *save_mean, float *save_invstd, float *running_mean,
-               float *running_var, const float *gamma, const float *beta, int64_t n, int C, float eps, float momentum,
-               int train, float leakiness, void *stream) {
+int scn_bn_fwd(const float *in, float *out, void *out_bf16, const double *stats_in, float *save_mean, float *save_invstd,
+               float *running_mean, float *running_var, const float *gamma, const float *beta, int64_t n, int C, float eps,
+               float momentum, int train, float leakiness, void *stream) {
   SCN_TRY
-  ProfScope ps(PK_BN, (out_bf16 ? 3.5 : 3.0) * 4.0 * (double)n * C, 0.0, (cudaStream_t)stream);
-  bn_fwd(in, out, (uint16_t *)out_bf16, save_mean, save_invstd, running_mean, running_var, gamma, beta, n, C, eps, momentum, train != 0,
+  ProfScope ps(PK_BN, ((out_bf16 ? 3.5 : 3.0) - (stats_in && train ? 1.0 : 0.0)) * 4.0 * (double)n * C, 0.0,
+               (cudaStream_t)stream);
+  bn_fwd(in, out, (uint16_t *)out_bf16, stats_in, save_mean, save_invstd, running_mean, running_var, gamma, beta, n, C, eps, momentum, train != 0,
          leakiness, (cudaStream_t)stream);
   SCN_CATCH
 }

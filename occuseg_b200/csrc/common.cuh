@@ -161,6 +161,7 @@ struct ConvArgs {
   bool bf16 = false;               // tensor-core kernel: `in` and `weight_nk` are bf16 ([rows][c] uint16), fp32 accumulate and output
   const float *bias = nullptr;     // GATHER only
   const float *residual = nullptr; // tensor-core kernel only: [n_rows, c_out] fp32 added to the result
+  double *stats = nullptr;         // tensor-core kernel only: [2][c_out] column sums / sums of squares of the result
   float *out = nullptr;
   const int *tbl = nullptr;
   int tbl_stride = 0;
@@ -219,7 +220,7 @@ void wgrad_tma(const WgradArgs &a, cudaStream_t s);
 void bias_grad(const float *d_out, float *d_bias, long long n_rows, int C, cudaStream_t s);
 
 // bn.cu
-void bn_fwd(const float *in, float *out, uint16_t *out_bf16, float *save_mean, float *save_invstd, float *running_mean,
+void bn_fwd(const float *in, float *out, uint16_t *out_bf16, const double *stats_in, float *save_mean, float *save_invstd, float *running_mean,
             float *running_var, const float *gamma, const float *beta, long long n, int C, float eps, float momentum,
             bool train, float leakiness, cudaStream_t s);
 void bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,

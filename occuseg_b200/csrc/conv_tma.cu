@@ -261,6 +261,7 @@ constexpr int MAX_MT = 2;
 struct ConvParams {
   const float *bias;
   const float *residual;       // optional [n_rows, c_out] fp32 added to the result (residual shortcut fused into the epilogue)
+  double *stats;               // optional [2][c_out]: column sums and sums of squares of the result (for the BatchNorm that follows)
   float *out;
   const int *tbl;
   int tbl_stride, n_rows, V, c_in, c_out, mirror;
@@ -538,6 +539,9 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
       const int buf = gi & 1;
       mbar_wait_warp(accf_bar + 8 * buf, (uint32_t)(gi >> 1) & 1u, lane);
       tc_fence_after();
+      float st_sum[8], st_sq[8];           // this lane's column (c0 + lane) of every 32-column chunk, summed over the group's rows
+#pragma unroll
+      for (int i = 0; i < 8; ++i) st_sum[i] = st_sq[i] = 0.f;
       for (int m = 0; m < p.MT; ++m) {
         int r = (tg * p.MT + m) * TM + quarter * 32 + lane;
         bool live = r < p.n_rows;
@@ -546,6 +550,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
           live = r >= 0 && r < p.out_limit;
         }
         float *orow = p.out + (long long)r * p.c_out + n0;
+#pragma unroll 1
         for (int c0 = 0; c0 < p.TN; c0 += 32) {
           float v[32];
           tmem_ld32(tq + buf * acc_cols + m * p.TN + c0, v);
@@ -564,9 +569,40 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
                 o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
               }
               *reinterpret_cast<float4 *>(orow + c0 + q) = o;
+              v[q] = o.x; v[q + 1] = o.y; v[q + 2] = o.z; v[q + 3] = o.w;
             }
           }
+          if (p.stats) {
+            // column sums over the warp's 32 rows: transpose-reduce, 31 shuffles per quantity; lane j ends up with column j
+            float w[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              v[i] = live ? v[i] : 0.f;
+              w[i] = v[i] * v[i];
+            }
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) {
+              const bool up = (lane & sft) != 0;
+#pragma unroll
+              for (int i = 0; i < sft; ++i) {
+                const float keep_v = up ? v[i + sft] : v[i], send_v = up ? v[i] : v[i + sft];
+                const float keep_w = up ? w[i + sft] : w[i], send_w = up ? w[i] : w[i + sft];
+                v[i] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, sft);
+                w[i] = keep_w + __shfl_xor_sync(0xffffffffu, send_w, sft);
+              }
+            }
+            st_sum[c0 >> 5] += v[0];
+            st_sq[c0 >> 5] += w[0];
+          }
         }
+      }
+      if (p.stats) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i * 32 < p.TN) {
+            atomicAdd(p.stats + n0 + i * 32 + lane, (double)st_sum[i]);
+            atomicAdd(p.stats + p.c_out + n0 + i * 32 + lane, (double)st_sq[i]);
+          }
       }
       for (int c = 0; c < acc_cols; c += 32) tmem_zero32(tq + buf * acc_cols + c);
       tmem_wait_st();
@@ -806,6 +842,8 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   p.out_rows = a.out_rows; p.item_off = a.item_off; p.rows_per_item = a.rows_per_item; p.n_taps = a.n_taps;
   p.out_limit = a.out_limit;
   p.residual = a.residual;
+  p.stats = a.stats;
+  if (a.stats) SCN_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(double) * 2 * (size_t)a.c_out, s));
   p.in = a.in; p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
   p.V = a.V; p.c_in = a.c_in; p.c_out = a.c_out; p.mirror = a.mirror ? 1 : 0;
   p.bf16 = a.bf16 ? 1 : 0;

@@ -52,6 +52,18 @@ def attach_bf16(t, copy):
     t._scn_bf16 = (t._version, t.data_ptr(), copy)
 
 
+def attach_stats(t, stats):
+    t._scn_stats = (t._version, t.data_ptr(), stats)
+
+
+def held_stats(t):
+    """The column statistics the producer of `t` attached, if `t` has not changed since."""
+    held = getattr(t, "_scn_stats", None)
+    if held is not None and held[0] == t._version and held[1] == t.data_ptr() and held[2].size(1) == t.size(1):
+        return held[2]
+    return None
+
+
 def bf16_operand(m, x, c_in, c_out):
     """Register the bf16 copy of `x` for the next convolution entry on handle m.  Returns the copy (kept by the
     caller for the backward pass) or None when this layer does not run on bf16 tiles."""
@@ -214,8 +226,9 @@ def _check_weight(weight, v):
 
 
 def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_features, output_features, weight, bias,
-                                        dilated_rate=1, residual=None):
-    """residual (extension): [N, nOut] tensor added to the result inside the kernel (see fuses_residual)."""
+                                        dilated_rate=1, residual=None, stats=None):
+    """residual (extension): [N, nOut] tensor added to the result inside the kernel (see fuses_residual).
+    stats (extension): float64 [2, nOut] tensor that receives the column sums / sums of squares of the result."""
     if int(dilated_rate) != 1 or any(int(f) != 3 for f in filter_size.tolist()):
         raise NotImplementedError("SubmanifoldConvolution: only 3x3x3, dilation 1 is on this path")
     x, w, b = _cuda_f32(input_features, "input"), _check_weight(weight, 27), _opt(bias)
@@ -230,8 +243,8 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
             raise ValueError(f"SubmanifoldConvolution: input is {tuple(x.shape)}, scale has {n} rows, nIn={w.size(1)}")
         output_features.resize_(n, w.size(2))
         _lib.check(_lib.lib().scn_subm_fwd(m._handle(), _lib.size3(spatial_size), _ptr(x), _ptr(w), _ptr(b),
-                                           _ptr(residual), _ptr(output_features), w.size(1), w.size(2), _precision,
-                                           _stream(), C.byref(macs)))
+                                           _ptr(residual), _ptr(stats), _ptr(output_features), w.size(1), w.size(2),
+                                           _precision, _stream(), C.byref(macs)))
     return macs.value
 
 
@@ -305,15 +318,18 @@ def Deconvolution_backward(in_size, out_size, filter_size, filter_stride, m, inp
 
 # ---- batch norm (sparseconvnet.h:21-33) ------------------------------------------------------------------
 def BatchNormalization_updateOutput(input_features, output_features, saveMean, saveInvStd, runningMean, runningVar,
-                                    weight, bias, eps, momentum, train, leakiness, output_bf16=None):
+                                    weight, bias, eps, momentum, train, leakiness, output_bf16=None, stats=None):
     """output_bf16 (extension): an EMPTY bfloat16 tensor that receives the bf16 copy of the output for the
-    tensor-core convolution that follows (see attach_bf16 / bf16_operand)."""
+    tensor-core convolution that follows (see attach_bf16 / bf16_operand).
+    stats (extension): float64 [2, C] column sums / sums of squares of the input, made by the convolution that
+    produced it (attach_stats); the training-mode reduction pass is skipped."""
     x = _cuda_f32(input_features, "input")
     with torch.cuda.device(x.device):
         output_features.resize_(x.size(0), x.size(1))
         if output_bf16 is not None:
             output_bf16.resize_(x.size(0), x.size(1))
-        _lib.check(_lib.lib().scn_bn_fwd(_ptr(x), _ptr(output_features), _ptr(output_bf16), _ptr(saveMean), _ptr(saveInvStd),
+        _lib.check(_lib.lib().scn_bn_fwd(_ptr(x), _ptr(output_features), _ptr(output_bf16), _ptr(stats), _ptr(saveMean),
+                                         _ptr(saveInvStd),
                                          _ptr(runningMean), _ptr(runningVar), _ptr(_opt(weight)), _ptr(_opt(bias)),
                                          x.size(0), x.size(1), float(eps), float(momentum), int(bool(train)),
                                          float(leakiness), _stream()))

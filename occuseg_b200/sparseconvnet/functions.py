@@ -22,18 +22,22 @@ def _count(macs, out):
 
 class SubmanifoldConvolutionFunction(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, metadata, spatial_size, dimension, filter_size, dilated_rate=1, residual=None):
-        """residual (extension): added to the result in the kernel epilogue; its gradient is grad_out itself."""
+    def forward(ctx, x, weight, bias, metadata, spatial_size, dimension, filter_size, dilated_rate=1, residual=None,
+                want_stats=False):
+        """Returns (out, stats).  residual (extension): added to the result in the kernel epilogue; its gradient is
+        grad_out itself.  stats: float64 [2, nOut] column sums / sums of squares of out when want_stats, else empty."""
         ctx.scn_meta, ctx.dilated_rate = metadata, dilated_rate
         ctx.save_for_backward(x, spatial_size, weight, bias, filter_size)
         out = x.new_empty(0)
+        stats = torch.empty((2, weight.size(2)) if want_stats else 0, dtype=torch.float64, device=x.device)
         ctx.x16 = SCN.bf16_operand(metadata, x, weight.size(1), weight.size(2))
         _count(SCN.SubmanifoldConvolution_updateOutput(spatial_size, filter_size, metadata, x, out, weight, bias,
-                                                       dilated_rate, residual), out)
-        return out
+                                                       dilated_rate, residual, stats if want_stats else None), out)
+        ctx.mark_non_differentiable(stats)
+        return out, stats
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_out, _grad_stats=None):
         x, spatial_size, weight, bias, filter_size = ctx.saved_tensors
         gw, gb = torch.zeros_like(weight), torch.zeros_like(bias)
         # the layer behind the InputLayer has no use for d_input (point features are data): skip that product
@@ -42,7 +46,8 @@ class SubmanifoldConvolutionFunction(Function):
         SCN.SubmanifoldConvolution_backward(spatial_size, filter_size, ctx.scn_meta, x, gx, grad_out.contiguous(),
                                             weight, gw, gb, ctx.dilated_rate)
         del ctx.scn_meta, ctx.x16
-        return gx, gw, optionalTensorReturn(gb), None, None, None, None, None, (grad_out if ctx.needs_input_grad[8] else None)
+        return (gx, gw, optionalTensorReturn(gb), None, None, None, None, None,
+                (grad_out if ctx.needs_input_grad[8] else None), None)
 
 
 class _StridedFunction(Function):
@@ -106,7 +111,8 @@ class BatchNormalizationFunction(Function):
         out16 = torch.empty(0, dtype=torch.bfloat16, device=x.device)
         SCN.BatchNormalization_updateOutput(x, out, save_mean, save_invstd, running_mean, running_var, weight, bias,
                                             eps, momentum, train, leakiness,
-                                            out16 if SCN.wants_bf16(n_planes) and x.is_cuda else None)
+                                            out16 if SCN.wants_bf16(n_planes) and x.is_cuda else None,
+                                            SCN.held_stats(x) if train else None)
         # the backward pass recomputes the activation mask from x, so `out` is not kept alive for it
         ctx.save_for_backward(x, weight, bias, running_mean, running_var, save_mean, save_invstd)
         ctx.mark_non_differentiable(out16)

@@ -167,9 +167,15 @@ class SubmanifoldConvolution(_ConvBase):
     def forward(self, input, residual=None):
         """residual (extension): features of the shortcut branch, added inside the kernel (SCN.fuses_residual)."""
         self._check(input)
-        feats = F.SubmanifoldConvolutionFunction.apply(input.features, self.weight, optionalTensor(self, "bias"),
-                                                       input.metadata, input.spatial_size, self.dimension,
-                                                       self.filter_size, self.dilated_rate, residual)
+        # training on the tensor-core path: the kernel epilogue also accumulates the column statistics of the result,
+        # which the BatchNorm that consumes it picks up instead of running its own reduction pass
+        want_stats = self.training and torch.is_grad_enabled() and input.features.is_cuda and \
+            SCN.fuses_residual(self.nIn, self.nOut)
+        feats, stats = F.SubmanifoldConvolutionFunction.apply(input.features, self.weight, optionalTensor(self, "bias"),
+                                                              input.metadata, input.spatial_size, self.dimension,
+                                                              self.filter_size, self.dilated_rate, residual, want_stats)
+        if stats.numel():
+            SCN.attach_stats(feats, stats)
         return _same(input, feats)
 
     def input_spatial_size(self, out_size):
