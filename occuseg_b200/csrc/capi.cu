@@ -8,6 +8,7 @@
 namespace scn {
 
 static thread_local std::string t_last_error;
+thread_local cudaStream_t t_last_stream = nullptr;
 void set_last_error(const std::string &s) { t_last_error = s; }
 std::atomic<long long> g_launches{0};
 
@@ -75,6 +76,7 @@ const char *prof_name(int kind) {
 }
 
 static Level *need_level(Meta *m, const int64_t size[3], const char *what) {
+  m->last_stream = t_last_stream;       // every entry that names a scale passes through here after note_stream()
   Level *L = find_level(m, size);
   if (!L) throw Error(std::string(what) + ": no such scale in this handle (size " + std::to_string(size[0]) + ")");
   return L;
@@ -286,6 +288,7 @@ scn_meta *scn_meta_create(int device) {
 void scn_meta_destroy(scn_meta *h) {
   if (!h) return;
   cudaSetDevice(h->m.device);
+  t_last_stream = h->m.last_stream;     // the handle's buffers are freed in stream order behind its last kernels
   delete h;
 }
 
@@ -318,30 +321,31 @@ int scn_input_layer_build(scn_meta *h, const int64_t size[3], const int64_t *coo
                           int batch, int mode, void *stream, int64_t *n_active) {
   SCN_TRY
   SCN_CHECK(h && coords && n_active, "null argument");
-  build_input_level(&h->m, size, coords, on_device != 0, P, batch, mode, (cudaStream_t)stream);
+  h->m.last_stream = note_stream(stream);
+  build_input_level(&h->m, size, coords, on_device != 0, P, batch, mode, note_stream(stream));
   *n_active = h->m.levels[0]->n;
-  prebuild_scales(&h->m, (cudaStream_t)stream);
+  prebuild_scales(&h->m, note_stream(stream));
   SCN_CATCH
 }
 
 int scn_input_layer_fwd(scn_meta *h, const float *feats, int C, float *out, void *stream) {
   SCN_TRY
-  input_layer_fwd(&h->m, feats, C, out, (cudaStream_t)stream);
+  input_layer_fwd(&h->m, feats, C, out, note_stream(stream));
   SCN_CATCH
 }
 int scn_input_layer_bwd(scn_meta *h, const float *d_out, int C, float *d_feats, void *stream) {
   SCN_TRY
-  input_layer_bwd(&h->m, d_out, C, d_feats, (cudaStream_t)stream);
+  input_layer_bwd(&h->m, d_out, C, d_feats, note_stream(stream));
   SCN_CATCH
 }
 int scn_output_layer_fwd(scn_meta *h, const float *in, int C, float *out, void *stream) {
   SCN_TRY
-  output_layer_fwd(&h->m, in, C, out, (cudaStream_t)stream);
+  output_layer_fwd(&h->m, in, C, out, note_stream(stream));
   SCN_CATCH
 }
 int scn_output_layer_bwd(scn_meta *h, const float *d_out, int C, float *d_in, void *stream) {
   SCN_TRY
-  output_layer_bwd(&h->m, d_out, C, d_in, (cudaStream_t)stream);
+  output_layer_bwd(&h->m, d_out, C, d_in, note_stream(stream));
   SCN_CATCH
 }
 int64_t scn_n_points(scn_meta *h) { return h ? h->m.n_points : -1; }
@@ -370,7 +374,7 @@ int scn_spatial_locations(scn_meta *h, const int64_t size[3], int64_t *out) {
 int scn_subm_rulebook(scn_meta *h, const int64_t size[3], void *stream, int64_t *n_rules) {
   SCN_TRY
   Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
-  ensure_neighbour_table(&h->m, L, (cudaStream_t)stream);
+  ensure_neighbour_table(&h->m, L, note_stream(stream));
   if (n_rules) *n_rules = L->n_rules;
   SCN_CATCH
 }
@@ -392,7 +396,7 @@ static void note_depth(Meta *m) {
 int scn_strided_rulebook(scn_meta *h, const int64_t fine[3], const int64_t coarse[3], void *stream, int64_t *n_coarse) {
   SCN_TRY
   Level *F = need_level(&h->m, fine, "Convolution");
-  Level *C = ensure_coarse_level(&h->m, F, coarse, (cudaStream_t)stream);
+  Level *C = ensure_coarse_level(&h->m, F, coarse, note_stream(stream));
   note_depth(&h->m);
   if (n_coarse) *n_coarse = C->n;
   SCN_CATCH
@@ -412,7 +416,7 @@ int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const floa
                  const float *residual, double *stats, float *out, int c_in, int c_out, int precision, void *stream,
                  double *macs) {
   SCN_TRY
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = note_stream(stream);
   check_channels(c_in, c_out);
   Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
   ensure_neighbour_table(&h->m, L, s);
@@ -435,7 +439,7 @@ int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const floa
 int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const float *d_out, const float *weight,
                  float *d_in, float *d_weight, float *d_bias, int c_in, int c_out, int precision, void *stream) {
   SCN_TRY
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = note_stream(stream);
   check_channels(c_in, c_out);
   Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
   ensure_neighbour_table(&h->m, L, s);
@@ -465,7 +469,7 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
 int scn_conv_fwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3], const float *in, const float *weight,
                  const float *bias, float *out, int c_in, int c_out, int precision, void *stream, double *macs) {
   SCN_TRY
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = note_stream(stream);
   check_channels(c_in, c_out);
   Level *F = need_level(&h->m, in_size, "Convolution");
   Level *C = ensure_coarse_level(&h->m, F, out_size, s);
@@ -483,7 +487,7 @@ int scn_conv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
                  const float *weight, float *d_in, float *d_weight, float *d_bias, int c_in, int c_out, int precision,
                  void *stream) {
   SCN_TRY
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = note_stream(stream);
   check_channels(c_in, c_out);
   Level *F = need_level(&h->m, in_size, "Convolution");
   Level *C = ensure_coarse_level(&h->m, F, out_size, s);
@@ -502,7 +506,7 @@ int scn_deconv_fwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
                    const float *weight, const float *bias, float *out, int c_in, int c_out, int precision, void *stream,
                    double *macs) {
   SCN_TRY
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = note_stream(stream);
   check_channels(c_in, c_out);
   Level *F = need_level(&h->m, out_size, "Deconvolution");
   SCN_CHECK(F->coarse && find_level(&h->m, in_size) == F->coarse,
@@ -519,7 +523,7 @@ int scn_deconv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
                    const float *d_out, const float *weight, float *d_in, float *d_weight, float *d_bias, int c_in,
                    int c_out, int precision, void *stream) {
   SCN_TRY
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t s = note_stream(stream);
   check_channels(c_in, c_out);
   Level *F = need_level(&h->m, out_size, "Deconvolution");
   SCN_CHECK(F->coarse && find_level(&h->m, in_size) == F->coarse,
@@ -563,9 +567,9 @@ int scn_bn_fwd(const float *in, float *out, void *out_bf16, const double *stats_
                float momentum, int train, float leakiness, void *stream) {
   SCN_TRY
   ProfScope ps(PK_BN, ((out_bf16 ? 3.5 : 3.0) - (stats_in && train ? 1.0 : 0.0)) * 4.0 * (double)n * C, 0.0,
-               (cudaStream_t)stream);
+               note_stream(stream));
   bn_fwd(in, out, (uint16_t *)out_bf16, stats_in, save_mean, save_invstd, running_mean, running_var, gamma, beta, n, C, eps, momentum, train != 0,
-         leakiness, (cudaStream_t)stream);
+         leakiness, note_stream(stream));
   SCN_CATCH
 }
 
@@ -573,9 +577,9 @@ int scn_bn_bwd(const float *in, const float *out, const float *d_out, const floa
                const float *gamma, const float *beta, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta,
                int64_t n, int C, float leakiness, void *stream) {
   SCN_TRY
-  ProfScope ps(PK_BN, (d_in_add ? 6.0 : 5.0) * 4.0 * (double)n * C, 0.0, (cudaStream_t)stream);
+  ProfScope ps(PK_BN, (d_in_add ? 6.0 : 5.0) * 4.0 * (double)n * C, 0.0, note_stream(stream));
   bn_bwd(in, out, d_out, save_mean, save_invstd, gamma, beta, d_in_add, d_in, d_gamma, d_beta, n, C, leakiness,
-         (cudaStream_t)stream);
+         note_stream(stream));
   SCN_CATCH
 }
 

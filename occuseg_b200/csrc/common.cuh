@@ -49,6 +49,12 @@ int prof_read(double *out, int max_kinds);   // out[kind*4 + {launches, ms, byte
 const char *prof_name(int kind);
 
 // ---- stream-ordered device buffers -------------------------------------------------------------------
+// Buffers that are not released explicitly (error paths, the members of a handle being destroyed) are freed on the
+// stream the library last worked on in this thread, so the free is ordered after the kernels that used them even
+// when the caller runs on a non-default stream.
+extern thread_local cudaStream_t t_last_stream;
+inline cudaStream_t note_stream(void *stream) { return t_last_stream = (cudaStream_t)stream; }
+
 template <typename T> struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
@@ -65,7 +71,7 @@ template <typename T> struct DevBuf {
     p = nullptr;
     n = 0;
   }
-  ~DevBuf() { if (p) cudaFreeAsync(p, 0); }
+  ~DevBuf() { if (p) cudaFreeAsync(p, t_last_stream); }
 };
 
 // ---- voxel key: 16 bits per field, (batch, z, y, x) most->least significant -------------------------
@@ -120,6 +126,7 @@ struct Level {
 
 struct Meta {
   int device = 0;
+  cudaStream_t last_stream = nullptr;   // stream of the most recent entry that used this handle (scn_meta_destroy frees on it)
   int batch = 0;
   int mode = 0;
   long long n_points = 0;

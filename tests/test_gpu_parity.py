@@ -442,3 +442,27 @@ def test_epilogue_statistics_and_residual_match_torch():
         s0, s1 = y1.double().sum(0), (y1.double() ** 2).sum(0)
         assert float((st[0] - s0).abs().max() / s0.abs().max()) < 1e-6
         assert float((st[1] - s1).abs().max() / s1.abs().max()) < 1e-6
+
+
+def test_runs_on_a_non_default_stream():
+    """All work is enqueued on the caller's stream and a handle's buffers are freed in that stream's order: the same
+    network on a side stream (handles created and destroyed there, no device-wide synchronisation in between) must
+    reproduce the default-stream result."""
+    coords, feats = scenes.make_batch("small", (0, 1))
+    x = [torch.from_numpy(coords).float(), torch.from_numpy(feats).cuda(), None, 2]
+    scn.set_precision("fp32")                       # deterministic forward: bit-exact comparison
+    try:
+        net = _small_unet()
+        with torch.no_grad():
+            ref = net(x).clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        outs = []
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(4):                      # handles of earlier iterations die while later ones are enqueued
+                outs.append(net(x))
+        side.synchronize()
+        for o in outs:
+            assert torch.equal(o, ref)
+    finally:
+        scn.set_precision("bf16")
