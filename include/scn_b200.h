@@ -114,6 +114,16 @@ int scn_subm_fwd(scn_meta *m, const int64_t spatial_size[3], const float *in, co
  * residual block (networkArchitectures.py:225-240) without a separate add pass.  Only the tensor-core kernels take it:
  * scn_fuses_residual(c_in, c_out, precision) says whether this layer shape does. */
 int scn_fuses_residual(int c_in, int c_out, int precision);
+/* Inference: SubmanifoldConvolution followed by BatchNormalization (running statistics) + (leaky) ReLU in ONE kernel --
+ * the fused BatchNorm+ReLU epilogue: out = leaky(bn_scale[c] * (conv + bias + residual) + bn_shift[c]); out_bf16 (may be
+ * NULL) also receives the bf16 copy of out for the next SCN_BF16 convolution.  bn_scale / bn_shift [Cout] come from
+ * scn_bn_eval_coeffs, which evaluates them exactly as scn_bn_fwd(train = 0) does, so the result is bit-identical to
+ * the two separate calls.  Tensor-core shapes only (scn_fuses_residual). */
+int scn_subm_fwd_bn(scn_meta *m, const int64_t spatial_size[3], const float *in, const float *weight, const float *bias,
+                    const float *residual, const float *bn_scale, const float *bn_shift, float leakiness, float *out,
+                    void *out_bf16, int c_in, int c_out, int precision, void *stream, double *macs);
+int scn_bn_eval_coeffs(const float *running_mean, const float *running_var, const float *gamma, const float *beta,
+                       int channels, float eps, float *scale, float *shift, void *stream);
 /* d_in[N,Cin] (NULL: the input gradient is not needed and is skipped), d_weight[27,Cin,Cout], d_bias[Cout] (NULL when no bias) */
 int scn_subm_bwd(scn_meta *m, const int64_t spatial_size[3], const float *in, const float *d_out, const float *weight,
                  float *d_in, float *d_weight, float *d_bias, int c_in, int c_out, int precision, void *stream);

@@ -37,6 +37,9 @@ PROTOTYPES = {
     "scn_strided_table": (C.c_int, [_vp, _i64p, _vp, _vp]),
     "scn_subm_fwd": (C.c_int, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
     "scn_fuses_residual": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "scn_subm_fwd_bn": (C.c_int, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp,
+                                  C.POINTER(C.c_double)]),
+    "scn_bn_eval_coeffs": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_float, _vp, _vp, _vp]),
     "scn_subm_bwd": (C.c_int, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "scn_conv_fwd": (C.c_int, [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
     "scn_conv_bwd": (C.c_int, [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),

@@ -248,6 +248,24 @@ __global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ 
   }
 }
 
+__global__ void k_bn_eval_coeffs(const float *__restrict__ running_mean, const float *__restrict__ running_var,
+                                 const float *__restrict__ gamma, const float *__restrict__ beta, int C, float eps,
+                                 float *__restrict__ scale, float *__restrict__ shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  // the same two roundings as k_bn_finalize_fwd (fp64 rsqrt -> float) and k_bn_apply_fwd's prologue
+  const float invstd = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
+  const float w = invstd * (gamma ? gamma[c] : 1.f);
+  scale[c] = w;
+  shift[c] = -running_mean[c] * w + (beta ? beta[c] : 0.f);
+}
+
+void bn_eval_coeffs(const float *running_mean, const float *running_var, const float *gamma, const float *beta, int C,
+                    float eps, float *scale, float *shift, cudaStream_t s) {
+  k_bn_eval_coeffs<<<(C + 127) / 128, 128, 0, s>>>(running_mean, running_var, gamma, beta, C, eps, scale, shift);
+  SCN_LAUNCH_CHECK();
+}
+
 static int stream_grid(long long work_items, int block) {
   long long g = (work_items + block - 1) / block;
   long long cap = (long long)sm_count() * 8;

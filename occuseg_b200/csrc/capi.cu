@@ -412,6 +412,34 @@ int scn_strided_table(scn_meta *h, const int64_t fine[3], int32_t *parent, uint8
 }
 
 // ---- submanifold ------------------------------------------------------------------------------------
+int scn_bn_eval_coeffs(const float *running_mean, const float *running_var, const float *gamma, const float *beta,
+                       int channels, float eps, float *scale, float *shift, void *stream) {
+  SCN_TRY
+  bn_eval_coeffs(running_mean, running_var, gamma, beta, channels, eps, scale, shift, note_stream(stream));
+  SCN_CATCH
+}
+
+int scn_subm_fwd_bn(scn_meta *h, const int64_t size[3], const float *in, const float *weight, const float *bias,
+                    const float *residual, const float *bn_scale, const float *bn_shift, float leakiness, float *out,
+                    void *out_bf16, int c_in, int c_out, int precision, void *stream, double *macs) {
+  SCN_TRY
+  cudaStream_t s = note_stream(stream);
+  check_channels(c_in, c_out);
+  SCN_CHECK(bn_scale && bn_shift, "scn_subm_fwd_bn: null coefficients");
+  Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
+  ensure_neighbour_table(&h->m, L, s);
+  ConvArgs a;
+  a.in = in; a.bias = bias; a.out = out;
+  a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_in; a.c_out = c_out; a.n_rules = L->n_rules; a.in_rows = L->n;
+  a.residual = residual; a.ep_scale = bn_scale; a.ep_shift = bn_shift; a.ep_leak = leakiness; a.out_bf16 = (uint16_t *)out_bf16;
+  ConvArgs probe = a;
+  probe.bf16 = bf16_conv_shape(c_in, c_out, precision);
+  SCN_CHECK(precision != SCN_FP32 && conv_tma_supported(probe), "scn_subm_fwd_bn needs the tensor-core path (see scn_fuses_residual)");
+  run_conv(a, weight, true, precision, s, take_bf16_hint(&h->m, in, (long long)L->n * c_in, s));
+  if (macs) *macs = (double)L->n_rules * c_in * c_out;
+  SCN_CATCH
+}
+
 int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const float *weight, const float *bias,
                  const float *residual, double *stats, float *out, int c_in, int c_out, int precision, void *stream,
                  double *macs) {

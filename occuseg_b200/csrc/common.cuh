@@ -169,6 +169,11 @@ struct ConvArgs {
   const float *bias = nullptr;     // GATHER only
   const float *residual = nullptr; // tensor-core kernel only: [n_rows, c_out] fp32 added to the result
   double *stats = nullptr;         // tensor-core kernel only: [2][c_out] column sums / sums of squares of the result
+  // tensor-core kernel only: inference BatchNorm + (leaky) ReLU of the following layer applied in the epilogue
+  // (out = leaky(scale * acc + shift)), optional bf16 copy of the result
+  const float *ep_scale = nullptr, *ep_shift = nullptr;
+  float ep_leak = 1.f;
+  uint16_t *out_bf16 = nullptr;
   float *out = nullptr;
   const int *tbl = nullptr;
   int tbl_stride = 0;
@@ -230,6 +235,9 @@ void bias_grad(const float *d_out, float *d_bias, long long n_rows, int C, cudaS
 void bn_fwd(const float *in, float *out, uint16_t *out_bf16, const double *stats_in, float *save_mean, float *save_invstd, float *running_mean,
             float *running_var, const float *gamma, const float *beta, long long n, int C, float eps, float momentum,
             bool train, float leakiness, cudaStream_t s);
+// inference coefficients exactly as bn_fwd(train = false) uses them: scale = invstd*gamma, shift = beta - mean*scale
+void bn_eval_coeffs(const float *running_mean, const float *running_var, const float *gamma, const float *beta, int C,
+                    float eps, float *scale, float *shift, cudaStream_t s);
 void bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
             const float *gamma, const float *beta, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta, long long n, int C, float leakiness,
             cudaStream_t s);

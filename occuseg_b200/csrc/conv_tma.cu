@@ -262,6 +262,11 @@ struct ConvParams {
   const float *bias;
   const float *residual;       // optional [n_rows, c_out] fp32 added to the result (residual shortcut fused into the epilogue)
   double *stats;               // optional [2][c_out]: column sums and sums of squares of the result (for the BatchNorm that follows)
+  // optional fused inference BatchNorm + (leaky) ReLU of the layer that follows: out = leaky(scale[c] * acc + shift[c]),
+  // plus an optional bf16 copy of that result for the next tensor-core convolution
+  const float *ep_scale, *ep_shift;
+  float ep_leak;
+  uint16_t *out_bf16;
   float *out;
   const int *tbl;
   int tbl_stride, n_rows, V, c_in, c_out, mirror;
@@ -568,7 +573,20 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
                 const float4 rv = __ldg(reinterpret_cast<const float4 *>(p.residual + (long long)r * p.c_out + n0 + c0 + q));
                 o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
               }
+              if (p.ep_scale) {
+                const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.ep_scale + n0 + c0 + q));
+                const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.ep_shift + n0 + c0 + q));
+                o.x = fmaf(sc.x, o.x, sh.x); o.y = fmaf(sc.y, o.y, sh.y); o.z = fmaf(sc.z, o.z, sh.z); o.w = fmaf(sc.w, o.w, sh.w);
+                o.x = o.x > 0.f ? o.x : o.x * p.ep_leak; o.y = o.y > 0.f ? o.y : o.y * p.ep_leak;
+                o.z = o.z > 0.f ? o.z : o.z * p.ep_leak; o.w = o.w > 0.f ? o.w : o.w * p.ep_leak;
+              }
               *reinterpret_cast<float4 *>(orow + c0 + q) = o;
+              if (p.out_bf16) {
+                uint2 h;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(o.y), "f"(o.x));
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(o.w), "f"(o.z));
+                *reinterpret_cast<uint2 *>(p.out_bf16 + (long long)r * p.c_out + n0 + c0 + q) = h;
+              }
               v[q] = o.x; v[q + 1] = o.y; v[q + 2] = o.z; v[q + 3] = o.w;
             }
           }
@@ -842,6 +860,7 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   p.out_rows = a.out_rows; p.item_off = a.item_off; p.rows_per_item = a.rows_per_item; p.n_taps = a.n_taps;
   p.out_limit = a.out_limit;
   p.residual = a.residual;
+  p.ep_scale = a.ep_scale; p.ep_shift = a.ep_shift; p.ep_leak = a.ep_leak; p.out_bf16 = a.out_bf16;
   p.stats = a.stats;
   if (a.stats) SCN_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(double) * 2 * (size_t)a.c_out, s));
   p.in = a.in; p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;

@@ -248,6 +248,39 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
     return macs.value
 
 
+def BatchNormalization_evalCoefficients(runningMean, runningVar, weight, bias, eps):
+    """(extension) scale, shift [C] of the inference BatchNorm y = scale*x + shift, evaluated exactly as
+    BatchNormalization_updateOutput(train=False) evaluates them."""
+    c = runningMean.numel()
+    scale, shift = torch.empty_like(runningMean), torch.empty_like(runningMean)
+    with torch.cuda.device(runningMean.device):
+        _lib.check(_lib.lib().scn_bn_eval_coeffs(_ptr(runningMean), _ptr(runningVar), _ptr(_opt(weight)), _ptr(_opt(bias)), c,
+                                                 float(eps), _ptr(scale), _ptr(shift), _stream()))
+    return scale, shift
+
+
+def SubmanifoldConvolutionBN_updateOutput(spatial_size, filter_size, m, input_features, output_features, weight, bias,
+                                          bn_scale, bn_shift, leakiness, residual=None, output_bf16=None):
+    """(extension, inference) SubmanifoldConvolution + BatchNorm(running statistics) + (leaky) ReLU in one kernel: the
+    BatchNorm+ReLU runs in the convolution epilogue.  Bit-identical to the two separate entries."""
+    if any(int(f) != 3 for f in filter_size.tolist()):
+        raise NotImplementedError("SubmanifoldConvolution: only 3x3x3 is on this path")
+    x, w, b = _cuda_f32(input_features, "input"), _check_weight(weight, 27), _opt(bias)
+    macs = C.c_double(0.0)
+    with torch.cuda.device(x.device):
+        n = m.getNActive(spatial_size)
+        if x.size(0) != n or x.size(1) != w.size(1):
+            raise ValueError(f"SubmanifoldConvolution: input is {tuple(x.shape)}, scale has {n} rows, nIn={w.size(1)}")
+        output_features.resize_(n, w.size(2))
+        if output_bf16 is not None:
+            output_bf16.resize_(n, w.size(2))
+        _lib.check(_lib.lib().scn_subm_fwd_bn(m._handle(), _lib.size3(spatial_size), _ptr(x), _ptr(w), _ptr(b), _ptr(residual),
+                                              _ptr(bn_scale), _ptr(bn_shift), float(leakiness), _ptr(output_features),
+                                              _ptr(output_bf16), w.size(1), w.size(2), _precision, _stream(),
+                                              C.byref(macs)))
+    return macs.value
+
+
 def SubmanifoldConvolution_backward(spatial_size, filter_size, m, input_features, d_input_features, d_output_features,
                                     weight, d_weight, d_bias, dilated_rate=1):
     x, g, w = _cuda_f32(input_features, "input"), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 27)

@@ -37,10 +37,55 @@ def _size_str(v):
 
 
 # ---- containers -------------------------------------------------------------------------------------------
+def _conv_bn_inference(conv, bn, input, residual=None):
+    """Inference only: SubmanifoldConvolution `conv` followed by BatchNormalization `bn` as ONE kernel (the BatchNorm +
+    ReLU runs in the convolution epilogue and, in bf16 mode, also leaves the bf16 copy for the next convolution)."""
+    conv._check(input)
+    x = input.features
+    # scale / shift depend only on the layer's parameters and running statistics: cached until one of them changes
+    tensors = [bn.running_mean, bn.running_var, optionalTensor(bn, "weight"), optionalTensor(bn, "bias")]
+    key = tuple((t.data_ptr(), t._version) for t in tensors)
+    held = getattr(bn, "_scn_eval_coeffs", None)
+    if held is None or held[0] != key:
+        held = (key,) + SCN.BatchNormalization_evalCoefficients(*tensors, bn.eps)
+        bn._scn_eval_coeffs = held
+    scale, shift = held[1], held[2]
+    out = x.new_empty(0)
+    out16 = torch.empty(0, dtype=torch.bfloat16, device=x.device) if SCN.wants_bf16(conv.nOut) else None
+    x16 = SCN.bf16_operand(input.metadata, x, conv.nIn, conv.nOut)
+    macs = SCN.SubmanifoldConvolutionBN_updateOutput(input.spatial_size, conv.filter_size, input.metadata, x, out, conv.weight,
+                                                     optionalTensor(conv, "bias"), scale, shift, bn.leakiness, residual, out16)
+    del x16
+    F._count(macs, out)
+    if out16 is not None:
+        SCN.attach_bf16(out, out16)
+    return _same(input, out)
+
+
+def _fusable_inference_pair(a, b, input):
+    return (isinstance(a, SubmanifoldConvolution) and isinstance(b, BatchNormalization) and not b.training
+            and not torch.is_grad_enabled() and input.features.is_cuda and a.nOut == b.nPlanes
+            and SCN.fuses_residual(a.nIn, a.nOut))
+
+
 class Sequential(torch.nn.Sequential):
     def add(self, module):
         self._modules[str(len(self._modules))] = module
         return self
+
+    def forward(self, input):
+        # same as torch.nn.Sequential, except that at inference a SubmanifoldConvolution directly followed by a
+        # BatchNorm(+ReLU) runs as one kernel (fused BatchNorm+ReLU epilogue)
+        mods = list(self._modules.values())
+        i = 0
+        while i < len(mods):
+            if i + 1 < len(mods) and isinstance(input, SparseConvNetTensor) and _fusable_inference_pair(mods[i], mods[i + 1], input):
+                input = _conv_bn_inference(mods[i], mods[i + 1], input)
+                i += 2
+            else:
+                input = mods[i](input)
+                i += 1
+        return input
 
     def input_spatial_size(self, out_size):
         for m in reversed(list(self._modules.values())):

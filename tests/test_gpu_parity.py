@@ -466,3 +466,32 @@ def test_runs_on_a_non_default_stream():
             assert torch.equal(o, ref)
     finally:
         scn.set_precision("bf16")
+
+
+def test_inference_bn_relu_epilogue_is_bit_identical():
+    """Inference: SubmanifoldConvolution followed by BatchNormReLU runs as one kernel (BatchNorm+ReLU in the convolution
+    epilogue, north_star item 3).  It evaluates the same fp32 expressions as the two separate kernels, so the whole
+    network output must be bit-identical to the unfused evaluation, in every tensor-core precision."""
+    from occuseg_b200.sparseconvnet import layers as L
+    coords, feats = scenes.make_batch("small", (0, 1))
+    x = [torch.from_numpy(coords).float(), torch.from_numpy(feats).cuda(), None, 2]
+    real = L._fusable_inference_pair
+    for precision in ("bf16", "tf32"):
+        scn.set_precision(precision)
+        try:
+            net = _small_unet()
+            with torch.no_grad():
+                net(x)                                   # one training-mode pass so the running statistics are not trivial
+            net.eval()
+            calls = []
+            L._fusable_inference_pair = lambda a, b, i: (calls.append(1) or True) if real(a, b, i) else False
+            with torch.no_grad():
+                fused = net(x).clone()
+            assert len(calls) >= 5                        # one conv+BN pair per residual block
+            L._fusable_inference_pair = lambda a, b, i: False
+            with torch.no_grad():
+                plain = net(x).clone()
+            assert torch.equal(fused, plain)
+        finally:
+            L._fusable_inference_pair = real
+            scn.set_precision("bf16")
