@@ -430,7 +430,7 @@ def test_epilogue_statistics_and_residual_match_torch():
     m, _ = build_meta(coords, 2)
     N = m.getNActive(lt(SIZE))
     gen = torch.Generator(device="cuda").manual_seed(7)
-    for C in (64, 192):
+    for C in (64, 192, 320):                    # 320: two column tiles of 160
         x = torch.randn(N, C, device="cuda", generator=gen)
         w = torch.randn(27, C, C, device="cuda", generator=gen) * 0.05
         r = torch.randn(N, C, device="cuda", generator=gen)
