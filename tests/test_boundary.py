@@ -115,3 +115,20 @@ def test_scene_generator_is_seeded_and_shaped():
     assert a.min() == 10 and fa.dtype == np.float32 and fa.shape == (len(a), 3)
     c, f = scenes.make_batch("tiny", (0, 1, 2))
     assert c.shape[1] == 4 and np.all(np.diff(c[:, 3]) >= 0) and c[:, 3].max() == 2
+
+
+def test_occuseg_model_heads_follow_the_reference_names():
+    """occuseg_b200.models mirrors examples/ScanNet/model.py:657-717: same attribute names and head shapes, so the
+    tensors of a reference checkpoint load by name (construction only: no CUDA needed)."""
+    from occuseg_b200 import models
+    cfg = models.default_config(m=32, levels=3, class_num=20)
+    net = models.LearningBWDenseUNet(cfg)
+    sd = net.state_dict()
+    for name, shape in {"backbone.linear.weight": (20, 32), "backbone.fc_regress.weight": (32, 32),
+                        "backbone.linear_regress.weight": (1, 32), "backbone.fc_embedding.weight": (32, 32),
+                        "backbone.linear_embedding.weight": (32, 32), "backbone.fc_displacement.weight": (32, 32),
+                        "backbone.linear_displacement.weight": (3, 32), "fc_bw.weight": (32, 32), "linear_bw.weight": (2, 32),
+                        "fc_occupancy.weight": (32, 32), "linear_occupancy.weight": (1, 32),
+                        "backbone.sub.weight": (27, 3, 32), "backbone.bn.running_mean": (32,)}.items():
+        assert tuple(sd[name].shape) == shape, name
+    assert any(k.startswith("backbone.unet.") for k in sd)

@@ -495,3 +495,15 @@ def test_inference_bn_relu_epilogue_is_bit_identical():
         finally:
             L._fusable_inference_pair = real
             scn.set_precision("bf16")
+
+
+def test_occuseg_networks_run_end_to_end():
+    """LearningBWDenseUNet (sparse backbone + the seven dense heads) forward and backward on the CUDA path."""
+    from occuseg_b200 import models
+    coords, feats = scenes.make_batch("small", (0, 1))
+    net = models.LearningBWDenseUNet(models.default_config(m=64, levels=3)).cuda()
+    outs = net([torch.from_numpy(coords).float(), torch.from_numpy(feats).cuda(), None, 2])
+    P = len(coords)
+    assert [tuple(o.shape) for o in outs] == [(P, 20), (P, 64), (P, 64), (P, 1), (P, 3), (P, 2), (P, 1)]
+    sum(o.square().mean() for o in outs).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
