@@ -5,10 +5,15 @@ bench.py's cpu_baseline / --impl reference legs do, and only as the checker.
 
 The reference builds its rulebooks with CUDA + the vendored cudpp cuckoo hash (GPU_GRID is
 hard-defined, Metadata/Metadata.h:42), which cannot be built or run here,
-and it ships no golden vectors for them.  PARITY FOR THE RULEBOOKS IS
-THEREFORE PINNED BY THIS RESTATEMENT ONLY ("parity unpinned" by any reference-side fixture);
-the floating-point arithmetic, by contrast, is pinned by the reference's own CPU code compiled
-unmodified (oracle/ref_shim.cpp).
+and it ships no golden vectors for them.  This restatement follows the GPU
+builders (row = sorted key rank, taps x-outermost) and is PINNED to reference-compiled code: the
+reference's CPU `SparseGrid` builders (IOLayersRules.h:19-130, SubmanifoldConvolutionRules.h:114-209,
+ConvolutionRules.h:95-119 -- the code the GPU builders are self-checked against,
+ConvolutionRules.h:786-815) are compiled from the reference tree into oracle/_ref/scn_rules_ref.so
+(oracle/build_rules_ref.py, oracle/rules_shim.cpp) and tests/test_oracle.py asserts that both produce
+the same rule relation {(tap, in xyz, out xyz)}, the same point->voxel grouping and the same coarse
+voxel sets on every golden fixture and on seeded scenes.  The floating-point arithmetic is pinned by
+the reference's own CPU code compiled unmodified (oracle/ref_shim.cpp).
 
 Each function cites the reference lines it restates.  All paths relative to
 /root/reference/sparseconvnet/SCN/ unless noted.

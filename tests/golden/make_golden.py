@@ -3,8 +3,11 @@ oracle/_ref):   python tests/golden/make_golden.py
 
 Every floating-point array in the fixture is an OUTPUT OF THE REFERENCE'S OWN CPU CODE
 (sparseconvnet/SCN/CPU/*.cpp compiled unmodified, oracle/ref_shim.cpp) on the seeded inputs stored
-beside it.  The integer rulebooks come from oracle/rulebook.py (the reference's GPU builders cannot
-run here) -- they are what the reference arithmetic above consumed.
+beside it.  The integer rulebooks are in the GPU builders' convention (row = sorted key rank, taps
+x-outermost; oracle/rulebook.py) and are checked here, before they are written, against the reference's own
+CPU rule builders compiled from the reference tree (oracle/_ref/scn_rules_ref.so, oracle/rules_ref.py):
+same relation {(tap, in xyz, out xyz)}, same point->voxel grouping, same coarse voxel set.  They are what the
+reference arithmetic above consumed.
 """
 import os
 import sys
@@ -14,7 +17,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from occuseg_b200 import scenes  # noqa: E402
-from oracle import reference, rulebook as rb  # noqa: E402
+from oracle import reference, rulebook as rb, rules_ref as rr  # noqa: E402
 
 
 def pack(lists):
@@ -36,6 +39,15 @@ def make(name, preset, seeds, cin, cout, seed):
     clocs, strided = rb.strided_rules(locs, B)
     Nc = len(clocs)
     subm_c = rb.submanifold_rules(clocs, B)
+    # pin: the reference's compiled CPU builders give the same relation through coordinates
+    assert rr.available(), "oracle/_ref/scn_rules_ref.so not built"
+    sc = rr.Scene(coords, B, 4)
+    assert sc.n == N and np.array_equal(sc.locs[sc.row_of_point], locs[vox["row_of_point"]])
+    assert np.array_equal(sc.submanifold(0), rr.relation_of_lists(subm, locs))
+    rel, cl, _ = sc.strided()
+    assert np.array_equal(rel, rr.relation_of_lists(strided, locs, clocs)) and len(cl) == Nc
+    sc_c = rr.Scene(clocs, B, 4)
+    assert np.array_equal(sc_c.submanifold(0), rr.relation_of_lists(subm_c, clocs))
     R = reference.Ref()
     R.load_submanifold(4096, subm, N)
     R.load_strided(4096, 2048, strided, N, Nc)
@@ -73,7 +85,7 @@ def make(name, preset, seeds, cin, cout, seed):
         out, coords=coords.astype(np.int32), feats=feats, batch=np.int64(B), locs=locs.astype(np.int32),
         row_of_point=vox["row_of_point"], coarse_locs=clocs.astype(np.int32),
         subm_flat=sf, subm_off=so, strided_flat=tf, strided_off=to, subm_coarse_flat=cf, subm_coarse_off=co,
-        input_mean=inp_mean,
+        input_mean=inp_mean, rules_pinned=np.int64(1),
         x=x, w=w, g=g, y=y, macs=np.float64(macs), dx=dx, dw=dw,
         w8=w8, gc=gc, yc=yc, dxc=dxc, dw8=dw8,
         xd=xd, wd=wd, gd=gd, yd=yd, dxd=dxd, dwd=dwd,

@@ -26,6 +26,56 @@ def test_rulebook_restatement_matches_golden(golden):
     assert _canon_equal(rb.submanifold_rules(clocs, B), unpack(g["subm_coarse_flat"], g["subm_coarse_off"]))
 
 
+def test_rulebook_pinned_to_reference_compiled_builders(golden):
+    """The pin: the reference's own CPU rule builders (Metadata/IOLayersRules.h:19-130,
+    SubmanifoldConvolutionRules.h:114-209, ConvolutionRules.h:95-119), compiled from the reference tree into
+    oracle/_ref/scn_rules_ref.so, produce exactly the relation {(tap, in xyz, out xyz)} and the point->voxel grouping
+    that the golden lists (= the numpy restatement of the GPU builders) hold.  Rows are compared through coordinates
+    because the CPU builders number rows in first-appearance order and the GPU ones by sorted key rank."""
+    from oracle import rules_ref as rr
+    if not rr.available():
+        pytest.skip("oracle/_ref/scn_rules_ref.so not available")
+    g = golden
+    B = int(g["batch"])
+    sc = rr.Scene(g["coords"].astype(np.int64), B, 4)
+    locs = g["locs"].astype(np.int64)
+    assert sc.n == len(locs) and set(map(tuple, sc.locs.tolist())) == set(map(tuple, locs.tolist()))
+    # InputLayer: same voxel for every point, same points (same order) for every voxel
+    assert np.array_equal(sc.locs[sc.row_of_point], locs[g["row_of_point"]])
+    vox = rb.voxelize(g["coords"].astype(np.int64), B)
+    pov = sc.points_of_voxels()
+    for r in range(len(locs)):
+        assert pov[tuple(locs[r].tolist())] == vox["rule_pts"][vox["rule_ptr"][r]:vox["rule_ptr"][r + 1]].tolist()
+    # submanifold 3x3x3: plain builder (tap order converted z-major -> x-major) and the normal-guided builder with
+    # the identity orientation (which enumerates x-major itself, RectangularRegions.h:77-92)
+    mine = rr.relation_of_lists(unpack(g["subm_flat"], g["subm_off"]), locs)
+    assert np.array_equal(sc.submanifold(0), mine)
+    ident = np.tile(np.array([[1, 0, 0]], np.float32), (sc.n, 1))
+    assert np.array_equal(sc.submanifold(1, normals=ident), mine)
+    # size-2 / stride-2 convolution: same (tap, fine, coarse) relation, same coarse voxel set
+    rel, cl, _ = sc.strided()
+    clocs = g["coarse_locs"].astype(np.int64)
+    assert np.array_equal(rel, rr.relation_of_lists(unpack(g["strided_flat"], g["strided_off"]), locs, clocs))
+    assert set(map(tuple, cl.tolist())) == set(map(tuple, clocs.tolist()))
+
+
+def test_restatement_pinned_on_a_scene_with_duplicates_and_empty_sample():
+    from oracle import rules_ref as rr
+    if not rr.available():
+        pytest.skip("oracle/_ref/scn_rules_ref.so not available")
+    from occuseg_b200 import scenes
+    c, _ = scenes.make_batch("tiny", (4, 5))
+    c[c[:, 3] == 1, 3] = 2                                   # sample 1 is empty
+    c = np.concatenate([c, c[:7]], 0)                        # exact duplicates, out of batch order -> re-sort
+    c = c[np.argsort(c[:, 3], kind="stable")]
+    v = rb.voxelize(c, 3)
+    sc = rr.Scene(c, 3, 4)
+    assert sc.n == len(v["locs"])
+    assert np.array_equal(sc.submanifold(0), rr.relation_of_lists(rb.submanifold_rules(v["locs"], 3), v["locs"]))
+    cl, lists = rb.strided_rules(v["locs"], 3)
+    assert np.array_equal(sc.strided()[0], rr.relation_of_lists(lists, v["locs"], cl))
+
+
 def test_arith_port_matches_reference_outputs(golden):
     """golden y/dx/dw... are outputs of sparseconvnet/SCN/CPU/*.cpp; tolerance 1e-5 (fp32, GEMM summation order)."""
     g = golden
