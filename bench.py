@@ -145,7 +145,7 @@ def run_ours(args):
     import occuseg_b200.sparseconvnet as scn
     from occuseg_b200 import _lib, scenes
     from occuseg_b200.backbone import SparseBackbone
-    from occuseg_b200.ddp import FlatGradAllReduce
+    from occuseg_b200.ddp import BucketedGradAllReduce
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -162,7 +162,7 @@ def run_ours(args):
     torch.manual_seed(1234)                       # identical initial weights on every rank
     net = SparseBackbone(m=args.m, levels=6).to(dev)
     opt = torch.optim.Adam(net.parameters(), lr=1e-3, fused=True)
-    reducer = FlatGradAllReduce(net.parameters(), world) if world > 1 else None
+    reducer = BucketedGradAllReduce(net.parameters(), world) if world > 1 else None
 
     # ---- synthetic batch: rank r gets seeds r*scenes .. r*scenes+scenes-1 (weak scaling)
     seeds = tuple(rank * args.scenes + i for i in range(args.scenes))
@@ -178,7 +178,7 @@ def run_ours(args):
         loss = out.square().mean()
         loss.backward()
         if reducer is not None:
-            reducer.all_reduce()
+            reducer.finish()
         opt.step()
         opt.zero_grad(set_to_none=False)
         return loss

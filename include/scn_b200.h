@@ -54,6 +54,10 @@ const char *scn_profile_kind_name(int kind);
 /* ---- handle: replaces py `Metadata_3()` / ~Metadata (pybind.cpp:11-13) ------------------------ */
 scn_meta *scn_meta_create(int device);
 void scn_meta_destroy(scn_meta *m);
+/* The library's scratch (rulebooks, operand copies) lives in the device's default stream-ordered memory pool, of which it
+ * keeps at most SCN_POOL_KEEP_MB (default 4096) cached across synchronisations.  scn_pool_trim releases the free part of
+ * that cache down to keep_bytes right now (e.g. before another allocator needs the memory). */
+int scn_pool_trim(int device, int64_t keep_bytes);
 
 /* ---- InputLayer: replaces InputLayer_updateOutput's Metadata::inputLayer -> inputLayerRulesSimple
  * (CUDA/IOLayers.cpp:17-80, Metadata/Metadata.cpp:425-437, Metadata/IOLayersRules.h:136-202).

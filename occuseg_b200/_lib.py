@@ -23,6 +23,7 @@ PROTOTYPES = {
     "scn_profile_kind_name": (C.c_char_p, [C.c_int]),
     "scn_meta_create": (_vp, [C.c_int]),
     "scn_meta_destroy": (None, [_vp]),
+    "scn_pool_trim": (C.c_int, [C.c_int, C.c_int64]),
     "scn_input_layer_build": (C.c_int, [_vp, _i64p, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _i64p]),
     "scn_input_layer_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "scn_input_layer_bwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
@@ -89,6 +90,14 @@ def size3(v):
     v = [int(x) for x in v]
     assert len(v) == 3, "only 3-D grids are on this path"
     return (C.c_int64 * 3)(*v)
+
+
+def trim_memory(device=None, keep_bytes=0):
+    """Return the free part of the library's cached scratch memory to the driver (see scn_pool_trim)."""
+    if device is None:
+        import torch
+        device = torch.cuda.current_device()
+    check(lib().scn_pool_trim(int(device), int(keep_bytes)))
 
 
 def launch_count():

@@ -283,10 +283,10 @@ void bn_fwd(const float *in, float *out, uint16_t *out_bf16, const double *stats
   DevBuf<double> acc;
   acc.alloc(2 * (size_t)C, s);
   const double *acc_use = acc.p;
+  if (train) SCN_CHECK(n > 1, "BatchNorm (train): needs at least two active rows");   // unbiased running variance divides by n-1
   if (train && stats_in) {
     acc_use = stats_in;          // column sums already accumulated by the kernel that produced `in`
   } else if (train) {
-    SCN_CHECK(n > 1, "BatchNorm (train): needs at least two active rows");
     SCN_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * 2 * C, s));
     const bool r4 = v4 && C / 4 <= RED_THREADS;
     SCN_CHECK(r4 || C <= RED_THREADS, "BatchNorm: more than 256 channels need 16-byte aligned rows");

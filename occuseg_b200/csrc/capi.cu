@@ -12,13 +12,20 @@ thread_local cudaStream_t t_last_stream = nullptr;
 void set_last_error(const std::string &s) { t_last_error = s; }
 std::atomic<long long> g_launches{0};
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  return dev;
+}
+
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[MAX_DEVICES];
+  const int dev = current_device();
+  int n = (dev >= 0 && dev < MAX_DEVICES) ? cache[dev].load(std::memory_order_relaxed) : 0;
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev < 0 ? 0 : dev);
     if (n <= 0) n = 148;
+    if (dev >= 0 && dev < MAX_DEVICES) cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -265,15 +272,21 @@ scn_meta *scn_meta_create(int device) {
   try {
     SCN_CUDA(cudaSetDevice(device));
     {
-      // keep freed blocks in the stream-ordered pool across synchronisation points; with the default
-      // threshold (0) every sync hands the memory back to the driver and the next batch pays for cudaMalloc
-      static bool pool_ready[64] = {};
-      if (device >= 0 && device < 64 && !pool_ready[device]) {
+      // keep freed blocks in the stream-ordered pool across synchronisation points; with the default threshold (0)
+      // every sync hands the memory back to the driver and the next batch pays for cudaMalloc.  The amount kept is
+      // BOUNDED (SCN_POOL_KEEP_MB, default 4096: a step of the 8 x 250k-voxel workload holds < 2 GB of rulebooks and
+      // operand copies) so the embedding process -- PyTorch's caching allocator cannot see this pool -- gets the rest
+      // back at the next synchronisation; scn_pool_trim() returns everything that is free right now.
+      static std::atomic<bool> pool_ready[MAX_DEVICES];
+      if (device >= 0 && device < MAX_DEVICES && !pool_ready[device].load()) {
         cudaMemPool_t pool;
         SCN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t keep = ~0ull;
-        SCN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        pool_ready[device] = true;
+        const char *e = getenv("SCN_POOL_KEEP_MB");
+        uint64_t keep = (uint64_t)(e ? atoll(e) : 4096) << 20;
+        uint64_t cur = 0;
+        SCN_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur));
+        if (cur < keep) SCN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));   // never lower someone else's setting
+        pool_ready[device].store(true);
       }
     }
     scn_meta *h = new scn_meta();
@@ -283,6 +296,14 @@ scn_meta *scn_meta_create(int device) {
     set_last_error(e.what());
     return nullptr;
   }
+}
+
+int scn_pool_trim(int device, int64_t keep_bytes) {
+  SCN_TRY
+  cudaMemPool_t pool;
+  SCN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  SCN_CUDA(cudaMemPoolTrimTo(pool, keep_bytes < 0 ? 0 : (size_t)keep_bytes));
+  SCN_CATCH
 }
 
 void scn_meta_destroy(scn_meta *h) {

@@ -34,7 +34,23 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     SCN_CUDA(cudaGetLastError());                                                                   \
   } while (0)
 
-int sm_count();
+int sm_count();                  // SM count of the CURRENT device (cached per device)
+int current_device();
+constexpr int MAX_DEVICES = 64;
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: call sites keep one of these per kernel
+struct SmemAttrCache {
+  std::atomic<size_t> configured[MAX_DEVICES];
+  SmemAttrCache() { for (auto &c : configured) c.store(0); }
+  template <typename K> void ensure(K kernel, size_t smem) {
+    const int dev = current_device();
+    if (dev >= 0 && dev < MAX_DEVICES && configured[dev].load(std::memory_order_acquire) >= smem) return;
+    SCN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < MAX_DEVICES) {
+      size_t cur = configured[dev].load();
+      while (cur < smem && !configured[dev].compare_exchange_weak(cur, smem)) {}
+    }
+  }
+};
 
 // ---- optional per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline) ----
 enum ProfKind { PK_RULEBOOK = 0, PK_CONV_TC, PK_CONV_FP32, PK_WGRAD_TC, PK_WGRAD_FP32, PK_BN, PK_IO, PK_CAST, PK_COUNT };

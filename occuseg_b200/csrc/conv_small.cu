@@ -77,11 +77,8 @@ void conv_small(const ConvArgs &a, cudaStream_t s) {
   const size_t smem = sizeof(float) * ((size_t)a.V * a.c_in * SC_TILE + 4 * 32 * (SC_TILE + 1));
 #define SCN_SMALL(CIN)                                                                                          \
   do {                                                                                                          \
-    static bool configured = false;                                                                             \
-    if (!configured) {                                                                                          \
-      SCN_CUDA(cudaFuncSetAttribute(k_conv_small_cin<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
-      configured = true;                                                                                        \
-    }                                                                                                           \
+    static SmemAttrCache smem_attr;                                                                             \
+    smem_attr.ensure(k_conv_small_cin<CIN>, 100 * 1024);                                                        \
     k_conv_small_cin<CIN><<<grid, SC_ROWS, smem, s>>>(a);                                                       \
   } while (0)
   switch (a.c_in) {

@@ -897,11 +897,8 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   CUtensorMap mx = make_map(a.in, a.bf16, (uint64_t)a.c_in, (uint64_t)a.in_rows, p.kelems, 1, CU_TENSOR_MAP_SWIZZLE_128B);
   CUtensorMap mw = make_map(a.weight_nk, a.bf16, (uint64_t)a.c_in, (uint64_t)(a.n_taps ? a.n_taps : a.V) * a.c_out, p.kelems, (uint32_t)p.TN,
                             CU_TENSOR_MAP_SWIZZLE_128B);
-  static size_t configured = 0;
-  if (smem > configured) {
-    SCN_CUDA(cudaFuncSetAttribute(k_conv_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemAttrCache smem_attr;       // per device: the attribute is device state
+  smem_attr.ensure(k_conv_tma, smem);
   const int n_tiles_n = a.c_out / p.TN;
   int gx = sm_count() / n_tiles_n;
   if (gx < 1) gx = 1;
@@ -995,11 +992,8 @@ void wgrad_tma(const WgradArgs &a, cudaStream_t s) {
   const CUtensorMapSwizzle sw = a.bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUtensorMap mg = make_map(G, a.bf16, (uint64_t)p.Cg, (uint64_t)a.g_rows, p.cpb, 1, sw);
   CUtensorMap ms = make_map(S, a.bf16, (uint64_t)p.Cs, (uint64_t)a.s_rows, p.cpb, 1, sw);
-  static size_t configured = 0;
-  if (smem > configured) {
-    SCN_CUDA(cudaFuncSetAttribute(k_wgrad_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemAttrCache smem_attr;
+  smem_attr.ensure(k_wgrad_tma, smem);
   dim3 grid(a.V, ranges, p.Cs / p.N);
   k_wgrad_tma<<<grid, WG_THREADS, smem, s>>>(mg, ms, p);
   SCN_LAUNCH_CHECK();

@@ -62,9 +62,17 @@ def _conv_bn_inference(conv, bn, input, residual=None):
     return _same(input, out)
 
 
+def _has_hooks(m):
+    return bool(m._forward_hooks or m._forward_pre_hooks or m._backward_hooks or m._backward_pre_hooks)
+
+
 def _fusable_inference_pair(a, b, input):
+    # the fused entry is the 3x3x3, dilation-1 kernel and bypasses the modules' __call__: anything else (dilated or
+    # other filter sizes, hooks registered on either module) takes the two separate layers
     return (isinstance(a, SubmanifoldConvolution) and isinstance(b, BatchNormalization) and not b.training
             and not torch.is_grad_enabled() and input.features.is_cuda and a.nOut == b.nPlanes
+            and getattr(a, "dilated_rate", 1) == 1 and a.filter_volume == 27
+            and not _has_hooks(a) and not _has_hooks(b)
             and SCN.fuses_residual(a.nIn, a.nOut))
 
 

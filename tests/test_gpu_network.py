@@ -1,0 +1,273 @@
+"""GPU parity tests (-m gpu) at NETWORK level and at full size, against the oracle -- not against the CUDA path itself:
+ * a residual UNet (NiN shortcuts, JoinTable, strided conv / deconv) replayed layer by layer through the reference's CPU
+   arithmetic (oracle/chain.py, validated against the reference's own Python package in tests/test_chain_oracle.py);
+ * every layer of that network in the tensor-core precisions, fed the ORACLE's input of that layer;
+ * NetworkInNetwork against cpu_NetworkInNetwork_* (CPU/NetworkInNetwork.cpp:7-60);
+ * rulebooks bit-exact at BASELINE.json's full sizes (8 x S250k, S1M) and convolutions on the S1M / m=32 shapes.
+Tolerances (conftest.rel_err, max-norm relative): fp32 path 1e-5 per layer and 1e-4 end to end; bf16 / tf32 tiles 2e-2."""
+import numpy as np
+import pytest
+
+from conftest import have_cuda, rel_err
+
+pytestmark = pytest.mark.gpu
+
+if have_cuda():
+    import torch
+    import occuseg_b200.sparseconvnet as scn
+    from occuseg_b200.sparseconvnet import SCN
+    from occuseg_b200 import scenes
+from oracle import arith, rulebook as rb
+
+SIZE = 4096
+FP32_TOL, TC_TOL = 1e-5, 2e-2
+
+
+@pytest.fixture(autouse=True)
+def _default_precision():
+    scn.set_precision("fp32")
+    yield
+    scn.set_precision("fp32")
+
+
+def lt(v):
+    return torch.LongTensor([v, v, v])
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def _net(planes, seed=11):
+    torch.manual_seed(seed)
+    return scn.Sequential().add(scn.InputLayer(3, SIZE, mode=4)).add(scn.SubmanifoldConvolution(3, 3, planes[0], 3, False)) \
+        .add(scn.UNet(3, 1, planes, True)).add(scn.BatchNormReLU(planes[0])).add(scn.OutputLayer(3))
+
+
+def _oracle_table(rules, n):
+    """reference rule lists -> output-stationary table [V][n] (input row or -1): equality of the tables is equality of
+    the canonically sorted lists, since an output row appears at most once per list"""
+    t = np.full((len(rules), n), -1, np.int32)
+    for k, r in enumerate(rules):
+        assert len(np.unique(r[:, 1])) == len(r)
+        t[k, r[:, 1]] = r[:, 0]
+    return t
+
+
+# ------------------------------------------------------------------------------------------- network vs chained oracle
+def test_unet_fp32_matches_the_chained_oracle():
+    """3-level residual UNet [32,64,96] (identity and NiN shortcuts, JoinTable, Convolution / Deconvolution 2/2, 17
+    BatchNorms) forward + backward on the CUDA fp32 path against the same network replayed through the reference's CPU
+    code with the same weights: output and EVERY parameter gradient within 1e-4 (max-norm relative)."""
+    from oracle import chain
+    coords, feats = scenes.make_batch("small", (0, 1))
+    x = [torch.from_numpy(coords).float(), torch.from_numpy(feats), None, 2]
+    net = _net([32, 64, 96])
+    rp, out0 = chain.replay(net, x)
+    out0.square().mean().backward()
+    net = net.cuda()
+    out = net([x[0], x[1].cuda(), None, 2])
+    out.square().mean().backward()
+    assert rel_err(out.detach().cpu().numpy(), out0.detach().numpy()) < 1e-4
+    worst = 0.0
+    for name, p in net.named_parameters():
+        e = rel_err(p.grad.cpu().numpy(), rp.named[name].grad.numpy())
+        worst = max(worst, e)
+        assert e < 1e-4, (name, e)
+    for name, b in net.named_buffers():                     # running statistics
+        assert rel_err(b.cpu().numpy(), rp.named[name].numpy()) < 1e-5, name
+    print(f"worst parameter-gradient error {worst:.2e}")
+
+
+def _gpu_meta(coords, batch, levels):
+    m = SCN.Metadata_3()
+    out = torch.empty(0, device="cuda")
+    SCN.InputLayer_updateOutput(m, lt(SIZE), torch.from_numpy(coords), torch.zeros(len(coords), 1, device="cuda"), out, batch, 4, None)
+    size = SIZE
+    for _ in range(levels - 1):
+        m.stridedTable(lt(size), lt(size // 2))
+        size //= 2
+    return m
+
+
+@pytest.mark.parametrize("precision", ["bf16", "tf32", "fp32"])
+def test_every_layer_matches_the_oracle_on_the_oracles_input(precision):
+    """The m=64 residual UNet [64,128,192] is replayed through the oracle once; then EVERY sparse layer of it
+    (SubmanifoldConvolution, Convolution, Deconvolution, NetworkInNetwork, BatchNormReLU) runs alone on the CUDA path in
+    `precision`, fed the oracle's input and upstream gradient of that layer, and its output, input gradient and weight
+    gradient are compared with the oracle's: 2e-2 for the tensor-core tiles, 1e-5 for fp32 (north_star budgets)."""
+    from oracle import chain
+    coords, feats = scenes.make_batch("small", (2, 3))
+    x = [torch.from_numpy(coords).float(), torch.from_numpy(feats), None, 2]
+    net = _net([64, 128, 192], seed=4)
+    rp, out0 = chain.replay(net, x)
+    out0.square().mean().backward()
+    m = _gpu_meta(coords, 2, 3)
+    tol = FP32_TOL if precision == "fp32" else TC_TOL
+    scn.set_precision(precision)
+    sizes = {}
+    # spatial size of every tape entry: recover from the row count
+    n_of = {SIZE >> l: m.getNActive(lt(SIZE >> l)) for l in range(3)}
+    size_of_n = {v: k for k, v in n_of.items()}
+    assert len(size_of_n) == 3
+    checked = {"subm": 0, "conv": 0, "deconv": 0, "nin": 0, "bn": 0}
+    e = lambda: torch.empty(0, device="cuda")  # noqa: E731
+    for rec in rp.tape:
+        kind, mod = rec["kind"], rec["module"]
+        if kind not in checked:
+            continue
+        xx, gy = cu(rec["x"].numpy()), cu(rec["gy"].numpy())
+        y, gx = e(), e()
+        if kind in ("subm", "conv", "deconv"):
+            w = cu(mod.weight.detach().numpy())
+            gw = torch.zeros_like(w)
+            if kind == "subm":
+                sz = size_of_n[xx.shape[0]]
+                SCN.SubmanifoldConvolution_updateOutput(lt(sz), lt(3), m, xx, y, w, torch.empty(0), 1)
+                SCN.SubmanifoldConvolution_backward(lt(sz), lt(3), m, xx, gx, gy, w, gw, torch.empty(0), 1)
+            elif kind == "conv":
+                sz = size_of_n[xx.shape[0]]
+                SCN.Convolution_updateOutput(lt(sz), lt(sz // 2), lt(2), lt(2), m, xx, y, w, torch.empty(0))
+                SCN.Convolution_backward(lt(sz), lt(sz // 2), lt(2), lt(2), m, xx, gx, gy, w, gw, torch.empty(0))
+            else:
+                sz = size_of_n[xx.shape[0]]
+                SCN.Deconvolution_updateOutput(lt(sz), lt(sz * 2), lt(2), lt(2), m, xx, y, w, torch.empty(0))
+                SCN.Deconvolution_backward(lt(sz), lt(sz * 2), lt(2), lt(2), m, xx, gx, gy, w, gw, torch.empty(0))
+            assert rel_err(gw.cpu().numpy(), rec["gw"].numpy()) < tol, (rec["name"], "gw")
+        elif kind == "nin":
+            w = cu(mod.weight.detach().numpy())
+            gw = torch.zeros_like(w)
+            SCN.NetworkInNetwork_updateOutput(xx, y, w, torch.empty(0))
+            SCN.NetworkInNetwork_updateGradInput(gx, gy, w)
+            SCN.NetworkInNetwork_accGradParameters(xx, gy, gw, None)
+            assert rel_err(gw.cpu().numpy(), rec["gw"].numpy()) < tol, (rec["name"], "gw")
+        else:   # bn: always fp32 arithmetic
+            C = xx.shape[1]
+            gamma, beta = cu(mod.weight.detach().numpy()), cu(mod.bias.detach().numpy())
+            rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+            sm, si = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+            SCN.BatchNormalization_updateOutput(xx, y, sm, si, rm, rv, gamma, beta, mod.eps, mod.momentum, True, mod.leakiness)
+            dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+            SCN.BatchNormalization_backward(xx, gx, y, gy, sm, si, rm, rv, gamma, beta, dg, db, mod.leakiness)
+            assert rel_err(dg.cpu().numpy(), rec["gw"].numpy()) < 1e-4, (rec["name"], "dgamma")
+            assert rel_err(db.cpu().numpy(), rec["gb"].numpy()) < 1e-4, (rec["name"], "dbeta")
+        t = 1e-4 if kind == "bn" else tol
+        assert rel_err(y.cpu().numpy(), rec["y"].numpy()) < t, (rec["name"], kind, "y")
+        if rec["gx"].numel():
+            assert rel_err(gx.cpu().numpy(), rec["gx"].numpy()) < t, (rec["name"], kind, "gx")
+        checked[kind] += 1
+    assert checked["subm"] >= 11 and checked["conv"] == 2 and checked["deconv"] == 2 and checked["nin"] == 2 and checked["bn"] >= 15, checked
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("bias", [False, True])
+def test_network_in_network_matches_reference(precision, bias):
+    """cpu_NetworkInNetwork_updateOutput / updateGradInput / accGradParameters (CPU/NetworkInNetwork.cpp:7-60) through
+    oracle/_ref against the CUDA entries; fp32 1e-5, tf32 2e-2."""
+    from oracle import reference
+    if not reference.available():
+        pytest.skip("oracle/_ref not available")
+    rng = np.random.default_rng(3)
+    n, a, b = 50_001, 128, 64
+    x = rng.standard_normal((n, a)).astype(np.float32)
+    w = (rng.standard_normal((a, b)) * (2.0 / a) ** 0.5).astype(np.float32)
+    bb = rng.standard_normal(b).astype(np.float32) if bias else np.zeros(0, np.float32)
+    g = rng.standard_normal((n, b)).astype(np.float32)
+    mod = reference.module()
+    T = lambda v: torch.from_numpy(v)  # noqa: E731
+    y0, gx0, gw0, gb0 = torch.empty(0), torch.empty(0), torch.zeros(a, b), torch.zeros(b if bias else 0)
+    mod.NetworkInNetwork_updateOutput(T(x), y0, T(w), T(bb))
+    mod.NetworkInNetwork_updateGradInput(gx0, T(g), T(w))
+    mod.NetworkInNetwork_accGradParameters(T(x), T(g), gw0, gb0)
+    scn.set_precision(precision)
+    tol = FP32_TOL if precision == "fp32" else TC_TOL
+    before = torch.backends.cuda.matmul.allow_tf32
+    y, gx, gw = torch.empty(0, device="cuda"), torch.empty(0, device="cuda"), torch.zeros(a, b, device="cuda")
+    gb = torch.zeros(b, device="cuda") if bias else None
+    SCN.NetworkInNetwork_updateOutput(cu(x), y, cu(w), cu(bb) if bias else torch.empty(0))
+    SCN.NetworkInNetwork_updateGradInput(gx, cu(g), cu(w))
+    SCN.NetworkInNetwork_accGradParameters(cu(x), cu(g), gw, gb)
+    assert torch.backends.cuda.matmul.allow_tf32 == before          # the caller's global setting is left alone
+    assert rel_err(y.cpu().numpy(), y0.numpy()) < tol
+    assert rel_err(gx.cpu().numpy(), gx0.numpy()) < tol
+    assert rel_err(gw.cpu().numpy(), gw0.numpy()) < tol
+    if bias:
+        assert rel_err(gb.cpu().numpy(), gb0.numpy()) < tol
+
+
+# ------------------------------------------------------------------------------------------- full-size rulebooks
+@pytest.mark.parametrize("preset,seeds", [("S250k", tuple(range(8))), ("S1M", (0,))])
+def test_rulebooks_bit_exact_at_full_size(preset, seeds):
+    """BASELINE.json configs 3 (8 x S250k, ~2 M voxels) and 5 (S1M): every scale's row order, 27-tap neighbour table,
+    stride-2 parents / offsets and InputLayer point->row map equal the oracle's, bit for bit."""
+    coords, _ = scenes.make_batch(preset, seeds)
+    B = len(seeds)
+    vox = rb.voxelize(coords, B)
+    m = SCN.Metadata_3()
+    out = torch.empty(0, device="cuda")
+    SCN.InputLayer_updateOutput(m, lt(SIZE), torch.from_numpy(coords), torch.zeros(len(coords), 1, device="cuda"), out, B, 4, None)
+    locs, size = vox["locs"], SIZE
+    assert len(locs) > (1_800_000 if preset == "S250k" else 900_000)
+    for level in range(6):
+        assert np.array_equal(m.getSpatialLocations(lt(size)).numpy(), locs), level
+        nbr, n_rules = m.submanifoldNeighbourTable(lt(size))
+        want = rb.submanifold_rules(locs, B)
+        assert n_rules == sum(len(r) for r in want)
+        assert np.array_equal(nbr.numpy(), _oracle_table(want, len(locs))), level
+        if level == 5:
+            break
+        parent, off, nc = m.stridedTable(lt(size), lt(size // 2))
+        clocs, want_s = rb.strided_rules(locs, B)
+        assert nc == len(clocs)
+        p0, o0 = np.full(len(locs), -1, np.int32), np.full(len(locs), 255, np.uint8)
+        for k, r in enumerate(want_s):
+            p0[r[:, 0]], o0[r[:, 0]] = r[:, 1], k
+        assert np.array_equal(parent.numpy(), p0) and np.array_equal(off.numpy(), o0), level
+        locs, size = clocs, size // 2
+
+
+@pytest.mark.parametrize("precision,c", [("fp32", 16), ("tf32", 32), ("bf16", 64), ("bf16", 128), ("bf16", 256)])
+def test_s1m_channel_sweep_vs_oracle(precision, c):
+    """BASELINE.json config 5: level-0 SubmanifoldConvolution c->c on the 1 M-voxel scene, forward + dgrad + wgrad against
+    the oracle arithmetic (numpy port of CPU/Convolution.cpp, itself pinned to oracle/_ref)."""
+    coords, _ = scenes.make_batch("S1M", (0,))
+    vox = rb.voxelize(coords, 1)
+    rules = rb.submanifold_rules(vox["locs"], 1)
+    N = len(vox["locs"])
+    rng = np.random.default_rng(c)
+    x = rng.standard_normal((N, c), dtype=np.float32)
+    w = (rng.standard_normal((27, c, c), dtype=np.float32) * (2.0 / c / 27) ** 0.5).astype(np.float32)
+    g = rng.standard_normal((N, c), dtype=np.float32)
+    m = _gpu_meta(coords, 1, 1)
+    scn.set_precision(precision)
+    y, gx, gw = torch.empty(0, device="cuda"), torch.empty(0, device="cuda"), torch.zeros(27, c, c, device="cuda")
+    macs = SCN.SubmanifoldConvolution_updateOutput(lt(SIZE), lt(3), m, cu(x), y, cu(w), torch.empty(0), 1)
+    SCN.SubmanifoldConvolution_backward(lt(SIZE), lt(3), m, cu(x), gx, cu(g), cu(w), gw, torch.empty(0), 1)
+    y0, macs0 = arith.rule_conv_forward(x, w, rules, N)
+    gx0, gw0 = arith.rule_conv_backward(x, g, w, rules)
+    tol = FP32_TOL if precision == "fp32" else TC_TOL
+    assert macs == macs0
+    assert rel_err(y.cpu().numpy(), y0) < tol and rel_err(gx.cpu().numpy(), gx0) < tol and rel_err(gw.cpu().numpy(), gw0) < tol
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (96, 96), (160, 160), (192, 192), (64, 32), (192, 96)])
+def test_m32_channel_set_vs_oracle(cin, cout):
+    """BASELINE.json config 2 (UNet m=32: widths 32..192): the widths that are not multiples of 64 run on tf32 tiles even
+    in bf16 mode; forward + backward vs the oracle on the 100k-voxel scene in the mode the inference config uses."""
+    coords, _ = scenes.make_batch("S100k", (1,))
+    vox = rb.voxelize(coords, 1)
+    rules = rb.submanifold_rules(vox["locs"], 1)
+    N = len(vox["locs"])
+    rng = np.random.default_rng(cin + cout)
+    x = rng.standard_normal((N, cin), dtype=np.float32)
+    w = (rng.standard_normal((27, cin, cout), dtype=np.float32) * (2.0 / cin / 27) ** 0.5).astype(np.float32)
+    g = rng.standard_normal((N, cout), dtype=np.float32)
+    m = _gpu_meta(coords, 1, 1)
+    scn.set_precision("bf16")
+    y, gx, gw = torch.empty(0, device="cuda"), torch.empty(0, device="cuda"), torch.zeros(27, cin, cout, device="cuda")
+    SCN.SubmanifoldConvolution_updateOutput(lt(SIZE), lt(3), m, cu(x), y, cu(w), torch.empty(0), 1)
+    SCN.SubmanifoldConvolution_backward(lt(SIZE), lt(3), m, cu(x), gx, cu(g), cu(w), gw, torch.empty(0), 1)
+    y0, _ = arith.rule_conv_forward(x, w, rules, N)
+    gx0, gw0 = arith.rule_conv_backward(x, g, w, rules)
+    assert rel_err(y.cpu().numpy(), y0) < TC_TOL and rel_err(gx.cpu().numpy(), gx0) < TC_TOL
+    assert rel_err(gw.cpu().numpy(), gw0) < TC_TOL

@@ -23,6 +23,14 @@ TF32_TOL = 2e-2
 SIZE = 4096
 
 
+@pytest.fixture(autouse=True)
+def _tensor_core_mode():
+    """The package default is the exact fp32 path; the tests in this file opt into bf16 tiles unless they say otherwise."""
+    scn.set_precision("bf16")
+    yield
+    scn.set_precision("fp32")
+
+
 def lt(v):
     return torch.LongTensor([v, v, v])
 
