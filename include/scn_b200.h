@@ -58,6 +58,11 @@ void scn_meta_destroy(scn_meta *m);
  * keeps at most SCN_POOL_KEEP_MB (default 4096) cached across synchronisations.  scn_pool_trim releases the free part of
  * that cache down to keep_bytes right now (e.g. before another allocator needs the memory). */
 int scn_pool_trim(int device, int64_t keep_bytes);
+/* Tile order of the tensor-core submanifold products: rows of every `block_rows`-row block are processed sorted by their
+ * 27-bit neighbourhood pattern (fewer non-empty (tile, tap) pairs, denser gathers); results are identical up to the
+ * order of fp32 accumulation inside the BatchNorm statistics.  0 = natural row order.  Default 262144, or the value of the
+ * SCN_TILE_SORT environment variable.  Applies to handles created afterwards.  Returns the previous setting. */
+int scn_tile_sort(int block_rows);
 
 /* ---- InputLayer: replaces InputLayer_updateOutput's Metadata::inputLayer -> inputLayerRulesSimple
  * (CUDA/IOLayers.cpp:17-80, Metadata/Metadata.cpp:425-437, Metadata/IOLayersRules.h:136-202).

@@ -24,6 +24,7 @@ PROTOTYPES = {
     "scn_meta_create": (_vp, [C.c_int]),
     "scn_meta_destroy": (None, [_vp]),
     "scn_pool_trim": (C.c_int, [C.c_int, C.c_int64]),
+    "scn_tile_sort": (C.c_int, [C.c_int]),
     "scn_input_layer_build": (C.c_int, [_vp, _i64p, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _i64p]),
     "scn_input_layer_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "scn_input_layer_bwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
@@ -98,6 +99,11 @@ def trim_memory(device=None, keep_bytes=0):
         import torch
         device = torch.cuda.current_device()
     check(lib().scn_pool_trim(int(device), int(keep_bytes)))
+
+
+def tile_sort(block_rows):
+    """Rows per pattern-sort block of the tensor-core tile order (0 = natural order); returns the previous setting."""
+    return int(lib().scn_tile_sort(int(block_rows)))
 
 
 def launch_count():

@@ -189,6 +189,21 @@ static void run_up(Level *F, Level *C, const float *in, const float *w, bool nat
   run_conv(a, w, native_kn, SCN_FP32, s);
 }
 
+// Tensor-core submanifold products walk the level in its pattern-sorted tile order (Level::perm / nbr_sorted) and write
+// their result rows through the permutation; the exact-fp32 kernels keep the natural order.
+static void use_sorted_tiles(ConvArgs &a, Level *L, int precision, cudaStream_t s) {
+  if (precision == SCN_FP32) return;
+  ConvArgs probe = a;
+  probe.bf16 = bf16_conv_shape(a.c_in, a.c_out, precision);
+  if (!conv_tma_supported(probe)) return;
+  ensure_sorted_table(L, s);
+  a.tile_mask = L->tile_mask.p;         // taps with no row in a tile group never enter the pipeline
+  if (!L->tile_mask_sorted) return;     // natural order
+  a.tbl = L->nbr_sorted.p;
+  a.out_rows = L->perm.p;
+  a.out_limit = L->n;
+}
+
 // a16 / b16: optional bf16 copies of a.a / a.b made by the caller
 static void run_wgrad(WgradArgs a, PairList &pairs, int precision, cudaStream_t s, const uint16_t *a16 = nullptr,
                       const uint16_t *b16 = nullptr) {
@@ -297,6 +312,8 @@ scn_meta *scn_meta_create(int device) {
     return nullptr;
   }
 }
+
+int scn_tile_sort(int block_rows) { return set_tile_sort(block_rows); }
 
 int scn_pool_trim(int device, int64_t keep_bytes) {
   SCN_TRY
@@ -456,6 +473,7 @@ int scn_subm_fwd_bn(scn_meta *h, const int64_t size[3], const float *in, const f
   ConvArgs probe = a;
   probe.bf16 = bf16_conv_shape(c_in, c_out, precision);
   SCN_CHECK(precision != SCN_FP32 && conv_tma_supported(probe), "scn_subm_fwd_bn needs the tensor-core path (see scn_fuses_residual)");
+  use_sorted_tiles(a, L, precision, s);
   run_conv(a, weight, true, precision, s, take_bf16_hint(&h->m, in, (long long)L->n * c_in, s));
   if (macs) *macs = (double)L->n_rules * c_in * c_out;
   SCN_CATCH
@@ -480,6 +498,7 @@ int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const floa
     SCN_CHECK(precision != SCN_FP32 && conv_tma_supported(probe) && (uintptr_t)residual % 16 == 0,
               "SubmanifoldConvolution: fused residual / statistics need the tensor-core path (see scn_fuses_residual)");
   }
+  use_sorted_tiles(a, L, precision, s);
   run_conv(a, weight, true, precision, s, take_bf16_hint(&h->m, in, (long long)L->n * c_in, s));
   if (macs) *macs = (double)L->n_rules * c_in * c_out;   // flops += nRules*ip*op, CPU/Convolution.cpp:134
   SCN_CATCH
@@ -503,7 +522,10 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   ConvArgs a;
   a.in = d_out; a.out = d_in;
   a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_out; a.c_out = c_in; a.mirror = true; a.n_rules = L->n_rules; a.in_rows = L->n;
-  if (d_in) run_conv(a, weight, false, precision, s, dgrad16 ? pg : nullptr);
+  if (d_in) {
+    use_sorted_tiles(a, L, precision, s);
+    run_conv(a, weight, false, precision, s, dgrad16 ? pg : nullptr);
+  }
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = L->nbr.p; w.tbl_stride = L->n_pad; w.n_rows = L->n; w.V = 27;
   w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules; w.g_rows = L->n; w.s_rows = L->n;

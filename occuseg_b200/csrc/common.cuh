@@ -130,6 +130,15 @@ struct Level {
   // submanifold 3x3x3 neighbour table (output-stationary form of the reference's 27 rule lists)
   DevBuf<int> nbr;           // [27][n_pad], -1 = absent
   long long n_rules = -1;    // sum_k n_k, centre offset included
+  // Tile order of the tensor-core convolutions: rows of every SORT_BLOCK-row block reordered by their 27-bit occupancy
+  // pattern, so that the 128-row tiles hold rows with similar neighbourhoods -- more (tile, tap) pairs are empty (skipped)
+  // and the present ones are denser (fewer wasted rows in 4-row gather groups).  Results are written through `perm`, so
+  // the row order the caller sees is unchanged.
+  DevBuf<unsigned long long> row_key;   // [n] (block << 27 | pattern), written by k_neighbours
+  DevBuf<int> perm;          // [n_pad] tile position -> row (-1 in the padding)
+  DevBuf<int> nbr_sorted;    // [27][n_pad] = nbr[k][perm[j]]
+  DevBuf<uint32_t> tile_mask; // [n_pad / 128] taps present in every 128-row tile of the order in use (sorted or natural)
+  bool tile_mask_sorted = false;
   PairList nbr_pairs;        // the same rules as 27 compacted (in, out) lists, built on first weight-gradient use
   // size-2/stride-2 link to the next coarser scale
   Level *coarse = nullptr;
@@ -164,6 +173,10 @@ Level *find_level(Meta *m, const int64_t size[3]);
 void build_input_level(Meta *m, const int64_t size[3], const int64_t *coords, bool on_device, long long P, int batch,
                        int mode, cudaStream_t s);
 void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s);
+constexpr int SORT_BLOCK_DEFAULT = 262144;
+bool tile_sort_enabled();
+int set_tile_sort(int block);   // returns the previous setting
+void ensure_sorted_table(Level *L, cudaStream_t s);     // builds perm / nbr_sorted / tile_mask (no-op when already built)
 Level *ensure_coarse_level(Meta *m, Level *fine, const int64_t coarse_size[3], cudaStream_t s);
 
 // io.cu
@@ -204,6 +217,7 @@ struct ConvArgs {
   // entries), result row j goes to out_rows[j] (< 0 or >= out_limit: padding)
   const int *out_rows = nullptr;
   const int *item_off = nullptr;
+  const uint32_t *tile_mask = nullptr;   // tensor-core kernel: per 128-row tile, bit t = table row t has a row in the tile
   int rows_per_item = 0, n_taps = 0, out_limit = 0;
   bool scatter = false;
 };

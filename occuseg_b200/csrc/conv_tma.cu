@@ -276,6 +276,11 @@ struct ConvParams {
   // one-tap-per-row form (see ConvArgs): weight tap of a tile group from item_off, result rows scattered through out_rows
   const int *out_rows, *item_off;
   int rows_per_item, n_taps, out_limit;
+  // optional [tiles] bit t set = table row t has at least one row in that 128-row tile: taps with no row in a tile group
+  // never enter the pipeline (NULL: all V taps are walked)
+  const uint32_t *tile_mask;
+  int n_tiles;
+  int prefetch;                // pull the next item's feature rows towards L2 (prefetch.global.L2) while the current one is issued
   unsigned long long *trace;   // SCN_TRACE=1: clock64 totals over all CTAs (debug only): see conv_tma()
 };
 
@@ -301,6 +306,17 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
   const int ipg = p.V * KC;                                   // items per tile group
   const int G = gridDim.x;
   const int acc_cols = p.MT * p.TN;
+  // table rows (taps) present in tile group tg; every role derives the group's item list from it
+  auto group_mask = [&](int tg_) -> uint32_t {
+    if (tg_ >= p.n_groups) return 0u;
+    if (!p.tile_mask) return p.V >= 32 ? 0xFFFFFFFFu : ((1u << p.V) - 1u);
+    uint32_t mk = 0u;
+    for (int m = 0; m < p.MT; ++m) {
+      const int tile = tg_ * p.MT + m;
+      if (tile < p.n_tiles) mk |= __ldg(&p.tile_mask[tile]);
+    }
+    return mk;
+  };
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -326,7 +342,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
       const uint32_t idesc = idesc_make(p.TN, 0, 0, p.bf16 != 0);
       int s = 0, gi = 0;
       uint32_t ph = 0;
-      TRC(long long w_full = 0; long long w_acc = 0; const long long t_begin = clock64();)
+      TRC(long long w_full = 0; long long w_acc = 0; long long n_tiles_mma = 0; long long t_mma = 0; long long t_commit = 0; const long long t_begin = clock64();)
       for (int tg = blockIdx.x; tg < p.n_groups; tg += G, ++gi) {
         const int buf = gi & 1;
         TRC(const long long ta = clock64();)
@@ -334,16 +350,19 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
         TRC(w_acc += clock64() - ta;)
         tc_fence_after();
         const uint32_t acc = tmem + buf * acc_cols;
-        for (int j = 0; j < ipg; ++j) {
+        const int n_items = __popc(group_mask(tg)) * KC;
+        for (int j = 0; j < n_items; ++j) {
           TRC(const long long tw = clock64();)
           mbar_wait(full_bar + 8 * s, ph);
           TRC(w_full += clock64() - tw;)
           tc_fence_after();
           const uint32_t st = base + s * p.stage_bytes;
           const uint64_t bd = desc_k128(st + p.MT * A_STAGE);
+          TRC(const long long tm0 = clock64();)
           for (int m = 0; m < p.MT; ++m) {
             const uint4 pm = s_masks[s * MAX_MT + m];
             if ((pm.x | pm.y | pm.z | pm.w) == 0u) continue;
+            TRC(++n_tiles_mma;)
             const uint64_t ad = desc_k128(st + m * A_STAGE);
             if (p.bf16) {
 #pragma unroll
@@ -357,7 +376,9 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
                                 ~pm.w);
             }
           }
+          TRC(const long long tc0 = clock64();)
           mma_commit(empty_bar + 8 * s);
+          TRC(const long long tc1 = clock64(); t_mma += tc1 - tm0; t_commit += tc1 - tc0;)
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
         mma_commit(accf_bar + 8 * buf);
@@ -366,6 +387,9 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
         atomicAdd(p.trace + 0, (unsigned long long)(clock64() - t_begin));
         atomicAdd(p.trace + 1, (unsigned long long)w_full);
         atomicAdd(p.trace + 2, (unsigned long long)w_acc);
+        atomicAdd(p.trace + 3, (unsigned long long)n_tiles_mma);
+        atomicAdd(p.trace + 40, (unsigned long long)t_mma);
+        atomicAdd(p.trace + 43, (unsigned long long)t_commit);
       })
     }
   } else if (warp <= p.nprod * p.ni) {
@@ -392,16 +416,31 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
         }
       };
       // item i -> (tile group, index inside the group); this slot's items are i = pw, pw + nprod, ...
-      auto advance = [&](int &tg_, int &j_) {
+      auto settle = [&](int &tg_, int &j_, uint32_t &gm_) {
+        while (tg_ < p.n_groups) {
+          const int n = __popc(gm_) * KC;
+          if (j_ < n) break;
+          j_ -= n;
+          tg_ += G;
+          gm_ = group_mask(tg_);
+        }
+      };
+      auto advance = [&](int &tg_, int &j_, uint32_t &gm_) {
         j_ += p.nprod;
-        while (j_ >= ipg) { j_ -= ipg; tg_ += G; }
+        settle(tg_, j_, gm_);
+      };
+      // table row of item j of a group: the (j / KC)-th present tap
+      auto tap_of = [&](uint32_t gm_, int j_) -> int {
+        for (int i = j_ / KC; i > 0; --i) gm_ &= gm_ - 1u;
+        return __ffs((int)gm_) - 1;
       };
       int tg = blockIdx.x, j = pw;
-      while (j >= ipg) { j -= ipg; tg += G; }
+      uint32_t gk = group_mask(tg);
+      settle(tg, j, gk);
       int s = pw;
       uint32_t ph = 1;                   // parity to wait for on the empty barrier (first pass: already free)
       TRC(long long w_empty = 0; long long t_issue = 0; long long n_items = 0; long long n_copies = 0; long long t_pre = 0;
-          long long t_b = 0; const long long t_begin = clock64();)
+          long long t_b = 0; long long t_ph[3]; t_ph[0] = t_ph[1] = t_ph[2] = 0; const long long t_begin = clock64();)
       // Table rows are fetched TWO items ahead (they stream from HBM once per kernel), and the feature rows of the
       // NEXT item are pulled towards L2 while the current one is issued: a gather that misses L2 holds a TMA
       // request slot for a full HBM round trip, and the slots, not the bandwidth, are what runs out.
@@ -409,19 +448,22 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
 #pragma unroll
       for (int m = 0; m < MAX_MT; ++m) cur[m] = nxt[m] = far[m] = make_int4(-1, -1, -1, -1);
       int tg1 = tg, j1 = j;
-      advance(tg1, j1);
-      if (tg < p.n_groups) load_tbl(tg, j / KC, cur);
-      if (tg1 < p.n_groups) load_tbl(tg1, j1 / KC, nxt);
+      uint32_t gk1 = gk;
+      advance(tg1, j1, gk1);
+      if (tg < p.n_groups) load_tbl(tg, tap_of(gk, j), cur);
+      if (tg1 < p.n_groups) load_tbl(tg1, tap_of(gk1, j1), nxt);
       const char *in_bytes = reinterpret_cast<const char *>(p.in);
       const long long row_bytes = (long long)p.c_in * (p.bf16 ? 2 : 4);
       while (tg < p.n_groups) {
         TRC(const long long t_top = clock64();)
-        const int trow = j / KC, kc = j - trow * KC;
+        const int trow = tap_of(gk, j), kc = j % KC;
         int tg2 = tg1, j2 = j1;
-        advance(tg2, j2);
-        if (tg2 < p.n_groups) load_tbl(tg2, j2 / KC, far);
-        if (tg1 < p.n_groups) {
-          const long long off = (long long)(j1 - (j1 / KC) * KC) * 128;
+        uint32_t gk2 = gk1;
+        advance(tg2, j2, gk2);
+        if (tg2 < p.n_groups) load_tbl(tg2, tap_of(gk2, j2), far);
+        TRC(const long long t_p1 = clock64(); t_ph[0] += t_p1 - t_top;)
+        if (p.prefetch && tg1 < p.n_groups) {
+          const long long off = (long long)(j1 % KC) * 128;
 #pragma unroll
           for (int m = 0; m < MAX_MT; ++m) {
             const int c = m * 4 + (lane >> 3);          // this lane's 8-group chunk: only the share that will issue it prefetches
@@ -434,6 +476,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
             }
           }
         }
+        TRC(const long long t_p2 = clock64(); t_ph[1] += t_p2 - t_p1;)
         // present-row bits of every row tile; absent rows repeat a present row of their 4-row gather group
         uint32_t gm[MAX_MT] = {0, 0}, any = 0;
         uint4 pm[MAX_MT];
@@ -459,6 +502,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
             any |= gm[m];
           }
         }
+        TRC(const long long t_p3 = clock64(); t_ph[2] += t_p3 - t_p2;)
         __syncwarp();
         if (elect_one()) {          // elect.sync, not lane == 0: ptxas then keeps the copy operands in uniform registers (no vote loops)
           TRC(const long long tw = clock64(); t_pre += tw - t_top;)
@@ -511,11 +555,11 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
           cur[m] = nxt[m];
           nxt[m] = far[m];
         }
-        tg = tg1; j = j1;
-        tg1 = tg2; j1 = j2;
+        tg = tg1; j = j1; gk = gk1;
+        tg1 = tg2; j1 = j2; gk1 = gk2;
         s += p.nprod;
         if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
-      }
+            }
       TRC(if (p.trace && lane == 0 && pw == 0) {
         unsigned long long *t = p.trace + 4 + 8 * part;
         atomicAdd(t + 0, (unsigned long long)(clock64() - t_begin));
@@ -525,6 +569,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
         atomicAdd(t + 4, (unsigned long long)n_copies);
         atomicAdd(t + 5, (unsigned long long)t_pre);
         atomicAdd(t + 6, (unsigned long long)t_b);
+        if (part == 0) { atomicAdd(p.trace + 44, (unsigned long long)t_ph[0]); atomicAdd(p.trace + 45, (unsigned long long)t_ph[1]); atomicAdd(p.trace + 46, (unsigned long long)t_ph[2]); }
       })
     }
   } else {
@@ -540,9 +585,12 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
       mbar_arrive(acce_bar + 8);
     }
     int gi = 0;
+    TRC(long long e_wait = 0; const long long e_begin = clock64();)
     for (int tg = blockIdx.x; tg < p.n_groups; tg += G, ++gi) {
       const int buf = gi & 1;
+      TRC(const long long ew = clock64();)
       mbar_wait_warp(accf_bar + 8 * buf, (uint32_t)(gi >> 1) & 1u, lane);
+      TRC(e_wait += clock64() - ew;)
       tc_fence_after();
       float st_sum[8], st_sq[8];           // this lane's column (c0 + lane) of every 32-column chunk, summed over the group's rows
 #pragma unroll
@@ -628,6 +676,10 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(acce_bar + 8 * buf);
     }
+    TRC(if (p.trace && lane == 0 && quarter == 0) {
+      atomicAdd(p.trace + 41, (unsigned long long)(clock64() - e_begin));
+      atomicAdd(p.trace + 42, (unsigned long long)e_wait);
+    })
   }
   tc_fence_before();
   __syncthreads();
@@ -859,6 +911,7 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   ConvParams p;
   p.out_rows = a.out_rows; p.item_off = a.item_off; p.rows_per_item = a.rows_per_item; p.n_taps = a.n_taps;
   p.out_limit = a.out_limit;
+  p.tile_mask = a.tile_mask;
   p.residual = a.residual;
   p.ep_scale = a.ep_scale; p.ep_shift = a.ep_shift; p.ep_leak = a.ep_leak; p.out_bf16 = a.out_bf16;
   p.stats = a.stats;
@@ -893,6 +946,9 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.MT * p.TN) p.tmem_cols <<= 1;
   p.n_groups = (tiles + p.MT - 1) / p.MT;
+  p.n_tiles = tiles;
+  static const int prefetch = env_int("SCN_CONV_PREFETCH", 0);
+  p.prefetch = prefetch;
   const size_t smem = (size_t)fixed + (size_t)p.stages * p.stage_bytes;
   CUtensorMap mx = make_map(a.in, a.bf16, (uint64_t)a.c_in, (uint64_t)a.in_rows, p.kelems, 1, CU_TENSOR_MAP_SWIZZLE_128B);
   CUtensorMap mw = make_map(a.weight_nk, a.bf16, (uint64_t)a.c_in, (uint64_t)(a.n_taps ? a.n_taps : a.V) * a.c_out, p.kelems, (uint32_t)p.TN,
@@ -923,8 +979,9 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
     cudaFree(p.trace);
     const double n = (double)grid.x * grid.y;
     fprintf(stderr, "[conv trace] rows %d C %d->%d V %d TN %d MT %d stages %d nprod %d ni %d ctas %.0f | per CTA: mma loop %.0f clk, "
-            "wait-full %.0f, wait-acc %.0f |", a.n_rows, a.c_in, a.c_out, a.V, p.TN, p.MT, p.stages, p.nprod, p.ni, n, h[0] / n,
-            h[1] / n, h[2] / n);
+            "wait-full %.0f, wait-acc %.0f, in-MMA-issue %.0f, tiles with MMAs %.0f of %.0f | epilogue loop %.0f wait %.0f |", a.n_rows, a.c_in, a.c_out, a.V, p.TN, p.MT, p.stages, p.nprod, p.ni, n, h[0] / n,
+            h[1] / n, h[2] / n, h[40] / n, h[3] / n, (double)p.n_groups * p.MT * a.V * (a.c_in / p.kelems) / n, h[41] / n, h[42] / n);
+    fprintf(stderr, " commit %.0f | share0 pre phases: table-load %.0f prefetch %.0f ballots+smem %.0f |", h[43] / n, h[44] / n, h[45] / n, h[46] / n);
     for (int q = 0; q < p.ni; ++q) {
       const unsigned long long *t = h + 4 + 8 * q;
       fprintf(stderr, " share%d: loop %.0f pre %.0f wait-empty %.0f issue %.0f (masks+B %.0f) items %.0f copies %.0f |", q, t[0] / n,

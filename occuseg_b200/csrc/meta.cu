@@ -124,10 +124,12 @@ __device__ __forceinline__ int hash_find(uint64_t k, const uint64_t *__restrict_
 // coalesced: consecutive threads -> consecutive rows of nbr[k][*].
 __global__ void k_neighbours(const uint64_t *__restrict__ keys, int n, int stride, const uint64_t *__restrict__ hkeys,
                              const int *__restrict__ hvals, uint32_t mask, int *__restrict__ nbr,
-                             unsigned long long *__restrict__ n_rules) {
+                             unsigned long long *__restrict__ n_rules, unsigned long long *__restrict__ row_key,
+                             int sort_block) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int hits = 0;
   if (i < n) {
+    uint32_t pattern = 0;
     uint64_t k = keys[i];
     int x = (int)(k & 0xFFFF), y = (int)((k >> 16) & 0xFFFF), z = (int)((k >> 32) & 0xFFFF);
     uint32_t b = (uint32_t)(k >> 48);
@@ -148,7 +150,9 @@ __global__ void k_neighbours(const uint64_t *__restrict__ keys, int n, int strid
           }
           nbr[t * stride + i] = r;
           hits += (r >= 0);
+          pattern |= (r >= 0 ? 1u : 0u) << t;
         }
+    if (row_key) row_key[i] = ((unsigned long long)(i / sort_block) << 27) | pattern;
   }
   // block-level count -> one atomic per block
   typedef cub::BlockReduce<int, 256> BR;
@@ -378,6 +382,86 @@ static void build_hash(Level *L, cudaStream_t s) {
   }
 }
 
+// rows per sort block; 0 = natural order.  SCN_TILE_SORT overrides the default at load, scn_tile_sort() at run time.
+static std::atomic<int> g_sort_block{[] {
+  const char *e = getenv("SCN_TILE_SORT");
+  const int b = e ? atoi(e) : SORT_BLOCK_DEFAULT;
+  return b < 0 ? 0 : b;
+}()};
+static int sort_block() {
+  const int v = g_sort_block.load(std::memory_order_relaxed);
+  return v > 0 ? v : SORT_BLOCK_DEFAULT;
+}
+bool tile_sort_enabled() { return g_sort_block.load(std::memory_order_relaxed) > 0; }
+int set_tile_sort(int block) { return g_sort_block.exchange(block < 0 ? 0 : block); }
+
+__global__ void k_iota(int *p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+__global__ void k_permute_table(const int *__restrict__ nbr, const int *__restrict__ perm, int n, int stride,
+                                int *__restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= stride) return;
+  const int r = j < n ? perm[j] : -1;
+#pragma unroll
+  for (int k = 0; k < 27; ++k) out[(long long)k * stride + j] = r >= 0 ? __ldg(&nbr[(long long)k * stride + r]) : -1;
+}
+
+// taps present in every 128-row tile (OR of the row patterns), for the order given by perm (NULL = natural)
+__global__ void k_tile_masks(const unsigned long long *__restrict__ row_key, const int *__restrict__ perm, int n,
+                             uint32_t *__restrict__ out) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  int r = j < n ? (perm ? perm[j] : j) : -1;
+  uint32_t pat = r >= 0 ? (uint32_t)(row_key[r] & 0x7FFFFFFull) : 0u;
+  pat = __reduce_or_sync(0xffffffffu, pat);
+  __shared__ uint32_t acc;
+  if (threadIdx.x == 0) acc = 0u;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) atomicOr(&acc, pat);
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = acc;
+}
+
+// Sort the rows of every block by occupancy pattern (keys from k_neighbours) and gather the table into that order.
+void ensure_sorted_table(Level *L, cudaStream_t s) {
+  if (L->tile_mask.p || !L->row_key.p || L->n == 0) return;
+  const int n = L->n;
+  L->tile_mask.alloc((size_t)(L->n_pad / 128), s);
+  if (!tile_sort_enabled()) {          // natural order: only the per-tile tap masks
+    k_tile_masks<<<L->n_pad / 128, 128, 0, s>>>(L->row_key.p, nullptr, n, L->tile_mask.p);
+    SCN_LAUNCH_CHECK();
+    L->row_key.release(s);
+    return;
+  }
+  DevBuf<unsigned long long> keys_out;
+  DevBuf<int> idx;
+  keys_out.alloc((size_t)n, s);
+  idx.alloc((size_t)n, s);
+  L->perm.alloc((size_t)L->n_pad, s);
+  if (L->n_pad != n) SCN_CUDA(cudaMemsetAsync(L->perm.p + n, 0xFF, sizeof(int) * (size_t)(L->n_pad - n), s));
+  k_iota<<<grid_for(n, 256), 256, 0, s>>>(idx.p, n);
+  SCN_LAUNCH_CHECK();
+  int end_bit = 27;
+  while (end_bit < 64 && ((unsigned long long)((n - 1) / sort_block()) >> (end_bit - 27)) != 0) ++end_bit;
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, L->row_key.p, keys_out.p, idx.p, L->perm.p, n, 0, end_bit, s);
+  DevBuf<uint8_t> tmp;
+  tmp.alloc(tb, s);
+  SCN_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, L->row_key.p, keys_out.p, idx.p, L->perm.p, n, 0, end_bit, s));
+  count_launch(4);
+  L->nbr_sorted.alloc((size_t)27 * L->n_pad, s);
+  k_permute_table<<<grid_for(L->n_pad, 256), 256, 0, s>>>(L->nbr.p, L->perm.p, n, L->n_pad, L->nbr_sorted.p);
+  SCN_LAUNCH_CHECK();
+  k_tile_masks<<<L->n_pad / 128, 128, 0, s>>>(L->row_key.p, L->perm.p, n, L->tile_mask.p);
+  SCN_LAUNCH_CHECK();
+  L->tile_mask_sorted = true;
+  keys_out.release(s);
+  idx.release(s);
+  tmp.release(s);
+  L->row_key.release(s);
+}
+
 void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
   (void)m;
   if (L->nbr.p) return;
@@ -390,8 +474,9 @@ void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
     for (int k = 0; k < 27; ++k)
       SCN_CUDA(cudaMemsetAsync(L->nbr.p + (size_t)k * L->n_pad + L->n, 0xFF, sizeof(int) * (size_t)(L->n_pad - L->n), s));
   if (L->n) {
+    L->row_key.alloc((size_t)L->n, s);
     k_neighbours<<<grid_for(L->n, 256), 256, 0, s>>>(L->keys.p, L->n, L->n_pad, L->hkeys.p, L->hvals.p, L->hmask,
-                                                     L->nbr.p, cnt.p);
+                                                     L->nbr.p, cnt.p, L->row_key.p, sort_block());
     SCN_LAUNCH_CHECK();
   }
   unsigned long long h = 0;

@@ -33,7 +33,7 @@ class _Subm(Function):
         ctx.save_for_backward(x, w, b)
         out = torch.empty(0)
         rec["macs"] = R.SubmanifoldConvolution_updateOutput(_lt(size), _lt(3), meta, x, out, w, b, 1)
-        rec["x"], rec["y"] = x.detach(), out
+        rec["x"], rec["y"] = x.detach(), out.detach()
         return out
 
     @staticmethod
@@ -53,7 +53,7 @@ class _Strided(Function):
         out = torch.empty(0)
         f = R.Deconvolution_updateOutput if deconv else R.Convolution_updateOutput
         rec["macs"] = f(_lt(in_size), _lt(out_size), _lt(2), _lt(2), meta, x, out, w, b)
-        rec["x"], rec["y"] = x.detach(), out
+        rec["x"], rec["y"] = x.detach(), out.detach()
         return out
 
     @staticmethod
@@ -74,7 +74,7 @@ class _BN(Function):
         R.BatchNormalization_updateOutput(x, out, sm, si, rm, rv, w, b, eps, momentum, train, leak)
         ctx.save_for_backward(x, out, w, b, rm, rv, sm, si)
         ctx.leak, ctx.rec = leak, rec
-        rec.update(x=x.detach(), y=out, save_mean=sm, save_invstd=si)
+        rec.update(x=x.detach(), y=out.detach(), save_mean=sm, save_invstd=si)
         return out
 
     @staticmethod
@@ -93,7 +93,7 @@ class _NiN(Function):
         ctx.save_for_backward(x, w, b)
         ctx.rec = rec
         R.NetworkInNetwork_updateOutput(x, out, w, b)
-        rec["x"], rec["y"] = x.detach(), out
+        rec["x"], rec["y"] = x.detach(), out.detach()
         return out
 
     @staticmethod
@@ -113,7 +113,7 @@ class _Input(Function):
         ctx.meta = meta
         out = torch.empty(0)
         R.InputLayer_updateOutput(meta, _lt(size), coords, feats, out, batch, mode, None)
-        rec["x"], rec["y"] = feats.detach(), out
+        rec["x"], rec["y"] = feats.detach(), out.detach()
         return out
 
     @staticmethod
@@ -129,7 +129,7 @@ class _Output(Function):
         ctx.meta, ctx.rec = meta, rec
         out = torch.empty(0)
         R.OutputLayer_updateOutput(meta, x, out)
-        rec["x"], rec["y"] = x.detach(), out
+        rec["x"], rec["y"] = x.detach(), out.detach()
         return out
 
     @staticmethod

@@ -515,3 +515,36 @@ def test_occuseg_networks_run_end_to_end():
     assert [tuple(o.shape) for o in outs] == [(P, 20), (P, 64), (P, 64), (P, 1), (P, 3), (P, 2), (P, 1)]
     sum(o.square().mean() for o in outs).backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+
+
+@pytest.mark.parametrize("precision,cin,cout", [("bf16", 64, 64), ("bf16", 128, 64), ("tf32", 32, 96)])
+def test_pattern_sorted_tile_order_is_bit_identical(precision, cin, cout):
+    """The tensor-core kernels walk every level in a tile order sorted by neighbourhood pattern (scn_tile_sort) and write
+    their rows back through the permutation.  Every output row still accumulates its taps in the same order, so forward
+    and dgrad results must be bit-identical to the natural row order, for any block size."""
+    coords, _ = scenes.make_batch("S100k", (2,))
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    res = []
+    scn.set_precision(precision)
+    prev = _lib.tile_sort(0)
+    try:
+        for block in (0, 1000, 32768, 1 << 30):
+            _lib.tile_sort(block)
+            m, _ = build_meta(coords, 1)
+            N = m.getNActive(lt(SIZE))
+            if not res:
+                x = torch.randn(N, cin, device="cuda", generator=gen)
+                w = torch.randn(27, cin, cout, device="cuda", generator=gen) * 0.05
+                g = torch.randn(N, cout, device="cuda", generator=gen)
+                r = torch.randn(N, cout, device="cuda", generator=gen)
+            y = torch.empty(0, device="cuda")
+            st = torch.empty(2, cout, dtype=torch.float64, device="cuda")
+            SCN.SubmanifoldConvolution_updateOutput(lt(SIZE), lt(3), m, x, y, w, torch.empty(0), 1, r, st)
+            dx, dw = torch.empty(0, device="cuda"), torch.zeros_like(w)
+            SCN.SubmanifoldConvolution_backward(lt(SIZE), lt(3), m, x, dx, g, w, dw, torch.empty(0), 1)
+            res.append((y, dx, st))
+    finally:
+        _lib.tile_sort(prev)
+    for y, dx, st in res[1:]:
+        assert torch.equal(y, res[0][0]) and torch.equal(dx, res[0][1])
+        assert float((st - res[0][2]).abs().max() / res[0][2].abs().max()) < 1e-6      # fp32 partial sums regroup
