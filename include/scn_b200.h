@@ -89,6 +89,13 @@ int scn_spatial_locations(scn_meta *m, const int64_t spatial_size[3], int64_t *o
 /* ---- rulebooks (built lazily and cached per scale like Metadata::getSubmanifoldRuleBook /
  * getRuleBook, Metadata.cpp:503-529,597-625).  Exposed so parity tests can compare them bit-exactly
  * with the reference's rule lists after canonical sorting. ------------------------------------- */
+/* Dilated submanifold convolution (SubmanifoldConvolution(..., dilated_rate), submanifoldConvolution.py:36-53): the NEXT
+ * scn_subm_rulebook / scn_subm_neighbour_table / scn_subm_fwd / scn_subm_fwd_bn / scn_subm_bwd on this handle uses the 27 taps
+ * at offsets rate*(dx,dy,dz) -- the rule relation of the reference's SubmanifoldConvolution_SgToRules(grid, rules, size, rate)
+ * (Metadata/SubmanifoldConvolutionRules.h:39-75,114-153; its GPU_GRID builder accepts the argument and ignores it,
+ * :248-275).  One use; rate 1 = the ordinary neighbourhood.  Tables are cached per (scale, rate) like Metadata's map keyed by
+ * TwoLongTensorsToPoint_Dilation (Metadata.cpp:511). */
+int scn_subm_dilation(scn_meta *m, int rate);
 /* ensure the 27-offset neighbour table of a scale exists; *n_rules = total rule count (centre included) */
 int scn_subm_rulebook(scn_meta *m, const int64_t spatial_size[3], void *stream, int64_t *n_rules);
 /* copy the table to HOST: int32 [27, N]; entry = input row feeding output row o at offset k, or -1 */
@@ -98,6 +105,14 @@ int scn_strided_rulebook(scn_meta *m, const int64_t fine_size[3], const int64_t 
                          int64_t *n_coarse);
 /* copy to HOST: parent int32 [Nfine] (coarse row of each fine row) and offset uint8 [Nfine] (0..7) */
 int scn_strided_table(scn_meta *m, const int64_t fine_size[3], int32_t *parent_host, uint8_t *offset_host);
+
+/* ---- ResolutionBasedScattering (sparseconvnet.h:63, sparseconvnet_cuda.cpp:203-209, Metadata/ConvolutionRules.h:327-342;
+ * caller: sparseconvnet/utils.py:72-132 upsample_feature).  lr_xyz int32 [n_lr,3], hr_xyz int32 [n_hr,3] in DEVICE memory;
+ * hr2lr[i] = row of the low-resolution voxel hr_xyz[i] / stride (integer division per axis), where the row of an lr voxel is
+ * its rank among the sorted (z,y,x) unique lr voxels -- the index into lr_xyz when that list is a sample's spatial locations --
+ * or -1 when no lr voxel exists there. */
+int scn_resolution_scatter(const int32_t *lr_xyz, int64_t n_lr, const int32_t *hr_xyz, int64_t n_hr, int stride,
+                           int32_t *hr2lr, void *stream);
 
 /* ---- SCN_BF16 operand copies ----------------------------------------------------------------------
  * The SCN_BF16 kernels read bf16 COPIES of the fp32 feature matrices.  By default every entry makes (and drops) the
@@ -173,6 +188,24 @@ int scn_bn_bwd(const float *in, const float *out, const float *d_out, const floa
                int64_t n_rows, int channels, float leakiness, void *stream);
 /* d_in_add (extension, may be NULL): [n_rows, channels] fp32 added to d_in in the same pass -- the gradient that
  * reaches the same input through a residual shortcut, instead of a separate accumulation pass. */
+
+/* ---- training-mode BatchNorm+ReLU fused with the convolution it feeds (the UNet pattern BN -> ReLU -> conv,
+ * networkArchitectures.py:225-229; the reference fuses BN with its ReLU, BatchNormalization.cu:61-69) ----------------
+ * Forward: scn_bn_fwd with out = NULL and out_bf16 set writes ONLY the bf16 operand the convolution gathers (the fp32
+ * activation is never materialised); the convolution entry then receives that buffer as `in` together with
+ * scn_bf16_operand(m, in, in, 1) -- with a ready copy registered, `in` is an identity key and is not dereferenced.
+ * Backward: scn_bn_bwd_fusion registers the BatchNorm (its input x, saved statistics, affine parameters) for the NEXT
+ * scn_subm_bwd / scn_conv_bwd / scn_deconv_bwd on the handle.  That entry's dgrad epilogue then recomputes the activation
+ * mask from x, writes the MASKED gradient d' into d_in, and accumulates acc[0][c] = sum d', acc[1][c] = sum d'*x (fp64,
+ * [2][channels], zeroed by the entry) -- the reduction pass of the BatchNorm backward disappears.  scn_bn_bwd_apply finishes:
+ * d_in = (d' - mean(d') - (x - mean)*k) * invstd*gamma (+ d_in_add), d_gamma, d_beta.  scn_bn_bwd_fusable says whether a
+ * [c_in -> c_out] layer's dgrad can do this in `precision` (tensor-core shapes only); otherwise use scn_bn_bwd. */
+int scn_bn_bwd_fusion(scn_meta *m, const float *bn_in, const float *save_mean, const float *save_invstd, const float *gamma,
+                      const float *beta, float leakiness, double *acc);
+int scn_bn_bwd_fusable(int c_in, int c_out, int precision);
+int scn_bn_bwd_apply(const float *in, const float *d_masked, const double *acc, const float *save_mean, const float *save_invstd,
+                     const float *gamma, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta, int64_t n_rows,
+                     int channels, void *stream);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,8 @@ PROTOTYPES = {
     "scn_n_points": (C.c_int64, [_vp]),
     "scn_nactive": (C.c_int64, [_vp, _i64p]),
     "scn_spatial_locations": (C.c_int, [_vp, _i64p, _vp]),
+    "scn_resolution_scatter": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, C.c_int, _vp, _vp]),
+    "scn_subm_dilation": (C.c_int, [_vp, C.c_int]),
     "scn_subm_rulebook": (C.c_int, [_vp, _i64p, _vp, _i64p]),
     "scn_subm_neighbour_table": (C.c_int, [_vp, _i64p, _vp]),
     "scn_strided_rulebook": (C.c_int, [_vp, _i64p, _i64p, _vp, _i64p]),
@@ -48,6 +50,9 @@ PROTOTYPES = {
     "scn_deconv_fwd": (C.c_int, [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
     "scn_deconv_bwd": (C.c_int, [_vp, _i64p, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "scn_bn_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, _vp]),
+    "scn_bn_bwd_fusion": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp]),
+    "scn_bn_bwd_fusable": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "scn_bn_bwd_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp]),
     "scn_bf16_operand": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "scn_bf16_plan": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "scn_bn_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, _vp]),

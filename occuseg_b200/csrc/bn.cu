@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) k_bn_apply_fwd(const float *__restrict__ 
       o.x = fmaf(w.x, t.x, b.x); o.y = fmaf(w.y, t.y, b.y); o.z = fmaf(w.z, t.z, b.z); o.w = fmaf(w.w, t.w, b.w);
       o.x = o.x > 0.f ? o.x : o.x * leak; o.y = o.y > 0.f ? o.y : o.y * leak;
       o.z = o.z > 0.f ? o.z : o.z * leak; o.w = o.w > 0.f ? o.w : o.w * leak;
-      reinterpret_cast<float4 *>(y)[e] = o;
+      if (y) reinterpret_cast<float4 *>(y)[e] = o;
       if (y16) {      // bf16 copy for the tensor-core convolution that consumes y (saves that layer's cast pass)
         uint2 h;
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(o.y), "f"(o.x));
@@ -186,12 +186,14 @@ __global__ void __launch_bounds__(256) k_bn_apply_fwd(const float *__restrict__ 
 
 // backward finalize: d_gamma = dotp*invstd, d_beta = sum d'; coef[0][c] = mean(d'), coef[1][c] = dotp*invstd^2/N
 // (BatchNormalization.cu:160-170)
+// raw_mean != NULL: acc[1] holds sum d'*x (not centred); dotp = acc[1] - mean * acc[0]
 __global__ void k_bn_finalize_bwd(const double *__restrict__ acc, long long n, int C,
                                   const float *__restrict__ save_invstd, float *__restrict__ d_gamma,
-                                  float *__restrict__ d_beta, float *__restrict__ coef) {
+                                  float *__restrict__ d_beta, float *__restrict__ coef, const float *__restrict__ raw_mean) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double gsum = acc[c], dotp = acc[C + c], is = (double)save_invstd[c];
+  if (raw_mean) dotp -= (double)raw_mean[c] * gsum;
   if (d_gamma) d_gamma[c] = (float)(dotp * is);
   if (d_beta) d_beta[c] = (float)gsum;
   coef[c] = (float)(gsum / (double)n);
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ 
                                                       const float *__restrict__ save_mean,
                                                       const float *__restrict__ save_invstd,
                                                       const float *__restrict__ gamma, const float *__restrict__ coef,
-                                                      long long n, int C, float leak) {
+                                                      long long n, int C, float leak, bool premasked) {
   extern __shared__ float sm[];   // [5][C]: mean, gradMean, k, w = invstd*gamma, b = beta - mean*w
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float w = save_invstd[c] * (gamma ? gamma[c] : 1.f);
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ 
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       int c = c0 + j;
-      float dd = fmaf(sm[3 * C + c], xv[j], sm[4 * C + c]) > 0.f ? dv[j] : dv[j] * leak;
+      float dd = (premasked || fmaf(sm[3 * C + c], xv[j], sm[4 * C + c]) > 0.f) ? dv[j] : dv[j] * leak;
       ov[j] = (dd - sm[C + c] - (xv[j] - sm[c]) * sm[2 * C + c]) * sm[3 * C + c];
     }
     if (add) {          // gradient arriving through the residual shortcut of the same input: accumulated here
@@ -300,6 +302,7 @@ void bn_fwd(const float *in, float *out, uint16_t *out_bf16, const double *stats
   SCN_LAUNCH_CHECK();
   size_t smem = sizeof(float) * 2 * C;
   SCN_CHECK(!out_bf16 || (v4 && (uintptr_t)out_bf16 % 8 == 0), "BatchNorm: the bf16 copy needs C % 4 == 0 and aligned buffers");
+  SCN_CHECK(out || (out_bf16 && v4), "BatchNorm: no output buffer (a bf16-only output needs C % 4 == 0)");
   if (v4) k_bn_apply_fwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, out, out_bf16, save_mean, save_invstd, gamma, beta, n, C, leakiness);
   else k_bn_apply_fwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, out, nullptr, save_mean, save_invstd, gamma, beta, n, C, leakiness);
   SCN_LAUNCH_CHECK();
@@ -324,13 +327,46 @@ void bn_bwd(const float *in, const float *out, const float *d_out, const float *
   if (r4) k_bn_reduce<4, 1><<<rc.grid, rc.threads, rc.smem, s>>>(in, save_invstd, d_out, save_mean, gamma, beta, n, C, leakiness, acc.p);
   else k_bn_reduce<1, 1><<<rc.grid, rc.threads, rc.smem, s>>>(in, save_invstd, d_out, save_mean, gamma, beta, n, C, leakiness, acc.p);
   SCN_LAUNCH_CHECK();
-  k_bn_finalize_bwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, save_invstd, d_gamma, d_beta, coef.p);
+  k_bn_finalize_bwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, save_invstd, d_gamma, d_beta, coef.p, nullptr);
   SCN_LAUNCH_CHECK();
   size_t smem = sizeof(float) * 5 * C;
-  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness);
-  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness);
+  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness, false);
+  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness, false);
   SCN_LAUNCH_CHECK();
   acc.release(s);
+  coef.release(s);
+}
+
+__global__ void k_bn_mask_coeffs(const float *__restrict__ save_mean, const float *__restrict__ save_invstd,
+                                 const float *__restrict__ gamma, const float *__restrict__ beta, int C, float *__restrict__ coef) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float w = save_invstd[c] * (gamma ? gamma[c] : 1.f);      // the very expressions of k_bn_apply_fwd's prologue
+  coef[c] = w;
+  coef[C + c] = -save_mean[c] * w + (beta ? beta[c] : 0.f);
+}
+
+void bn_mask_coeffs(const float *save_mean, const float *save_invstd, const float *gamma, const float *beta, int C, float *coef,
+                    cudaStream_t s) {
+  k_bn_mask_coeffs<<<(C + 127) / 128, 128, 0, s>>>(save_mean, save_invstd, gamma, beta, C, coef);
+  SCN_LAUNCH_CHECK();
+}
+
+void bn_bwd_apply(const float *in, const float *d_masked, const double *acc, const float *save_mean, const float *save_invstd,
+                  const float *gamma, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta, long long n, int C,
+                  cudaStream_t s) {
+  SCN_CHECK(C > 0 && C <= 4096, "BatchNorm: channel count out of range");
+  if (n == 0) return;
+  const bool v4 = (C % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)d_masked % 16 == 0) && ((uintptr_t)d_in % 16 == 0) &&
+                  ((uintptr_t)d_in_add % 16 == 0);
+  DevBuf<float> coef;
+  coef.alloc(2 * (size_t)C, s);
+  k_bn_finalize_bwd<<<(C + 127) / 128, 128, 0, s>>>(acc, n, C, save_invstd, d_gamma, d_beta, coef.p, save_mean);
+  SCN_LAUNCH_CHECK();
+  const size_t smem = sizeof(float) * 5 * C;
+  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, nullptr, d_masked, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, 0.f, true);
+  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, nullptr, d_masked, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, 0.f, true);
+  SCN_LAUNCH_CHECK();
   coef.release(s);
 }
 

@@ -10,7 +10,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["capi.cu", "meta.cu", "io.cu", "conv_simt.cu", "conv_small.cu", "conv_tma.cu", "bn.cu"]
+SOURCES = ["capi.cu", "meta.cu", "io.cu", "conv_simt.cu", "conv_small.cu", "conv_tma.cu", "bn.cu", "scatter.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "scn_b200.h")]
 LIB = os.path.join(HERE, "libscn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -89,6 +89,14 @@ static Level *need_level(Meta *m, const int64_t size[3], const char *what) {
   return L;
 }
 
+// the (possibly dilated) neighbourhood a submanifold entry works on: consumes the one-use hint of scn_subm_dilation
+static Level *subm_level(Meta *m, const int64_t size[3], cudaStream_t s) {
+  Level *L = need_level(m, size, "SubmanifoldConvolution");
+  const int rate = m->next_dilation;
+  m->next_dilation = 1;
+  return dilated_level(m, L, rate, s);
+}
+
 // ---- precision plumbing ----------------------------------------------------------------------------------
 // SCN_BF16: operands of the tensor-core kernels are bf16 COPIES of the caller's fp32 matrices (made here, one
 // streaming pass each, or handed in by the caller when two products share one), products accumulate in fp32 and
@@ -161,8 +169,32 @@ static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, 
 // One-rule-per-fine-row products (Deconvolution forward, strided-Convolution dgrad):
 //   out[i] = in[parent[i]] * Wk(off[i]).   fp32: input-stationary scatter over the child table;
 //   tensor cores: the fine rows regrouped by tap (see below).
+// The BatchNorm-backward hint of a handle (scn_bn_bwd_fusion) applied to the dgrad product `a` of the next backward entry:
+// returns the scratch buffer holding the mask coefficients (released by the caller after the launch).  Throws when the
+// product cannot honour it (not on the tensor-core path) -- callers ask scn_bn_bwd_fusable first.
+struct BnbScratch {
+  DevBuf<float> coef;
+  void release(cudaStream_t s) { coef.release(s); }
+};
+static void apply_bnb_hint(Meta *m, ConvArgs &a, int precision, BnbScratch &scr, cudaStream_t s) {
+  Meta::BnBwdHint h = m->bnb;
+  m->bnb = Meta::BnBwdHint();
+  if (!h.x) return;
+  ConvArgs probe = a;
+  probe.bf16 = bf16_conv_shape(a.c_in, a.c_out, precision);
+  if (probe.n_rows == 0) probe.n_rows = 1;
+  SCN_CHECK(precision != SCN_FP32 && conv_tma_supported(probe) && a.out != nullptr && (uintptr_t)h.x % 16 == 0,
+            "fused BatchNorm backward: this layer's dgrad does not run on the tensor-core path (see scn_bn_bwd_fusable)");
+  scr.coef.alloc(2 * (size_t)a.c_out, s);
+  bn_mask_coeffs(h.mean, h.invstd, h.gamma, h.beta, a.c_out, scr.coef.p, s);
+  a.bnb_x = h.x;
+  a.bnb_coef = scr.coef.p;
+  a.bnb_leak = h.leak;
+  a.stats = h.acc;
+}
+
 static void run_up(Level *F, Level *C, const float *in, const float *w, bool native_kn, float *out, int c_in, int c_out,
-                   int precision, cudaStream_t s, const uint16_t *in16 = nullptr) {
+                   int precision, cudaStream_t s, const uint16_t *in16 = nullptr, Meta *bnb_from = nullptr) {
   // tensor cores: the fine rows grouped by tap (whole 256-row tile groups per tap), one gathered row and one weight tap
   // per row -- no work is spent on the 7 taps a row does not have
   ConvArgs g;
@@ -180,9 +212,13 @@ static void run_up(Level *F, Level *C, const float *in, const float *w, bool nat
     g.rows_per_item = 256;
     g.n_taps = 8;
     g.out_limit = F->n;
+    BnbScratch scr;
+    if (bnb_from) apply_bnb_hint(bnb_from, g, precision, scr, s);
     run_conv(g, w, native_kn, precision, s, in16);
+    scr.release(s);
     return;
   }
+  SCN_CHECK(!bnb_from || !bnb_from->bnb.x, "fused BatchNorm backward: this layer's dgrad does not run on the tensor-core path");
   ConvArgs a;
   a.in = in; a.out = out; a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8;
   a.c_in = c_in; a.c_out = c_out; a.scatter = true; a.n_rules = F->n;
@@ -409,10 +445,16 @@ int scn_spatial_locations(scn_meta *h, const int64_t size[3], int64_t *out) {
   SCN_CATCH
 }
 
+int scn_subm_dilation(scn_meta *h, int rate) {
+  SCN_TRY
+  SCN_CHECK(h && rate >= 1 && rate < 4096, "scn_subm_dilation: bad dilation rate");
+  h->m.next_dilation = rate;
+  SCN_CATCH
+}
+
 int scn_subm_rulebook(scn_meta *h, const int64_t size[3], void *stream, int64_t *n_rules) {
   SCN_TRY
-  Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
-  ensure_neighbour_table(&h->m, L, note_stream(stream));
+  Level *L = subm_level(&h->m, size, note_stream(stream));
   if (n_rules) *n_rules = L->n_rules;
   SCN_CATCH
 }
@@ -420,6 +462,14 @@ int scn_subm_rulebook(scn_meta *h, const int64_t size[3], void *stream, int64_t 
 int scn_subm_neighbour_table(scn_meta *h, const int64_t size[3], int32_t *out) {
   SCN_TRY
   Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
+  if (h->m.next_dilation != 1) {                 // the table of a dilated neighbourhood (must have been built)
+    Level *D = nullptr;
+    for (Level *c : L->dilated)
+      if (c->dilation == h->m.next_dilation) D = c;
+    h->m.next_dilation = 1;
+    SCN_CHECK(D, "dilated neighbour table not built yet (call scn_subm_dilation + scn_subm_rulebook)");
+    L = D;
+  }
   SCN_CHECK(L->nbr.p, "neighbour table not built yet (call scn_subm_rulebook)");
   SCN_CUDA(cudaMemcpy2D(out, sizeof(int) * L->n, L->nbr.p, sizeof(int) * L->n_pad, sizeof(int) * L->n, 27,
                         cudaMemcpyDeviceToHost));
@@ -449,6 +499,14 @@ int scn_strided_table(scn_meta *h, const int64_t fine[3], int32_t *parent, uint8
   SCN_CATCH
 }
 
+int scn_resolution_scatter(const int32_t *lr_xyz, int64_t n_lr, const int32_t *hr_xyz, int64_t n_hr, int stride,
+                           int32_t *hr2lr, void *stream) {
+  SCN_TRY
+  ProfScope ps(PK_RULEBOOK, 12.0 * (double)(n_lr + n_hr) + 4.0 * (double)n_hr, 0.0, note_stream(stream));
+  resolution_scatter(lr_xyz, n_lr, hr_xyz, n_hr, stride, hr2lr, note_stream(stream));
+  SCN_CATCH
+}
+
 // ---- submanifold ------------------------------------------------------------------------------------
 int scn_bn_eval_coeffs(const float *running_mean, const float *running_var, const float *gamma, const float *beta,
                        int channels, float eps, float *scale, float *shift, void *stream) {
@@ -464,8 +522,7 @@ int scn_subm_fwd_bn(scn_meta *h, const int64_t size[3], const float *in, const f
   cudaStream_t s = note_stream(stream);
   check_channels(c_in, c_out);
   SCN_CHECK(bn_scale && bn_shift, "scn_subm_fwd_bn: null coefficients");
-  Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
-  ensure_neighbour_table(&h->m, L, s);
+  Level *L = subm_level(&h->m, size, s);
   ConvArgs a;
   a.in = in; a.bias = bias; a.out = out;
   a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_in; a.c_out = c_out; a.n_rules = L->n_rules; a.in_rows = L->n;
@@ -485,8 +542,7 @@ int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   SCN_TRY
   cudaStream_t s = note_stream(stream);
   check_channels(c_in, c_out);
-  Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
-  ensure_neighbour_table(&h->m, L, s);
+  Level *L = subm_level(&h->m, size, s);
   ConvArgs a;
   a.in = in; a.bias = bias; a.out = out;
   a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_in; a.c_out = c_out; a.n_rules = L->n_rules; a.in_rows = L->n;
@@ -509,8 +565,7 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   SCN_TRY
   cudaStream_t s = note_stream(stream);
   check_channels(c_in, c_out);
-  Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
-  ensure_neighbour_table(&h->m, L, s);
+  Level *L = subm_level(&h->m, size, s);
   // dgrad: d_in[i] = sum_k d_out[nbr[26-k][i]] * W[k]^T  (rule (i,o) at offset k  <=>  o sits at offset 26-k of i)
   // for this product K = c_out and N = c_in, so the caller's [27][c_in][c_out] array reads as [V][N][K]
   const bool dgrad16 = d_in && bf16_conv_shape(c_out, c_in, precision), wgrad16 = bf16_wgrad_shape(c_in, c_out, precision);
@@ -522,10 +577,15 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   ConvArgs a;
   a.in = d_out; a.out = d_in;
   a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_out; a.c_out = c_in; a.mirror = true; a.n_rules = L->n_rules; a.in_rows = L->n;
+  BnbScratch scr;
   if (d_in) {
     use_sorted_tiles(a, L, precision, s);
+    apply_bnb_hint(&h->m, a, precision, scr, s);
     run_conv(a, weight, false, precision, s, dgrad16 ? pg : nullptr);
+  } else {
+    SCN_CHECK(!h->m.bnb.x, "fused BatchNorm backward needs d_in");
   }
+  scr.release(s);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = L->nbr.p; w.tbl_stride = L->n_pad; w.n_rows = L->n; w.V = 27;
   w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules; w.g_rows = L->n; w.s_rows = L->n;
@@ -563,7 +623,7 @@ int scn_conv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   Level *F = need_level(&h->m, in_size, "Convolution");
   Level *C = ensure_coarse_level(&h->m, F, out_size, s);
   // dgrad: d_in[child[k][p]] = d_out[p] * W[k]^T  (scatter; each fine row has one parent)
-  run_up(F, C, d_out, weight, false, d_in, c_out, c_in, precision, s);
+  run_up(F, C, d_out, weight, false, d_in, c_out, c_in, precision, s, nullptr, &h->m);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
   w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = F->n; w.g_rows = F->n; w.s_rows = C->n;
@@ -604,7 +664,10 @@ int scn_deconv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
   ConvArgs a;
   a.in = d_out; a.out = d_in;
   a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_out; a.c_out = c_in; a.n_rules = F->n; a.in_rows = F->n;
+  BnbScratch scr;
+  apply_bnb_hint(&h->m, a, precision, scr, s);
   run_conv(a, weight, false, precision, s);
+  scr.release(s);
   // dW[k] = sum_p in[p]^T d_out[child[k][p]]
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
@@ -624,6 +687,30 @@ int scn_bf16_operand(scn_meta *h, const float *fp32, void *bf16, int ready) {
   SCN_CATCH
 }
 
+int scn_bn_bwd_fusion(scn_meta *h, const float *bn_in, const float *save_mean, const float *save_invstd, const float *gamma,
+                      const float *beta, float leakiness, double *acc) {
+  SCN_TRY
+  SCN_CHECK(h && bn_in && save_mean && save_invstd && acc, "scn_bn_bwd_fusion: null argument");
+  h->m.bnb.x = bn_in; h->m.bnb.mean = save_mean; h->m.bnb.invstd = save_invstd; h->m.bnb.gamma = gamma; h->m.bnb.beta = beta;
+  h->m.bnb.leak = leakiness; h->m.bnb.acc = acc;
+  SCN_CATCH
+}
+
+int scn_bn_bwd_fusable(int c_in, int c_out, int precision) {
+  // the dgrad product of a [c_in -> c_out] layer contracts over c_out and produces c_in columns
+  const int kel = bf16_conv_shape(c_out, c_in, precision) ? 64 : 32;
+  return precision != SCN_FP32 && c_out >= kel && c_out % kel == 0 && c_in >= 32 && c_in % 32 == 0;
+}
+
+int scn_bn_bwd_apply(const float *in, const float *d_masked, const double *acc, const float *save_mean, const float *save_invstd,
+                     const float *gamma, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta, int64_t n, int C,
+                     void *stream) {
+  SCN_TRY
+  ProfScope ps(PK_BN, (d_in_add ? 4.0 : 3.0) * 4.0 * (double)n * C, 0.0, note_stream(stream));
+  bn_bwd_apply(in, d_masked, acc, save_mean, save_invstd, gamma, d_in_add, d_in, d_gamma, d_beta, n, C, note_stream(stream));
+  SCN_CATCH
+}
+
 int scn_fuses_residual(int c_in, int c_out, int precision) {
   const int kel = bf16_conv_shape(c_in, c_out, precision) ? 64 : 32;
   return precision != SCN_FP32 && c_in >= kel && c_in % kel == 0 && c_out >= 32 && c_out % 32 == 0;
@@ -637,7 +724,7 @@ int scn_bn_fwd(const float *in, float *out, void *out_bf16, const double *stats_
                float *running_mean, float *running_var, const float *gamma, const float *beta, int64_t n, int C, float eps,
                float momentum, int train, float leakiness, void *stream) {
   SCN_TRY
-  ProfScope ps(PK_BN, ((out_bf16 ? 3.5 : 3.0) - (stats_in && train ? 1.0 : 0.0)) * 4.0 * (double)n * C, 0.0,
+  ProfScope ps(PK_BN, ((out_bf16 ? 3.5 : 3.0) - (stats_in && train ? 1.0 : 0.0) - (out ? 0.0 : 1.0)) * 4.0 * (double)n * C, 0.0,
                note_stream(stream));
   bn_fwd(in, out, (uint16_t *)out_bf16, stats_in, save_mean, save_invstd, running_mean, running_var, gamma, beta, n, C, eps, momentum, train != 0,
          leakiness, note_stream(stream));

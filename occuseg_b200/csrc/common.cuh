@@ -119,6 +119,13 @@ void build_pair_list(PairList &out, const int *tbl, int V, int stride, long long
 
 // ---- one scale of one batch -------------------------------------------------------------------------
 struct Level {
+  ~Level();
+  // Dilated 3x3x3 neighbourhoods of this scale (SubmanifoldConvolution(dilated_rate = d): taps at offsets d*(dx,dy,dz),
+  // Metadata/SubmanifoldConvolutionRules.h:39-75,114-153): each is a Level of its own that shares this scale's rows and
+  // hash (borrowed through `base`) and owns its table, rule lists and tile order.
+  std::vector<Level *> dilated;
+  Level *base = nullptr;
+  int dilation = 1;
   int64_t size[3] = {0, 0, 0};
   int n = 0;                 // active rows
   int n_pad = 0;             // row stride of the [V][n_pad] tables (multiple of 128)
@@ -164,6 +171,13 @@ struct Meta {
   const float *hint_src = nullptr;
   void *hint_bf16 = nullptr;
   int hint_ready = 0;
+  int next_dilation = 1;     // scn_subm_dilation(): dilation of the next submanifold entry (one use)
+  // scn_bn_bwd_fusion(): the BatchNorm whose backward the next *_bwd entry folds into its dgrad epilogue (one use)
+  struct BnBwdHint {
+    const float *x = nullptr, *mean = nullptr, *invstd = nullptr, *gamma = nullptr, *beta = nullptr;
+    float leak = 0.f;
+    double *acc = nullptr;
+  } bnb;
   ~Meta();
 };
 
@@ -173,6 +187,7 @@ Level *find_level(Meta *m, const int64_t size[3]);
 void build_input_level(Meta *m, const int64_t size[3], const int64_t *coords, bool on_device, long long P, int batch,
                        int mode, cudaStream_t s);
 void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s);
+Level *dilated_level(Meta *m, Level *L, int rate, cudaStream_t s);    // rate 1 = L itself; table built on return
 constexpr int SORT_BLOCK_DEFAULT = 262144;
 bool tile_sort_enabled();
 int set_tile_sort(int block);   // returns the previous setting
@@ -203,6 +218,10 @@ struct ConvArgs {
   const float *ep_scale = nullptr, *ep_shift = nullptr;
   float ep_leak = 1.f;
   uint16_t *out_bf16 = nullptr;
+  // tensor-core kernel only (dgrad products): fused backward of the BatchNorm that produced this product's input operand --
+  // see ConvParams in conv_tma.cu.  bnb_x [n_rows, c_out] fp32, bnb_coef [2][c_out] (w, b); `stats` receives (sum d', sum d'*x)
+  const float *bnb_x = nullptr, *bnb_coef = nullptr;
+  float bnb_leak = 0.f;
   float *out = nullptr;
   const int *tbl = nullptr;
   int tbl_stride = 0;
@@ -261,6 +280,10 @@ void wgrad_tma(const WgradArgs &a, cudaStream_t s);
 
 void bias_grad(const float *d_out, float *d_bias, long long n_rows, int C, cudaStream_t s);
 
+// scatter.cu
+void resolution_scatter(const int *lr_xyz, long long n_lr, const int *hr_xyz, long long n_hr, int stride, int *hr2lr,
+                        cudaStream_t s);
+
 // bn.cu
 void bn_fwd(const float *in, float *out, uint16_t *out_bf16, const double *stats_in, float *save_mean, float *save_invstd, float *running_mean,
             float *running_var, const float *gamma, const float *beta, long long n, int C, float eps, float momentum,
@@ -271,5 +294,13 @@ void bn_eval_coeffs(const float *running_mean, const float *running_var, const f
 void bn_bwd(const float *in, const float *out, const float *d_out, const float *save_mean, const float *save_invstd,
             const float *gamma, const float *beta, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta, long long n, int C, float leakiness,
             cudaStream_t s);
+// coefficients of the activation mask for a fused BatchNorm backward: coef[0][c] = w = invstd*gamma, coef[1][c] = b = beta - mean*w
+void bn_mask_coeffs(const float *save_mean, const float *save_invstd, const float *gamma, const float *beta, int C, float *coef,
+                    cudaStream_t s);
+// second half of bn_bwd when a convolution epilogue already produced the masked gradient d' and acc = (sum d', sum d'*x):
+// d_in = (d' - mean(d') - (x - mean) * k) * invstd * gamma (+ d_in_add); d_gamma, d_beta.  d_in may alias d_masked.
+void bn_bwd_apply(const float *in, const float *d_masked, const double *acc, const float *save_mean, const float *save_invstd,
+                  const float *gamma, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta, long long n, int C,
+                  cudaStream_t s);
 
 }  // namespace scn

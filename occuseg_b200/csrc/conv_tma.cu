@@ -220,6 +220,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+  uint32_t *r = reinterpret_cast<uint32_t *>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 // zero 32 consecutive columns of this warp's 32 TMEM lanes
 __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
   const uint32_t z = 0;
@@ -267,6 +277,12 @@ struct ConvParams {
   const float *ep_scale, *ep_shift;
   float ep_leak;
   uint16_t *out_bf16;
+  // optional fused BatchNorm BACKWARD of the layer that produced this product's input operand (dgrad products): the result
+  // row r is the gradient w.r.t. that BatchNorm's output; bnb_x = the BatchNorm's input [rows, c_out], bnb_coef = [2][c_out]
+  // (w = invstd*gamma, b = beta - mean*w).  The epilogue applies the activation mask recomputed from x, writes the masked
+  // gradient d', and accumulates the column sums of d' and d'*x into `stats` instead of (sum, sum of squares).
+  const float *bnb_x, *bnb_coef;
+  float bnb_leak;
   float *out;
   const int *tbl;
   int tbl_stride, n_rows, V, c_in, c_out, mirror;
@@ -298,6 +314,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
   const uint32_t accf_bar = empty_bar + 8 * p.stages;       // [2] accumulator buffer complete
   const uint32_t acce_bar = accf_bar + 16;                  // [2] accumulator buffer drained and zeroed
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 4);
+  float4 *s_tile = reinterpret_cast<float4 *>(s_tmem + 4);                              // [4 epilogue warps][32 rows][4] transpose tiles (8 KB)
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler
@@ -592,83 +609,106 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
       mbar_wait_warp(accf_bar + 8 * buf, (uint32_t)(gi >> 1) & 1u, lane);
       TRC(e_wait += clock64() - ew;)
       tc_fence_after();
-      float st_sum[8], st_sq[8];           // this lane's column (c0 + lane) of every 32-column chunk, summed over the group's rows
+      // Epilogue, 16 accumulator columns at a time.  tcgen05.ld hands every lane one ROW (16 consecutive columns); writing
+      // rows from that layout makes each store instruction touch 32 different lines, and the load/store unit -- shared
+      // with the producers' table loads and the MMA thread's mask loads -- was what this kernel queued on.  So the chunk
+      // is transposed through a conflict-free 2 KB shared-memory tile: afterwards 4 consecutive lanes hold the 64
+      // contiguous bytes of one row, a warp instruction covers 8 rows x 64 B, and the residual / BatchNorm-input reads
+      // and the result stores are coalesced.  The column statistics fall out of this layout for free: a lane keeps the
+      // same 4 columns for all its rows, so it sums them in registers and only the 8 lanes that share a column group
+      // are folded with shuffles, once per chunk.
+      float4 *my_t = s_tile + quarter * 128;                 // [32 rows][4 chunks of 16 B], chunk index XOR-swizzled by row
+      const int cj = lane & 3, rg = lane >> 2;                // after the transpose: this lane's column chunk and row slot
+      int r_m[MAX_MT];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) st_sum[i] = st_sq[i] = 0.f;
-      for (int m = 0; m < p.MT; ++m) {
+      for (int m = 0; m < MAX_MT; ++m) {
         int r = (tg * p.MT + m) * TM + quarter * 32 + lane;
-        bool live = r < p.n_rows;
-        if (p.out_rows) {                 // scattered result rows (each written exactly once)
-          r = live ? __ldg(&p.out_rows[r]) : -1;
+        bool live = m < p.MT && r < p.n_rows;
+        if (live && p.out_rows) {         // scattered result rows (each written exactly once)
+          r = __ldg(&p.out_rows[r]);
           live = r >= 0 && r < p.out_limit;
         }
-        float *orow = p.out + (long long)r * p.c_out + n0;
+        r_m[m] = live ? r : -1;
+      }
 #pragma unroll 1
-        for (int c0 = 0; c0 < p.TN; c0 += 32) {
-          float v[32];
-          tmem_ld32(tq + buf * acc_cols + m * p.TN + c0, v);
-          if (live) {
+      for (int c0 = 0; c0 < p.TN; c0 += 16) {
+        const int col = n0 + c0 + 4 * cj;                     // first of this lane's 4 columns
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc = bias4, sh = bias4, wv = bias4, bv = bias4;
+        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
+        if (p.ep_scale) {
+          sc = __ldg(reinterpret_cast<const float4 *>(p.ep_scale + col));
+          sh = __ldg(reinterpret_cast<const float4 *>(p.ep_shift + col));
+        }
+        if (p.bnb_x) {
+          wv = __ldg(reinterpret_cast<const float4 *>(p.bnb_coef + col));
+          bv = __ldg(reinterpret_cast<const float4 *>(p.bnb_coef + p.c_out + col));
+        }
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;   // column statistics of this lane's 4 columns
 #pragma unroll
-            for (int q = 0; q < 32; q += 4) {
-              float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-              if (p.bias) {
-                o.x += __ldg(&p.bias[n0 + c0 + q]);
-                o.y += __ldg(&p.bias[n0 + c0 + q + 1]);
-                o.z += __ldg(&p.bias[n0 + c0 + q + 2]);
-                o.w += __ldg(&p.bias[n0 + c0 + q + 3]);
-              }
+        for (int m = 0; m < MAX_MT; ++m) {
+          if (m >= p.MT) break;
+          float v[16];
+          tmem_ld16(tq + buf * acc_cols + m * p.TN + c0, v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            my_t[lane * 4 + (j ^ ((lane >> 1) & 3))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int row = 8 * it + rg;
+            const int r = __shfl_sync(0xffffffffu, r_m[m], row);
+            float4 o = my_t[row * 4 + (cj ^ ((row >> 1) & 3))];
+            if (r >= 0) {
+              const long long at = (long long)r * p.c_out + col;
+              if (p.bias) { o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w; }
               if (p.residual) {
-                const float4 rv = __ldg(reinterpret_cast<const float4 *>(p.residual + (long long)r * p.c_out + n0 + c0 + q));
+                const float4 rv = __ldg(reinterpret_cast<const float4 *>(p.residual + at));
                 o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
               }
               if (p.ep_scale) {
-                const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.ep_scale + n0 + c0 + q));
-                const float4 sh = __ldg(reinterpret_cast<const float4 *>(p.ep_shift + n0 + c0 + q));
                 o.x = fmaf(sc.x, o.x, sh.x); o.y = fmaf(sc.y, o.y, sh.y); o.z = fmaf(sc.z, o.z, sh.z); o.w = fmaf(sc.w, o.w, sh.w);
                 o.x = o.x > 0.f ? o.x : o.x * p.ep_leak; o.y = o.y > 0.f ? o.y : o.y * p.ep_leak;
                 o.z = o.z > 0.f ? o.z : o.z * p.ep_leak; o.w = o.w > 0.f ? o.w : o.w * p.ep_leak;
               }
-              *reinterpret_cast<float4 *>(orow + c0 + q) = o;
+              float4 sq = make_float4(o.x * o.x, o.y * o.y, o.z * o.z, o.w * o.w);       // second statistic
+              if (p.bnb_x) {
+                // BatchNorm backward: mask recomputed from the BatchNorm's input exactly as its forward pass evaluated it
+                const float4 xv = __ldg(reinterpret_cast<const float4 *>(p.bnb_x + at));
+                o.x = fmaf(wv.x, xv.x, bv.x) > 0.f ? o.x : o.x * p.bnb_leak;
+                o.y = fmaf(wv.y, xv.y, bv.y) > 0.f ? o.y : o.y * p.bnb_leak;
+                o.z = fmaf(wv.z, xv.z, bv.z) > 0.f ? o.z : o.z * p.bnb_leak;
+                o.w = fmaf(wv.w, xv.w, bv.w) > 0.f ? o.w : o.w * p.bnb_leak;
+                sq = make_float4(o.x * xv.x, o.y * xv.y, o.z * xv.z, o.w * xv.w);
+              }
+              *reinterpret_cast<float4 *>(p.out + at) = o;
               if (p.out_bf16) {
                 uint2 h;
                 asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(o.y), "f"(o.x));
                 asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(o.w), "f"(o.z));
-                *reinterpret_cast<uint2 *>(p.out_bf16 + (long long)r * p.c_out + n0 + c0 + q) = h;
+                *reinterpret_cast<uint2 *>(p.out_bf16 + at) = h;
               }
-              v[q] = o.x; v[q + 1] = o.y; v[q + 2] = o.z; v[q + 3] = o.w;
+              s1.x += o.x; s1.y += o.y; s1.z += o.z; s1.w += o.w;
+              s2.x += sq.x; s2.y += sq.y; s2.z += sq.z; s2.w += sq.w;
             }
           }
-          if (p.stats) {
-            // column sums over the warp's 32 rows: transpose-reduce, 31 shuffles per quantity; lane j ends up with column j
-            float w[32];
+          __syncwarp();                  // the tile is rewritten by the next chunk
+        }
+        if (p.stats) {
+          // fold the 8 lanes that hold the same 4 columns (lane bits 2..4), then lanes 0..3 add to the fp64 totals
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              v[i] = live ? v[i] : 0.f;
-              w[i] = v[i] * v[i];
-            }
-#pragma unroll
-            for (int sft = 16; sft >= 1; sft >>= 1) {
-              const bool up = (lane & sft) != 0;
-#pragma unroll
-              for (int i = 0; i < sft; ++i) {
-                const float keep_v = up ? v[i + sft] : v[i], send_v = up ? v[i] : v[i + sft];
-                const float keep_w = up ? w[i + sft] : w[i], send_w = up ? w[i] : w[i + sft];
-                v[i] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, sft);
-                w[i] = keep_w + __shfl_xor_sync(0xffffffffu, send_w, sft);
-              }
-            }
-            st_sum[c0 >> 5] += v[0];
-            st_sq[c0 >> 5] += w[0];
+          for (int sft = 4; sft <= 16; sft <<= 1) {
+            s1.x += __shfl_xor_sync(0xffffffffu, s1.x, sft); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, sft);
+            s1.z += __shfl_xor_sync(0xffffffffu, s1.z, sft); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, sft);
+            s2.x += __shfl_xor_sync(0xffffffffu, s2.x, sft); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, sft);
+            s2.z += __shfl_xor_sync(0xffffffffu, s2.z, sft); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, sft);
+          }
+          if (lane < 4) {
+            double *t = p.stats + col;
+            atomicAdd(t, (double)s1.x); atomicAdd(t + 1, (double)s1.y); atomicAdd(t + 2, (double)s1.z); atomicAdd(t + 3, (double)s1.w);
+            t += p.c_out;
+            atomicAdd(t, (double)s2.x); atomicAdd(t + 1, (double)s2.y); atomicAdd(t + 2, (double)s2.z); atomicAdd(t + 3, (double)s2.w);
           }
         }
-      }
-      if (p.stats) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i * 32 < p.TN) {
-            atomicAdd(p.stats + n0 + i * 32 + lane, (double)st_sum[i]);
-            atomicAdd(p.stats + p.c_out + n0 + i * 32 + lane, (double)st_sq[i]);
-          }
       }
       for (int c = 0; c < acc_cols; c += 32) tmem_zero32(tq + buf * acc_cols + c);
       tmem_wait_st();
@@ -914,6 +954,8 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   p.tile_mask = a.tile_mask;
   p.residual = a.residual;
   p.ep_scale = a.ep_scale; p.ep_shift = a.ep_shift; p.ep_leak = a.ep_leak; p.out_bf16 = a.out_bf16;
+  p.bnb_x = a.bnb_x; p.bnb_coef = a.bnb_coef; p.bnb_leak = a.bnb_leak;
+  SCN_CHECK(!a.bnb_x || a.stats, "conv_tma: the fused BatchNorm backward needs the statistics buffer");
   p.stats = a.stats;
   if (a.stats) SCN_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(double) * 2 * (size_t)a.c_out, s));
   p.in = a.in; p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
@@ -934,7 +976,7 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   if (tiles < mt * sm_count()) mt = 1;                 // small levels: more, smaller groups keep every SM busy
   p.MT = mt;
   p.stage_bytes = p.MT * A_STAGE + p.b_stage;
-  const int fixed = 1024 + 8 * MAX_MT * 16 + 16 * p.MT * 32 * 16 + 8 * (2 * 8 + 4) + 64;
+  const int fixed = 1024 + 8 * MAX_MT * 16 + 16 * p.MT * 32 * 16 + 8 * (2 * 8 + 4) + 64 + 4 * 2 * 256 * 4;
   int st = (225 * 1024 - fixed) / p.stage_bytes;
   if (st > 8) st = 8;
   SCN_CHECK(st >= 2, "conv_tma: shared memory budget");

@@ -11,6 +11,9 @@ namespace scn {
 Meta::~Meta() {
   for (Level *L : levels) delete L;
 }
+Level::~Level() {
+  for (Level *D : dilated) delete D;
+}
 
 Level *find_level(Meta *m, const int64_t size[3]) {
   for (Level *L : m->levels)
@@ -125,7 +128,7 @@ __device__ __forceinline__ int hash_find(uint64_t k, const uint64_t *__restrict_
 __global__ void k_neighbours(const uint64_t *__restrict__ keys, int n, int stride, const uint64_t *__restrict__ hkeys,
                              const int *__restrict__ hvals, uint32_t mask, int *__restrict__ nbr,
                              unsigned long long *__restrict__ n_rules, unsigned long long *__restrict__ row_key,
-                             int sort_block) {
+                             int sort_block, int dil) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int hits = 0;
   if (i < n) {
@@ -144,7 +147,7 @@ __global__ void k_neighbours(const uint64_t *__restrict__ keys, int n, int strid
           if (t == 13) {
             r = i;
           } else {
-            int qx = x + dx, qy = y + dy, qz = z + dz;
+            int qx = x + dx * dil, qy = y + dy * dil, qz = z + dz * dil;
             bool inside = qx >= 0 && qy >= 0 && qz >= 0 && qx < COORD_LIMIT && qy < COORD_LIMIT && qz < COORD_LIMIT;
             r = inside ? hash_find(make_key(b, qz, qy, qx), hkeys, hvals, mask) : -1;
           }
@@ -465,7 +468,8 @@ void ensure_sorted_table(Level *L, cudaStream_t s) {
 void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
   (void)m;
   if (L->nbr.p) return;
-  build_hash(L, s);
+  Level *K = L->base ? L->base : L;       // the scale whose rows and hash this table is built on
+  build_hash(K, s);
   L->nbr.alloc((size_t)27 * L->n_pad, s);
   DevBuf<unsigned long long> cnt;
   cnt.alloc(1, s);
@@ -475,8 +479,8 @@ void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
       SCN_CUDA(cudaMemsetAsync(L->nbr.p + (size_t)k * L->n_pad + L->n, 0xFF, sizeof(int) * (size_t)(L->n_pad - L->n), s));
   if (L->n) {
     L->row_key.alloc((size_t)L->n, s);
-    k_neighbours<<<grid_for(L->n, 256), 256, 0, s>>>(L->keys.p, L->n, L->n_pad, L->hkeys.p, L->hvals.p, L->hmask,
-                                                     L->nbr.p, cnt.p, L->row_key.p, sort_block());
+    k_neighbours<<<grid_for(L->n, 256), 256, 0, s>>>(K->keys.p, L->n, L->n_pad, K->hkeys.p, K->hvals.p, K->hmask,
+                                                     L->nbr.p, cnt.p, L->row_key.p, sort_block(), L->dilation);
     SCN_LAUNCH_CHECK();
   }
   unsigned long long h = 0;
@@ -484,6 +488,27 @@ void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
   SCN_CUDA(cudaStreamSynchronize(s));   // once per scale per batch: the MAC count is part of the API
   L->n_rules = (long long)h;
   cnt.release(s);
+}
+
+Level *dilated_level(Meta *m, Level *L, int rate, cudaStream_t s) {
+  SCN_CHECK(rate >= 1 && rate < 4096, "SubmanifoldConvolution: bad dilation rate");
+  Level *D = L;
+  if (rate != 1) {
+    D = nullptr;
+    for (Level *c : L->dilated)
+      if (c->dilation == rate) D = c;
+    if (!D) {
+      D = new Level();
+      for (int d = 0; d < 3; ++d) D->size[d] = L->size[d];
+      D->n = L->n;
+      D->n_pad = L->n_pad;
+      D->base = L;
+      D->dilation = rate;
+      L->dilated.push_back(D);
+    }
+  }
+  ensure_neighbour_table(m, D, s);
+  return D;
 }
 
 Level *ensure_coarse_level(Meta *m, Level *F, const int64_t coarse_size[3], cudaStream_t s) {

@@ -102,6 +102,26 @@ def _opt(t):
     return t if (t is not None and t.numel()) else None
 
 
+def _conv_input(m, input_features, input_bf16):
+    """The `in` operand of a convolution entry.  input_bf16 (extension): the bf16 operand produced by a fused
+    BatchNorm+ReLU (BatchNormalization_updateOutput(output_features=None, output_bf16=...)); there is no fp32 activation,
+    so the bf16 buffer itself is handed in as `in` with a ready copy registered for it (include/scn_b200.h)."""
+    if input_bf16 is None:
+        return _cuda_f32(input_features, "input")
+    if not (input_bf16.is_cuda and input_bf16.dtype == torch.bfloat16 and input_bf16.is_contiguous()):
+        raise TypeError("input_bf16: expected a contiguous CUDA bfloat16 tensor")
+    _lib.check(_lib.lib().scn_bf16_operand(m._handle(), _ptr(input_bf16), _ptr(input_bf16), 1))
+    return input_bf16
+
+
+def fuses_bn_conv(c_in, c_out):
+    """True when a training-mode BatchNorm(+ReLU) -> convolution [c_in -> c_out] pair can run fused: the BatchNorm writes
+    only the bf16 operand (forward product and weight gradient both read bf16), and the convolution's dgrad epilogue does
+    the BatchNorm's backward reduction."""
+    return (_precision == _lib.BF16 and _lib.lib().scn_bf16_plan(int(c_in), int(c_out), _precision) == 3
+            and bool(_lib.lib().scn_bn_bwd_fusable(int(c_in), int(c_out), _precision)))
+
+
 class Metadata_3:
     """Replaces Metadata<3> (Metadata/Metadata.h:218-364): one handle per batch, owns every scale's voxel
     keys, hash, neighbour tables and stride-2 links on the device; freed with the last Python reference."""
@@ -149,13 +169,15 @@ class Metadata_3:
         return out
 
     # --- rulebook access for parity tests ------------------------------------------------------------
-    def submanifoldNeighbourTable(self, spatial_size):
-        """int32 [27,N] CPU tensor: input row feeding output row o at offset k, or -1."""
+    def submanifoldNeighbourTable(self, spatial_size, dilated_rate=1):
+        """int32 [27,N] CPU tensor: input row feeding output row o at offset k (times dilated_rate), or -1."""
         sz = _lib.size3(spatial_size)
         nr = C.c_int64(0)
+        _dilation(self, dilated_rate)
         _lib.check(_lib.lib().scn_subm_rulebook(self._handle(), sz, _stream(), C.byref(nr)))
         n = self.getNActive(spatial_size)
         out = torch.empty((27, n), dtype=torch.int32)
+        _dilation(self, dilated_rate)
         _lib.check(_lib.lib().scn_subm_neighbour_table(self._handle(), sz, _ptr(out)))
         return out, int(nr.value)
 
@@ -173,6 +195,22 @@ class Metadata_3:
 
 def n_rulebook_bits():
     return 32
+
+
+def ResolutionBasedScattering(m, points_lr, points_hr, stride):
+    """Same entry as the reference's (pybind.cpp:33-35, sparseconvnet_cuda.cpp:203-209): points_lr [Nl,3], points_hr [Nh,3]
+    CUDA int tensors; returns int32 [Nh] = row of the low-resolution voxel points_hr // stride falls into (its rank among the
+    sorted unique lr voxels = the index into points_lr for a sample's spatial locations), -1 where there is none."""
+    lr, hr = points_lr, points_hr
+    if not (lr.is_cuda and hr.is_cuda):
+        raise TypeError("ResolutionBasedScattering: expected CUDA tensors (there is no CPU path)")
+    lr = lr[:, :3].to(torch.int32).contiguous()
+    hr = hr[:, :3].to(torch.int32).contiguous()
+    out = torch.empty(hr.size(0), dtype=torch.int32, device=hr.device)
+    with torch.cuda.device(hr.device):
+        _lib.check(_lib.lib().scn_resolution_scatter(_ptr(lr), lr.size(0), _ptr(hr), hr.size(0), int(stride), _ptr(out),
+                                                     _stream()))
+    return out
 
 
 # ---- IO layers (sparseconvnet.h:151-179) -------------------------------------------------------------
@@ -221,6 +259,12 @@ def OutputLayer_updateGradInput(m, d_input_features, d_output_features):
 
 
 # ---- convolutions (sparseconvnet.h:50-61, 89-116) ------------------------------------------------------
+def _dilation(m, rate):
+    """dilated_rate of the reference entries: taps at offsets rate*(dx,dy,dz) for the next submanifold entry on this handle"""
+    if int(rate) != 1:
+        _lib.check(_lib.lib().scn_subm_dilation(m._handle(), int(rate)))
+
+
 def _check_weight(weight, v):
     w = _cuda_f32(weight, "weight")
     if w.dim() != 3 or w.size(0) != v:
@@ -229,12 +273,13 @@ def _check_weight(weight, v):
 
 
 def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_features, output_features, weight, bias,
-                                        dilated_rate=1, residual=None, stats=None):
+                                        dilated_rate=1, residual=None, stats=None, input_bf16=None):
     """residual (extension): [N, nOut] tensor added to the result inside the kernel (see fuses_residual).
-    stats (extension): float64 [2, nOut] tensor that receives the column sums / sums of squares of the result."""
-    if int(dilated_rate) != 1 or any(int(f) != 3 for f in filter_size.tolist()):
-        raise NotImplementedError("SubmanifoldConvolution: only 3x3x3, dilation 1 is on this path")
-    x, w, b = _cuda_f32(input_features, "input"), _check_weight(weight, 27), _opt(bias)
+    stats (extension): float64 [2, nOut] tensor that receives the column sums / sums of squares of the result.
+    input_bf16 (extension): see _conv_input."""
+    if any(int(f) != 3 for f in filter_size.tolist()):
+        raise NotImplementedError("SubmanifoldConvolution: only 3x3x3 filters are on this path")
+    x, w, b = _conv_input(m, input_features, input_bf16), _check_weight(weight, 27), _opt(bias)
     if residual is not None:
         residual = _cuda_f32(residual, "residual")
         if residual.shape != (x.size(0), w.size(2)):
@@ -245,6 +290,7 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
         if x.size(0) != n or x.size(1) != w.size(1):
             raise ValueError(f"SubmanifoldConvolution: input is {tuple(x.shape)}, scale has {n} rows, nIn={w.size(1)}")
         output_features.resize_(n, w.size(2))
+        _dilation(m, dilated_rate)
         _lib.check(_lib.lib().scn_subm_fwd(m._handle(), _lib.size3(spatial_size), _ptr(x), _ptr(w), _ptr(b),
                                            _ptr(residual), _ptr(stats), _ptr(output_features), w.size(1), w.size(2),
                                            _precision, _stream(), C.byref(macs)))
@@ -285,11 +331,12 @@ def SubmanifoldConvolutionBN_updateOutput(spatial_size, filter_size, m, input_fe
 
 
 def SubmanifoldConvolution_backward(spatial_size, filter_size, m, input_features, d_input_features, d_output_features,
-                                    weight, d_weight, d_bias, dilated_rate=1):
-    x, g, w = _cuda_f32(input_features, "input"), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 27)
+                                    weight, d_weight, d_bias, dilated_rate=1, input_bf16=None):
+    x, g, w = _conv_input(m, input_features, input_bf16), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 27)
     with torch.cuda.device(x.device):
         if d_input_features is not None:      # None: the caller does not need the input gradient (first layer)
             d_input_features.resize_(x.size(0), x.size(1))
+        _dilation(m, dilated_rate)
         _lib.check(_lib.lib().scn_subm_bwd(m._handle(), _lib.size3(spatial_size), _ptr(x), _ptr(g), _ptr(w),
                                            _ptr(d_input_features), _ptr(d_weight), _ptr(_opt(d_bias)), w.size(1),
                                            w.size(2), _precision, _stream()))
@@ -302,13 +349,14 @@ def _check_2s2(filter_size, filter_stride):
 
 
 def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, input_features, output_features, weight,
-                             bias):
+                             bias, input_bf16=None):
     _check_2s2(filter_size, filter_stride)
-    x, w, b = _cuda_f32(input_features, "input"), _check_weight(weight, 8), _opt(bias)
+    w, b = _check_weight(weight, 8), _opt(bias)
     macs, nc = C.c_double(0.0), C.c_int64(0)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(weight.device):
         _lib.check(_lib.lib().scn_strided_rulebook(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _stream(),
                                                    C.byref(nc)))
+        x = _conv_input(m, input_features, input_bf16)
         output_features.resize_(nc.value, w.size(2))
         _lib.check(_lib.lib().scn_conv_fwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(w),
                                            _ptr(b), _ptr(output_features), w.size(1), w.size(2), _precision, _stream(),
@@ -317,8 +365,8 @@ def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, i
 
 
 def Convolution_backward(in_size, out_size, filter_size, filter_stride, m, input_features, d_input_features,
-                         d_output_features, weight, d_weight, d_bias):
-    x, g, w = _cuda_f32(input_features, "input"), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 8)
+                         d_output_features, weight, d_weight, d_bias, input_bf16=None):
+    x, g, w = _conv_input(m, input_features, input_bf16), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 8)
     with torch.cuda.device(x.device):
         d_input_features.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_conv_bwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(g),
@@ -327,9 +375,9 @@ def Convolution_backward(in_size, out_size, filter_size, filter_stride, m, input
 
 
 def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, input_features, output_features,
-                               weight, bias):
+                               weight, bias, input_bf16=None):
     _check_2s2(filter_size, filter_stride)
-    x, w, b = _cuda_f32(input_features, "input"), _check_weight(weight, 8), _opt(bias)
+    x, w, b = _conv_input(m, input_features, input_bf16), _check_weight(weight, 8), _opt(bias)
     macs = C.c_double(0.0)
     with torch.cuda.device(x.device):
         n = m.getNActive(out_size)
@@ -343,8 +391,8 @@ def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m,
 
 
 def Deconvolution_backward(in_size, out_size, filter_size, filter_stride, m, input_features, d_input_features,
-                           d_output_features, weight, d_weight, d_bias):
-    x, g, w = _cuda_f32(input_features, "input"), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 8)
+                           d_output_features, weight, d_weight, d_bias, input_bf16=None):
+    x, g, w = _conv_input(m, input_features, input_bf16), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 8)
     with torch.cuda.device(x.device):
         d_input_features.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_deconv_bwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(g),
@@ -361,7 +409,8 @@ def BatchNormalization_updateOutput(input_features, output_features, saveMean, s
     produced it (attach_stats); the training-mode reduction pass is skipped."""
     x = _cuda_f32(input_features, "input")
     with torch.cuda.device(x.device):
-        output_features.resize_(x.size(0), x.size(1))
+        if output_features is not None:        # None (extension): only the bf16 operand is written
+            output_features.resize_(x.size(0), x.size(1))
         if output_bf16 is not None:
             output_bf16.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_bn_fwd(_ptr(x), _ptr(output_features), _ptr(output_bf16), _ptr(stats), _ptr(saveMean),
@@ -385,6 +434,27 @@ def BatchNormalization_backward(input_features, d_input_features, output_feature
                                          _ptr(_opt(weight)), _ptr(_opt(bias)), _ptr(d_input_add), _ptr(d_input_features),
                                          _ptr(_opt(d_weight)),
                                          _ptr(_opt(d_bias)), x.size(0), x.size(1), float(leakiness), _stream()))
+
+
+def BatchNormalization_backwardFusion(m, input_features, saveMean, saveInvStd, weight, bias, leakiness, acc):
+    """(extension) register this BatchNorm for the NEXT *_backward entry on handle m: that entry's d_input comes back
+    already multiplied by the activation mask, and acc (float64 [2, C]) holds sum d' and sum d'*x (scn_bn_bwd_fusion)."""
+    x = _cuda_f32(input_features, "input")
+    _lib.check(_lib.lib().scn_bn_bwd_fusion(m._handle(), _ptr(x), _ptr(saveMean), _ptr(saveInvStd), _ptr(_opt(weight)),
+                                            _ptr(_opt(bias)), float(leakiness), _ptr(acc)))
+
+
+def BatchNormalization_backwardApply(input_features, d_masked, acc, saveMean, saveInvStd, weight, d_input_features, d_weight,
+                                     d_bias, d_input_add=None):
+    """(extension) second half of BatchNormalization_backward after a fused dgrad epilogue (scn_bn_bwd_apply)."""
+    x, g = _cuda_f32(input_features, "input"), _cuda_f32(d_masked, "grad")
+    if d_input_add is not None:
+        d_input_add = _cuda_f32(d_input_add, "d_input_add")
+    with torch.cuda.device(x.device):
+        d_input_features.resize_(x.size(0), x.size(1))
+        _lib.check(_lib.lib().scn_bn_bwd_apply(_ptr(x), _ptr(g), _ptr(acc), _ptr(saveMean), _ptr(saveInvStd), _ptr(_opt(weight)),
+                                               _ptr(d_input_add), _ptr(d_input_features), _ptr(_opt(d_weight)),
+                                               _ptr(_opt(d_bias)), x.size(0), x.size(1), _stream()))
 
 
 # ---- 1x1 "NetworkInNetwork": the reference itself calls ATen's GEMM here (CUDA/NetworkInNetwork.cpp:9-50).

@@ -10,7 +10,7 @@ from .layers import (AddTable, BatchNormalization, BatchNormLeakyReLU, BatchNorm
                      Deconvolution, Identity, InputLayer, JoinTable, Metadata, NetworkInNetwork, OutputLayer,
                      Sequential, SubmanifoldConvolution, ValidConvolution)
 from .tensor import SparseConvNetTensor
-from .utils import optionalTensor, optionalTensorReturn, toLongTensor
+from .utils import optionalTensor, optionalTensorReturn, toLongTensor, upsample_feature
 
 forward_pass_multiplyAdd_count = 0
 forward_pass_hidden_states = 0

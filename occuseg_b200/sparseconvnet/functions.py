@@ -129,6 +129,76 @@ class BatchNormalizationFunction(Function):
         return gx, optionalTensorReturn(gw), optionalTensorReturn(gb), None, None, None, None, None, None, None
 
 
+class BatchNormConvFunction(Function):
+    """Training-mode BatchNorm(+ReLU) followed by a convolution (SubmanifoldConvolution / Convolution / Deconvolution) as
+    ONE autograd node -- the UNet's BN -> ReLU -> conv pattern (networkArchitectures.py:225-229).
+
+    forward : the BatchNorm writes only the bf16 operand the convolution gathers (the fp32 activation is never
+              materialised: 6 instead of 10 bytes per element), the convolution runs on it (+ residual / statistics
+              epilogue as in SubmanifoldConvolutionFunction);
+    backward: the convolution's dgrad epilogue recomputes the activation mask from the BatchNorm's input, writes the masked
+              gradient and accumulates the BatchNorm's two backward column sums (its reduction pass disappears); one
+              apply pass finishes d_x (+ the gradient arriving through a residual shortcut), d_gamma, d_beta.
+    Same arithmetic as the two separate layers up to fp32 summation order of the column sums."""
+
+    KINDS = {
+        "subm": (SCN.SubmanifoldConvolution_updateOutput, SCN.SubmanifoldConvolution_backward),
+        "conv": (SCN.Convolution_updateOutput, SCN.Convolution_backward),
+        "deconv": (SCN.Deconvolution_updateOutput, SCN.Deconvolution_backward),
+    }
+
+    @staticmethod
+    def forward(ctx, x, bn_weight, bn_bias, running_mean, running_var, eps, momentum, leakiness, conv_weight, conv_bias,
+                metadata, kind, in_size, out_size, filter_size, filter_stride, residual=None, want_stats=False,
+                with_alias=False):
+        """Returns (out, stats, alias) -- see SubmanifoldConvolutionFunction / BatchNormalizationFunction."""
+        n_planes = running_mean.shape[0]
+        save_mean, save_invstd = x.new_empty(n_planes), x.new_empty(n_planes)
+        y16 = torch.empty(0, dtype=torch.bfloat16, device=x.device)
+        SCN.BatchNormalization_updateOutput(x, None, save_mean, save_invstd, running_mean, running_var, bn_weight, bn_bias,
+                                            eps, momentum, True, leakiness, y16, SCN.held_stats(x))
+        out = x.new_empty(0)
+        n_out = conv_weight.size(2)
+        stats = torch.empty((2, n_out) if want_stats else 0, dtype=torch.float64, device=x.device)
+        fwd = BatchNormConvFunction.KINDS[kind][0]
+        if kind == "subm":
+            macs = fwd(in_size, filter_size, metadata, None, out, conv_weight, conv_bias, 1, residual,
+                       stats if want_stats else None, input_bf16=y16)
+        else:
+            macs = fwd(in_size, out_size, filter_size, filter_stride, metadata, None, out, conv_weight, conv_bias,
+                       input_bf16=y16)
+        _count(macs, out)
+        ctx.scn_meta, ctx.kind, ctx.leakiness = metadata, kind, leakiness
+        ctx.save_for_backward(x, bn_weight, bn_bias, save_mean, save_invstd, y16, conv_weight, conv_bias, in_size, out_size,
+                              filter_size, filter_stride)
+        ctx.mark_non_differentiable(stats)
+        return out, stats, (x.view_as(x) if with_alias else x.new_empty(0))
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_stats=None, grad_alias=None):
+        (x, bn_weight, bn_bias, save_mean, save_invstd, y16, conv_weight, conv_bias, in_size, out_size, filter_size,
+         filter_stride) = ctx.saved_tensors
+        m, kind = ctx.scn_meta, ctx.kind
+        g = grad_out.contiguous()
+        acc = torch.empty((2, x.size(1)), dtype=torch.float64, device=x.device)      # zeroed by the convolution entry
+        d_masked = g.new_empty(0)
+        gw, gb = torch.zeros_like(conv_weight), torch.zeros_like(conv_bias)
+        SCN.BatchNormalization_backwardFusion(m, x, save_mean, save_invstd, bn_weight, bn_bias, ctx.leakiness, acc)
+        bwd = BatchNormConvFunction.KINDS[kind][1]
+        if kind == "subm":
+            bwd(in_size, filter_size, m, None, d_masked, g, conv_weight, gw, gb, 1, input_bf16=y16)
+        else:
+            bwd(in_size, out_size, filter_size, filter_stride, m, None, d_masked, g, conv_weight, gw, gb, input_bf16=y16)
+        gx = g.new_empty(0)
+        g_gamma, g_beta = torch.zeros_like(bn_weight), torch.zeros_like(bn_bias)
+        add = grad_alias.contiguous() if grad_alias is not None and grad_alias.numel() == x.numel() else None
+        SCN.BatchNormalization_backwardApply(x, d_masked, acc, save_mean, save_invstd, bn_weight, gx, g_gamma, g_beta, add)
+        del ctx.scn_meta
+        return (gx, optionalTensorReturn(g_gamma), optionalTensorReturn(g_beta), None, None, None, None, None, gw,
+                optionalTensorReturn(gb), None, None, None, None, None, None,
+                (grad_out if ctx.needs_input_grad[16] else None), None, None)
+
+
 class NetworkInNetworkFunction(Function):
     @staticmethod
     def forward(ctx, x, weight, bias):

@@ -76,6 +76,39 @@ def _fusable_inference_pair(a, b, input):
             and SCN.fuses_residual(a.nIn, a.nOut))
 
 
+def _fusable_training_pair(bn, conv, input):
+    """Training: BatchNorm(+ReLU) `bn` directly followed by a convolution `conv` runs as one autograd node
+    (functions.BatchNormConvFunction) when both of the convolution's bf16 products and its dgrad epilogue allow it."""
+    return (isinstance(bn, BatchNormalization) and isinstance(conv, (SubmanifoldConvolution, Convolution, Deconvolution))
+            and bn.training and torch.is_grad_enabled() and input.features.is_cuda and input.features.requires_grad
+            and bn.nPlanes == conv.nIn and getattr(conv, "dilated_rate", 1) == 1
+            and conv.filter_volume == (27 if isinstance(conv, SubmanifoldConvolution) else 8)
+            and not _has_hooks(bn) and not _has_hooks(conv) and input.features.size(0) > 1
+            and SCN.fuses_bn_conv(conv.nIn, conv.nOut))
+
+
+def _bn_conv_training(bn, conv, input, residual=None, with_alias=False):
+    conv._check(input)
+    if isinstance(conv, SubmanifoldConvolution):
+        kind, in_size, out_size, stride = "subm", input.spatial_size, input.spatial_size, conv.filter_size
+    elif isinstance(conv, Convolution):
+        kind, in_size, stride = "conv", input.spatial_size, conv.filter_stride
+        out_size = (in_size - conv.filter_size) // stride + 1
+        assert ((out_size - 1) * stride + conv.filter_size == in_size).all(), (in_size, out_size)
+    else:
+        kind, in_size, stride = "deconv", input.spatial_size, conv.filter_stride
+        out_size = (in_size - 1) * stride + conv.filter_size
+    want_stats = kind == "subm" and SCN.fuses_residual(conv.nIn, conv.nOut)
+    out, stats, alias = F.BatchNormConvFunction.apply(
+        input.features, optionalTensor(bn, "weight"), optionalTensor(bn, "bias"), bn.running_mean, bn.running_var, bn.eps,
+        bn.momentum, bn.leakiness, conv.weight, optionalTensor(conv, "bias"), input.metadata, kind, in_size, out_size,
+        conv.filter_size, stride, residual, want_stats, with_alias)
+    if stats.numel():
+        SCN.attach_stats(out, stats)
+    t = _same(input, out, out_size)
+    return (t, _same(input, alias)) if with_alias else t
+
+
 class Sequential(torch.nn.Sequential):
     def add(self, module):
         self._modules[str(len(self._modules))] = module
@@ -89,6 +122,9 @@ class Sequential(torch.nn.Sequential):
         while i < len(mods):
             if i + 1 < len(mods) and isinstance(input, SparseConvNetTensor) and _fusable_inference_pair(mods[i], mods[i + 1], input):
                 input = _conv_bn_inference(mods[i], mods[i + 1], input)
+                i += 2
+            elif i + 1 < len(mods) and isinstance(input, SparseConvNetTensor) and _fusable_training_pair(mods[i], mods[i + 1], input):
+                input = _bn_conv_training(mods[i], mods[i + 1], input)      # training: BN(+ReLU) -> conv as one node
                 i += 2
             else:
                 input = mods[i](input)
@@ -129,6 +165,12 @@ class ResidualConcatTable(ConcatTable):
                    and SCN.fuses_residual(last.nIn, last.nOut) and mods[0].training)
         if not fusable:
             return [shortcut(input), body(input)]
+        if _fusable_training_pair(mods[0], mods[1], input) and isinstance(mods[1], SubmanifoldConvolution) \
+                and _fusable_training_pair(mods[2], last, input):
+            # both BN -> conv pairs as single nodes: bf16-only activations, BatchNorm backward reductions in the dgrad epilogues
+            t, alias = _bn_conv_training(mods[0], mods[1], input, with_alias=True)
+            s = shortcut(alias)
+            return [_bn_conv_training(mods[2], last, t, residual=s.features)]
         t, alias = mods[0](input, with_alias=True)
         s = shortcut(alias)
         for m in mods[1:-1]:

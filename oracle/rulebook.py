@@ -101,8 +101,10 @@ def _ctr_from_locs(locs, batch_size):
     return _sample_bounds(locs[:, 3], batch_size)
 
 
-def submanifold_rules(locs, batch_size=None):
-    """27 rule lists for a 3x3x3 submanifold convolution:
+def submanifold_rules(locs, batch_size=None, dilated_rate=1):
+    """27 rule lists for a 3x3x3 submanifold convolution (dilated_rate d: taps at offsets d*(dx,dy,dz), the relation of
+    the reference's CPU builder Metadata/SubmanifoldConvolutionRules.h:39-75,114-153 -- its NearestNeighborSearch probes the
+    unshifted candidate only, :84-107, so dilation is an exact lookup; the GPU_GRID builder ignores the argument, :248-275):
     Metadata/SubmanifoldConvolutionRules.h:435-468 (per-sample loop, lists appended) ->
     CUDA/SubmanifoldRules_cuda.cpp:97-202.  Offset index k enumerates dx outermost, dz innermost
     (SubmanifoldRules_cuda.cu:63-73): k = (dx+1)*9 + (dy+1)*3 + (dz+1).  For each voxel `self`
@@ -126,7 +128,7 @@ def submanifold_rules(locs, batch_size=None):
         for dx in (-1, 0, 1):
             for dy in (-1, 0, 1):
                 for dz in (-1, 0, 1):
-                    q = key31(x + dx, y + dy, z + dz)
+                    q = key31(x + dx * dilated_rate, y + dy * dilated_rate, z + dz * dilated_rate)
                     pos = np.searchsorted(keys, q)
                     pos_c = np.minimum(pos, max(e - s - 1, 0))
                     hit = (keys[pos_c] == q) if e > s else np.zeros(0, bool)
@@ -205,3 +207,18 @@ def input_layer_mean(feats, vox, average=True):
         m = cnt > j
         out[m] += mult[m, None] * feats[pts[ptr[:-1][m] + j]]
     return out
+
+
+def resolution_scatter(points_lr, points_hr, stride):
+    """ResolutionBasedScatteringCuda, Metadata/ConvolutionRules.h:327-342: hr // stride (ATen integer division) looked up in the
+    multivalue hash of the lr points, whose value is the rank of the key among the sorted unique lr keys
+    (CUDA/CUDPPWrapper.hpp:789-829); 0xFFFFFFFF (-1) when absent.  Keys are the 31-bit z/y/x packing, aliasing included."""
+    lr = np.asarray(points_lr, np.int64).reshape(-1, 3)
+    hr = np.asarray(points_hr, np.int64).reshape(-1, 3)
+    uk = np.unique(key31(lr[:, 0], lr[:, 1], lr[:, 2]))
+    q3 = np.trunc(hr / stride).astype(np.int64) if stride != 1 else hr
+    q = key31(q3[:, 0], q3[:, 1], q3[:, 2])
+    pos = np.searchsorted(uk, q)
+    pos_c = np.minimum(pos, max(len(uk) - 1, 0))
+    hit = (uk[pos_c] == q) if len(uk) else np.zeros(len(q), bool)
+    return np.where(hit, pos_c, NOT_FOUND).astype(np.int32)

@@ -316,3 +316,87 @@ def test_m32_channel_set_vs_oracle(cin, cout):
     gx0, gw0 = arith.rule_conv_backward(x, g, w, rules)
     assert rel_err(y.cpu().numpy(), y0) < TC_TOL and rel_err(gx.cpu().numpy(), gx0) < TC_TOL
     assert rel_err(gw.cpu().numpy(), gw0) < TC_TOL
+
+
+# ------------------------------------------------------------------------------------------- ResolutionBasedScattering
+def test_resolution_based_scattering_and_upsample_feature():
+    """SCN.ResolutionBasedScattering (sparseconvnet_cuda.cpp:203-209) vs the restatement of the reference's hash lookup, and
+    sparseconvnet.utils.upsample_feature (utils.py:72-132), nearest and bilinear, vs a direct numpy evaluation."""
+    coords, feats = scenes.make_batch("small", (0, 1))
+    B = 2
+    inp = scn.InputLayer(3, SIZE, mode=4)
+    t0 = inp([torch.from_numpy(coords).float(), torch.from_numpy(feats).cuda(), None, B])
+    m = t0.metadata
+    m.stridedTable(lt(SIZE), lt(SIZE // 2))
+    m.stridedTable(lt(SIZE // 2), lt(SIZE // 4))
+    loc_hr = m.getSpatialLocations(lt(SIZE)).numpy()
+    loc_lr = m.getSpatialLocations(lt(SIZE // 4)).numpy()
+    rng = np.random.default_rng(0)
+    for k in range(B):
+        lr, hr = loc_lr[loc_lr[:, 3] == k, :3], loc_hr[loc_hr[:, 3] == k, :3]
+        for stride, q in ((4, hr), (2, hr), (1, hr // 4 + rng.integers(-1, 2, hr.shape))):
+            got = SCN.ResolutionBasedScattering(m, cu(lr.astype(np.int32)), cu(q.astype(np.int32)), stride).cpu().numpy()
+            want = rb.resolution_scatter(lr, q, stride)
+            assert np.array_equal(got, want), (k, stride)
+            if stride == 4:
+                assert (got >= 0).all() and np.array_equal(lr[got], hr // 4)      # every fine voxel has its coarse parent
+    # upsample_feature: level-2 features carried to level 0
+    n_lr = len(loc_lr)
+    f_lr = rng.standard_normal((n_lr, 8)).astype(np.float32)
+    lr_t = scn.SparseConvNetTensor(cu(f_lr), m, lt(SIZE // 4))
+    up = scn.upsample_feature(lr_t, t0, 4).features.cpu().numpy()
+    start = {k: int((loc_lr[:, 3] < k).sum()) for k in range(B)}
+    want = np.concatenate([f_lr[start[k] + rb.resolution_scatter(loc_lr[loc_lr[:, 3] == k, :3], loc_hr[loc_hr[:, 3] == k, :3], 4)]
+                           for k in range(B)], 0)
+    assert np.array_equal(up, want)
+    upb = scn.upsample_feature(lr_t, t0, 4, bilinear=True).features.cpu().numpy()
+    # direct evaluation of the trilinear formula for a sample of rows
+    lut = [{tuple(p): i for i, p in enumerate(loc_lr[loc_lr[:, 3] == k, :3].tolist())} for k in range(B)]
+    for i in rng.integers(0, len(loc_hr), 200):
+        x, k = loc_hr[i, :3].astype(np.float64), int(loc_hr[i, 3])
+        c = (x - 1.5) / 4
+        acc, wsum = np.zeros(8), 0.0
+        for ax in (np.ceil(c[0]), np.floor(c[0])):
+            for ay in (np.ceil(c[1]), np.floor(c[1])):
+                for az in (np.ceil(c[2]), np.floor(c[2])):
+                    w = (1 - abs(ax - c[0])) * (1 - abs(ay - c[1])) * (1 - abs(az - c[2]))
+                    j = lut[k].get((int(ax), int(ay), int(az)))
+                    if j is not None:
+                        acc += w * f_lr[start[k] + j]
+                        wsum += w
+        if wsum > 0:
+            assert np.allclose(upb[i], acc / wsum, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------- dilated submanifold convolution
+@pytest.mark.parametrize("rate,precision,c", [(2, "fp32", 16), (3, "bf16", 64), (2, "tf32", 32)])
+def test_dilated_submanifold_convolution(rate, precision, c):
+    """SubmanifoldConvolution(dilated_rate): rulebook bit-exact vs the oracle (pinned to the reference's compiled CPU builder,
+    tests/test_oracle.py), forward + backward vs the oracle arithmetic on those rules; the ordinary (rate 1) table of the same
+    handle is untouched."""
+    coords, _ = scenes.make_batch("small", (3, 4))
+    vox = rb.voxelize(coords, 2)
+    rules = rb.submanifold_rules(vox["locs"], 2, rate)
+    N = len(vox["locs"])
+    m = _gpu_meta(coords, 2, 1)
+    nbr1, r1 = m.submanifoldNeighbourTable(lt(SIZE))
+    nbr, n_rules = m.submanifoldNeighbourTable(lt(SIZE), rate)
+    assert n_rules == sum(len(r) for r in rules) and n_rules != r1
+    assert np.array_equal(nbr.numpy(), _oracle_table(rules, N))
+    assert np.array_equal(m.submanifoldNeighbourTable(lt(SIZE))[0].numpy(), nbr1.numpy())
+    rng = np.random.default_rng(rate)
+    x = rng.standard_normal((N, c), dtype=np.float32)
+    w = (rng.standard_normal((27, c, c), dtype=np.float32) * (2.0 / c / 27) ** 0.5).astype(np.float32)
+    g = rng.standard_normal((N, c), dtype=np.float32)
+    scn.set_precision(precision)
+    conv = scn.SubmanifoldConvolution(3, c, c, 3, False, dilated_rate=rate).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(cu(w))
+    xin = cu(x).requires_grad_(True)
+    y = conv(scn.SparseConvNetTensor(xin, m, lt(SIZE))).features
+    y.backward(cu(g))
+    y0, _ = arith.rule_conv_forward(x, w, rules, N)
+    gx0, gw0 = arith.rule_conv_backward(x, g, w, rules)
+    tol = FP32_TOL if precision == "fp32" else TC_TOL
+    assert rel_err(y.detach().cpu().numpy(), y0) < tol and rel_err(xin.grad.cpu().numpy(), gx0) < tol
+    assert rel_err(conv.weight.grad.cpu().numpy(), gw0) < tol

@@ -416,16 +416,17 @@ def test_fused_residual_block_equals_unfused():
     feats = torch.randn(len(coords), 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
     x = [torch.from_numpy(coords).float(), feats, None, 2]
     res = []
-    real = scn_SCN.fuses_residual
+    real, real_bn = scn_SCN.fuses_residual, scn_SCN.fuses_bn_conv
     for fused in (True, False):
         scn_SCN.fuses_residual = real if fused else (lambda a, b: False)
+        scn_SCN.fuses_bn_conv = real_bn if fused else (lambda a, b: False)
         try:
             net = _small_unet()
             out = net(x)
             out.square().mean().backward()
             res.append((out.detach().clone(), [p.grad.detach().clone() for p in net.parameters()]))
         finally:
-            scn_SCN.fuses_residual = real
+            scn_SCN.fuses_residual, scn_SCN.fuses_bn_conv = real, real_bn
     assert _l2_err(res[0][0].cpu().numpy(), res[1][0].cpu().numpy()) < 1e-2
     ga = torch.cat([g.flatten() for g in res[0][1]]).cpu().numpy()      # all parameter gradients as one vector
     gb = torch.cat([g.flatten() for g in res[1][1]]).cpu().numpy()
@@ -548,3 +549,51 @@ def test_pattern_sorted_tile_order_is_bit_identical(precision, cin, cout):
     for y, dx, st in res[1:]:
         assert torch.equal(y, res[0][0]) and torch.equal(dx, res[0][1])
         assert float((st - res[0][2]).abs().max() / res[0][2].abs().max()) < 1e-6      # fp32 partial sums regroup
+
+
+@pytest.mark.parametrize("kind", ["subm", "conv", "deconv"])
+def test_fused_batchnorm_conv_pair_equals_the_two_layers(kind):
+    """Training-mode BatchNormReLU -> convolution as one autograd node (bf16-only activation, BatchNorm backward sums in
+    the dgrad epilogue, functions.BatchNormConvFunction) against the same two modules run separately.  The forward
+    arithmetic is identical (same bf16 operand, same mask expression): outputs must be bit-identical; the backward differs
+    only in the fp32 grouping of the two BatchNorm column sums: 1e-5."""
+    from occuseg_b200.sparseconvnet import SCN as scn_SCN
+    coords, _ = scenes.make_batch("small", (0, 1))
+    torch.manual_seed(21)
+    cin, cout = (128, 64) if kind != "conv" else (64, 128)
+    inp = scn.InputLayer(3, SIZE, mode=4)
+    pre = scn.Convolution(3, 64, 64, 2, 2, False).cuda()           # creates the coarse scale the deconvolution needs
+    bn = scn.BatchNormLeakyReLU(cin, leakiness=0.2).cuda()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_()
+    conv = {"subm": lambda: scn.SubmanifoldConvolution(3, cin, cout, 3, False),
+            "conv": lambda: scn.Convolution(3, cin, cout, 2, 2, False),
+            "deconv": lambda: scn.Deconvolution(3, cin, cout, 2, 2, False)}[kind]().cuda()
+    seq = scn.Sequential().add(bn).add(conv)
+    feats0 = torch.randn(len(coords), 64, device="cuda")
+    real = scn_SCN.fuses_bn_conv
+    res = []
+    for fused in (True, False):
+        scn_SCN.fuses_bn_conv = real if fused else (lambda a, b: False)
+        try:
+            t0 = inp([torch.from_numpy(coords).float(), feats0, None, 2])
+            tc = pre(t0)
+            base = tc if kind == "deconv" else t0
+            n = base.features.size(0)
+            gen = torch.Generator(device="cuda").manual_seed(5)
+            xin = torch.randn(n, cin, device="cuda", generator=gen).requires_grad_(True)
+            bn.running_mean.zero_(); bn.running_var.fill_(1.0)
+            for p_ in list(bn.parameters()) + list(conv.parameters()):
+                p_.grad = None
+            out = seq(scn.SparseConvNetTensor(xin, base.metadata, base.spatial_size))
+            g = torch.randn(out.features.shape, device="cuda", generator=gen)
+            out.features.backward(g)
+            res.append((out.features.detach().clone(), xin.grad.clone(), bn.weight.grad.clone(), bn.bias.grad.clone(),
+                        conv.weight.grad.clone(), bn.running_mean.clone(), bn.running_var.clone()))
+        finally:
+            scn_SCN.fuses_bn_conv = real
+    a, b = res
+    assert torch.equal(a[0], b[0]) and torch.equal(a[5], b[5]) and torch.equal(a[6], b[6])
+    for i, name in ((1, "d_x"), (2, "d_gamma"), (3, "d_beta"), (4, "d_weight")):
+        assert rel_err(a[i].cpu().numpy(), b[i].cpu().numpy()) < 1e-5, (kind, name)

@@ -202,3 +202,24 @@ def test_total_rules_symmetry():
     rules = rb.submanifold_rules(v["locs"], 2)
     for k in range(27):
         assert _canon_equal([rules[k][:, ::-1]], [rules[26 - k]])
+
+
+@pytest.mark.parametrize("rate", [2, 3])
+def test_dilated_rules_pinned_to_reference_compiled_builder(rate):
+    """SubmanifoldConvolution(dilated_rate): the restatement against SubmanifoldConvolution_SgToRules(grid, rules, size, rate)
+    compiled from the reference tree (Metadata/SubmanifoldConvolutionRules.h:114-153)."""
+    from oracle import rules_ref as rr
+    if not rr.available():
+        pytest.skip("oracle/_ref/scn_rules_ref.so not available")
+    from occuseg_b200 import scenes
+    c, _ = scenes.make_batch("tiny", (7, 8))
+    v = rb.voxelize(c, 2)
+    sc = rr.Scene(c, 2, 4)
+    mine = rr.relation_of_lists(rb.submanifold_rules(v["locs"], 2, rate), v["locs"])
+    ref = sc.submanifold(0, dilated_rate=rate)
+    assert len(ref) > len(v["locs"]) and np.array_equal(ref, mine)
+    # the dilated relation really differs from the plain one, and taps sit `rate` voxels away
+    plain = rr.relation_of_lists(rb.submanifold_rules(v["locs"], 2, 1), v["locs"])
+    assert not np.array_equal(plain, mine)
+    off = mine[:, 1:4] - mine[:, 4:7]
+    assert set(np.unique(np.abs(off)).tolist()) <= {0, rate}
