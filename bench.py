@@ -34,8 +34,17 @@ def parse():
     ap.add_argument("--scenes", type=int, default=8, help="scenes per GPU per step")
     ap.add_argument("--m", type=int, default=64)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 5],
+                    help="BASELINE.json configs: 3 = UNet m=64 training step, 8 x S250k (the metric's configuration, default); "
+                         "2 = UNet m=32 inference on one S250k scene; 5 = UNet m=64 fwd+bwd on one 1M-voxel scene")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-precision-sweep", action="store_true", help="skip the tf32 / fp32 side measurements")
+    a = ap.parse_args()
+    if a.config == 2:
+        a.preset, a.scenes, a.m = "S250k", 1, 32
+    elif a.config == 5:
+        a.preset, a.scenes, a.m = "S1M", 1, 64
+    return a
 
 
 def peaks():
@@ -161,8 +170,11 @@ def run_ours(args):
 
     torch.manual_seed(1234)                       # identical initial weights on every rank
     net = SparseBackbone(m=args.m, levels=6).to(dev)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3, fused=True)
-    reducer = BucketedGradAllReduce(net.parameters(), world) if world > 1 else None
+    inference = args.config == 2
+    if inference:
+        net.eval()
+    opt = None if inference else torch.optim.Adam(net.parameters(), lr=1e-3, fused=True)
+    reducer = BucketedGradAllReduce(net.parameters(), world) if (world > 1 and not inference) else None
 
     # ---- synthetic batch: rank r gets seeds r*scenes .. r*scenes+scenes-1 (weak scaling)
     seeds = tuple(rank * args.scenes + i for i in range(args.scenes))
@@ -174,6 +186,9 @@ def run_ours(args):
     B = args.scenes
 
     def step(coords, feats):
+        if inference:
+            with torch.no_grad():
+                return net([coords, feats, None, B]).square().mean()
         out = net([coords, feats, None, B])
         loss = out.square().mean()
         loss.backward()
@@ -256,6 +271,21 @@ def run_ours(args):
     h2d = coords_host.numel() * 8 + feats_host.numel() * 4
     d2h = 4
 
+    # ---- side measurement: the same step on the tf32 tiles and on the exact fp32 path (rel 1e-5), two steps each
+    precision_ms = {args.precision: ms / args.steps}
+    if world == 1 and not args.no_precision_sweep:
+        for prec in ("tf32", "fp32"):
+            if prec == args.precision:
+                continue
+            try:
+                scn.set_precision(prec)
+                step(coords_dev, feats_dev)
+                precision_ms[prec] = timed(lambda: step(coords_dev, feats_dev), 2) / 2
+            except Exception as e:      # never lose the headline number to a side measurement
+                precision_ms[prec] = f"failed: {e}"
+            finally:
+                scn.set_precision(args.precision)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -275,13 +305,25 @@ def run_ours(args):
                 traffic = json.load(f).get(top)
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+        # two predictions of the launch time: gather-model bytes at the measured HBM copy peak, and the launch's FLOPs at the
+        # sustained tensor peak of the operand type; the LARGER predicted time is the binding roofline
+        tc_peak_used = tc_peak if args.precision == "bf16" else tc_peak / 2
+        t_hbm = t["bytes"] / t["launches"] / (hbm_peak * 1e9) * 1e3
+        t_tc = t["flops"] / t["launches"] / (tc_peak_used * 1e12) * 1e3 if t["flops"] else 0.0
+        bound = "tensor" if t_tc > t_hbm else "hbm"
+        if bound == "tensor":
+            ach_tc = t["flops"] / (t["ms"] * 1e-3) / 1e12
+            head = {"bound": "tensor", "achieved": ach_tc, "peak": tc_peak_used, "unit": "TFLOP/s", "frac": ach_tc / tc_peak_used}
+        else:
+            head = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak}
+        roofline = {**head, "kernel": top, "traffic": traffic, "peak_source": peak_src,
+                    "frac_hbm_gather_model": t_hbm / per_launch_ms, "frac_tensor": t_tc / per_launch_ms,
+                    "predicted_ms_hbm": t_hbm, "predicted_ms_tensor": t_tc,
                     "launches": t["launches"], "avg_launch_ms": per_launch_ms,
                     "algorithmic_bytes_per_launch": t["bytes"] / t["launches"],
                     "share_of_step": t["ms"] / ms_prof, "instrumented_ms_per_step": ms_prof / args.steps,
                     "tensor_tflops": t["flops"] / (t["ms"] * 1e-3) / 1e12 if t["flops"] else None,
-                    "tensor_peak_tflops": tc_peak if args.precision == "bf16" else tc_peak / 2,
+                    "tensor_peak_tflops": tc_peak_used,
                     "by_kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in kinds.items()},
                     # the same algorithmic-bytes / CUDA-event-time ratio for every kernel family of the library
                     "families": {k: {"achieved_gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] else None,
@@ -307,14 +349,18 @@ def run_ours(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"bf16": "bf16 tensor-core operands (fp32 storage, fp32 accumulate)",
                   "tf32": "tf32 (fp32 storage, fp32 accumulate)", "fp32": "f32"}[args.precision], "data": "synthetic",
-        "config": {"workload": f"OccuSeg UNet m={args.m} (reps 1, residual, 6 levels) fwd+bwd+Adam, "
-                               f"{args.scenes} x {args.preset} scenes per GPU, rulebook build included",
+        "config": {"workload": (f"BASELINE.json configs[1]: OccuSeg UNet m={args.m} inference (eval mode, no grad), "
+                                f"{args.scenes} x {args.preset} scene, rulebook build included" if inference else
+                                f"BASELINE.json configs[{2 if args.config == 3 else 4}]: OccuSeg UNet m={args.m} (reps 1, residual, 6 levels) "
+                                f"fwd+bwd+Adam, {args.scenes} x {args.preset} scenes per GPU, rulebook build included"),
+                   "baseline_config": args.config,
                    "preset": args.preset, "scenes_per_gpu": args.scenes, "m": args.m,
                    "voxels_per_step": total_voxels, "parallelism": f"scene-sharded dp{world}",
                    "l2": "inputs larger than L2 (level-0 activations 0.5 GB per tensor); no explicit flush"},
         "e2e": {"value": total_voxels * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",
                 "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "precision_ms": precision_ms,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -204,8 +204,14 @@ int scn_bn_bwd_fusion(scn_meta *m, const float *bn_in, const float *save_mean, c
                       const float *beta, float leakiness, double *acc);
 int scn_bn_bwd_fusable(int c_in, int c_out, int precision);
 int scn_bn_bwd_apply(const float *in, const float *d_masked, const double *acc, const float *save_mean, const float *save_invstd,
-                     const float *gamma, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta, int64_t n_rows,
-                     int channels, void *stream);
+                     const float *gamma, const float *d_in_add, int64_t ld_add, float *d_in, float *d_gamma, float *d_beta,
+                     int64_t n_rows, int channels, void *stream);
+/* ld_add: row stride of d_in_add in floats (0 = dense).
+ * Row-strided gradients: a JoinTable's backward hands its consumers column slices of one [N, 2c] gradient.  scn_grad_stride
+ * registers the row stride (floats) of the d_out argument of the NEXT scn_subm_bwd / scn_conv_bwd / scn_deconv_bwd on the handle,
+ * so the slice is read where it lies (by the bf16 cast every product of that entry works from) instead of being copied out
+ * first.  One use; needs the SCN_BF16 path for all of the entry's products (the entry fails otherwise) and no bias gradient. */
+int scn_grad_stride(scn_meta *m, int64_t ld);
 
 #ifdef __cplusplus
 }

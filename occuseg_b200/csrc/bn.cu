@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ 
                                                       const float *__restrict__ save_mean,
                                                       const float *__restrict__ save_invstd,
                                                       const float *__restrict__ gamma, const float *__restrict__ coef,
-                                                      long long n, int C, float leak, bool premasked) {
+                                                      long long n, int C, float leak, bool premasked, long long ld_add) {
   extern __shared__ float sm[];   // [5][C]: mean, gradMean, k, w = invstd*gamma, b = beta - mean*w
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float w = save_invstd[c] * (gamma ? gamma[c] : 1.f);
@@ -238,11 +238,12 @@ __global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ 
       ov[j] = (dd - sm[C + c] - (xv[j] - sm[c]) * sm[2 * C + c]) * sm[3 * C + c];
     }
     if (add) {          // gradient arriving through the residual shortcut of the same input: accumulated here
+      const long long ea = ld_add == C ? e * VEC : (e / cv) * ld_add + c0;     // rows of `add` may be ld_add floats apart
       if (VEC == 4) {
-        const float4 av = __ldg(reinterpret_cast<const float4 *>(add) + e);
+        const float4 av = __ldg(reinterpret_cast<const float4 *>(add + ea));
         ov[0] += av.x; ov[1] += av.y; ov[2] += av.z; ov[3] += av.w;
       } else {
-        ov[0] += __ldg(add + e);
+        ov[0] += __ldg(add + ea);
       }
     }
     if (VEC == 4) reinterpret_cast<float4 *>(dx)[e] = make_float4(ov[0], ov[1], ov[2], ov[3]);
@@ -330,8 +331,8 @@ void bn_bwd(const float *in, const float *out, const float *d_out, const float *
   k_bn_finalize_bwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, save_invstd, d_gamma, d_beta, coef.p, nullptr);
   SCN_LAUNCH_CHECK();
   size_t smem = sizeof(float) * 5 * C;
-  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness, false);
-  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness, false);
+  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness, false, C);
+  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness, false, C);
   SCN_LAUNCH_CHECK();
   acc.release(s);
   coef.release(s);
@@ -353,8 +354,10 @@ void bn_mask_coeffs(const float *save_mean, const float *save_invstd, const floa
 }
 
 void bn_bwd_apply(const float *in, const float *d_masked, const double *acc, const float *save_mean, const float *save_invstd,
-                  const float *gamma, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta, long long n, int C,
-                  cudaStream_t s) {
+                  const float *gamma, const float *d_in_add, long long ld_add, float *d_in, float *d_gamma, float *d_beta,
+                  long long n, int C, cudaStream_t s) {
+  if (!d_in_add || ld_add == 0) ld_add = C;
+  SCN_CHECK(ld_add >= C && (ld_add == C || ld_add % 4 == 0), "BatchNorm: bad row stride of d_in_add");
   SCN_CHECK(C > 0 && C <= 4096, "BatchNorm: channel count out of range");
   if (n == 0) return;
   const bool v4 = (C % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)d_masked % 16 == 0) && ((uintptr_t)d_in % 16 == 0) &&
@@ -364,8 +367,8 @@ void bn_bwd_apply(const float *in, const float *d_masked, const double *acc, con
   k_bn_finalize_bwd<<<(C + 127) / 128, 128, 0, s>>>(acc, n, C, save_invstd, d_gamma, d_beta, coef.p, save_mean);
   SCN_LAUNCH_CHECK();
   const size_t smem = sizeof(float) * 5 * C;
-  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, nullptr, d_masked, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, 0.f, true);
-  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, nullptr, d_masked, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, 0.f, true);
+  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, nullptr, d_masked, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, 0.f, true, ld_add);
+  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, nullptr, d_masked, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, 0.f, true, ld_add);
   SCN_LAUNCH_CHECK();
   coef.release(s);
 }

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include <mutex>
 #include <cstdlib>
+#include <cstdio>
 
 namespace scn {
 
@@ -53,10 +54,12 @@ ProfScope::~ProfScope() {
   if (slot >= 0) cudaEventRecord(g_prof[slot].e1, s);
 }
 static void prof_drain() {
+  static const bool log_each = getenv("SCN_PROF_LOG") != nullptr;      // one line per instrumented launch (debugging aid)
   for (ProfRec &r : g_prof) {
     cudaEventSynchronize(r.e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (log_each) fprintf(stderr, "[scn prof] %-10s %8.4f ms  %10.1f MB  %9.2f GFLOP\n", prof_name(r.kind), ms, r.bytes / 1e6, r.flops / 1e9);
     g_prof_acc[r.kind][0] += 1;
     g_prof_acc[r.kind][1] += ms;
     g_prof_acc[r.kind][2] += r.bytes;
@@ -113,8 +116,26 @@ struct Bf16Copy {
     cast_bf16(src, buf.p, n, s);
     return buf.p;
   }
+  // from rows `ld` floats apart (0 = dense)
+  const uint16_t *make_rows(const float *src, long long ld, long long rows, int cols, cudaStream_t s) {
+    buf.alloc((size_t)rows * cols, s);
+    ProfScope ps(PK_CAST, 6.0 * (double)rows * cols, 0.0, s);
+    cast_bf16_rows(src, ld, rows, cols, buf.p, s);
+    return buf.p;
+  }
   void release(cudaStream_t s) { buf.release(s); }
 };
+
+// row stride of d_out registered for this backward entry (scn_grad_stride); 0 = dense.  A strided d_out is only ever read by
+// the bf16 cast, so every product of the entry must run on bf16 copies (and there must be no bias gradient).
+static long long take_grad_ld(Meta *m, int cols, bool all_bf16, const float *d_bias) {
+  long long ld = m->next_grad_ld;
+  m->next_grad_ld = 0;
+  if (ld == cols) ld = 0;
+  SCN_CHECK(ld == 0 || (all_bf16 && !d_bias && ld > cols),
+            "row-strided d_out needs the bf16 tensor-core path for every product of this entry (scn_grad_stride)");
+  return ld;
+}
 
 // `w` is the caller's weight array; native_kn says whether, for THIS product, it already reads as
 // [V][K=c_in][N=c_out] (true) or as [V][N][K] (false).  The fp32 kernels want KN, the tensor-core kernel
@@ -141,8 +162,12 @@ static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, 
   }
   const double es = a.bf16 ? 2.0 : 4.0;      // bytes per gathered element
   // algorithmic work (gather/scatter model): R*Cin*s + N*Cout*4 + 4*R + V*Cin*Cout*s
-  const double bytes = es * (double)a.n_rules * a.c_in + 4.0 * (double)(a.scatter ? a.n_rules : a.n_rows) * a.c_out +
-                       4.0 * (double)a.n_rules + es * (double)wv * a.c_in * a.c_out;
+  // + the per-row fp32 operand an epilogue fusion reads in the same pass (residual shortcut, or the BatchNorm input of a fused
+  //   BatchNorm backward): N*Cout*4 -- algorithmic traffic of the fused elementwise layer, which no longer has a pass of its own
+  const double out_rows = (double)(a.scatter || a.out_rows ? a.n_rules : a.n_rows);
+  const double bytes = es * (double)a.n_rules * a.c_in + 4.0 * out_rows * a.c_out + 4.0 * (double)a.n_rules +
+                       es * (double)wv * a.c_in * a.c_out + ((a.residual || a.bnb_x) ? 4.0 * out_rows * a.c_out : 0.0) +
+                       (a.out_bf16 ? 2.0 * out_rows * a.c_out : 0.0);
   const double flops = 2.0 * (double)a.n_rules * a.c_in * a.c_out;
   if (a.bf16) {
     w16.alloc(wn, s);
@@ -404,21 +429,27 @@ int scn_input_layer_build(scn_meta *h, const int64_t size[3], const int64_t *coo
 
 int scn_input_layer_fwd(scn_meta *h, const float *feats, int C, float *out, void *stream) {
   SCN_TRY
+  const double n0 = h->m.levels.empty() ? 0.0 : (double)h->m.levels[0]->n;
+  ProfScope ps(PK_IO, 4.0 * C * ((double)h->m.n_points + n0) + 4.0 * (double)h->m.n_points + 4.0 * n0, 0.0, note_stream(stream));
   input_layer_fwd(&h->m, feats, C, out, note_stream(stream));
   SCN_CATCH
 }
 int scn_input_layer_bwd(scn_meta *h, const float *d_out, int C, float *d_feats, void *stream) {
   SCN_TRY
+  ProfScope ps(PK_IO, 8.0 * C * (double)h->m.n_points + 4.0 * (double)h->m.n_points, 0.0, note_stream(stream));
   input_layer_bwd(&h->m, d_out, C, d_feats, note_stream(stream));
   SCN_CATCH
 }
 int scn_output_layer_fwd(scn_meta *h, const float *in, int C, float *out, void *stream) {
   SCN_TRY
+  ProfScope ps(PK_IO, 8.0 * C * (double)h->m.n_points + 4.0 * (double)h->m.n_points, 0.0, note_stream(stream));
   output_layer_fwd(&h->m, in, C, out, note_stream(stream));
   SCN_CATCH
 }
 int scn_output_layer_bwd(scn_meta *h, const float *d_out, int C, float *d_in, void *stream) {
   SCN_TRY
+  const double n0 = h->m.levels.empty() ? 0.0 : (double)h->m.levels[0]->n;
+  ProfScope ps(PK_IO, 4.0 * C * ((double)h->m.n_points + n0) + 4.0 * (double)h->m.n_points + 4.0 * n0, 0.0, note_stream(stream));
   output_layer_bwd(&h->m, d_out, C, d_in, note_stream(stream));
   SCN_CATCH
 }
@@ -570,7 +601,8 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   // for this product K = c_out and N = c_in, so the caller's [27][c_in][c_out] array reads as [V][N][K]
   const bool dgrad16 = d_in && bf16_conv_shape(c_out, c_in, precision), wgrad16 = bf16_wgrad_shape(c_in, c_out, precision);
   Bf16Copy g16, x16;
-  const uint16_t *pg = (dgrad16 || wgrad16) ? g16.make(d_out, (long long)L->n * c_out, s) : nullptr;
+  const long long ld_g = take_grad_ld(&h->m, c_out, (!d_in || dgrad16) && wgrad16, d_bias);
+  const uint16_t *pg = (dgrad16 || wgrad16) ? g16.make_rows(d_out, ld_g, (long long)L->n, c_out, s) : nullptr;
   const uint16_t *px = take_bf16_hint(&h->m, in, (long long)L->n * c_in, s);
   if (!wgrad16) px = nullptr;
   else if (!px) px = x16.make(in, (long long)L->n * c_in, s);
@@ -622,12 +654,18 @@ int scn_conv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   check_channels(c_in, c_out);
   Level *F = need_level(&h->m, in_size, "Convolution");
   Level *C = ensure_coarse_level(&h->m, F, out_size, s);
+  // one bf16 copy of d_out serves both the dgrad (gathered operand) and the weight gradient
+  const bool dgrad16 = bf16_conv_shape(c_out, c_in, precision), wgrad16 = bf16_wgrad_shape(c_in, c_out, precision);
+  const long long ld_g = take_grad_ld(&h->m, c_out, dgrad16 && wgrad16, d_bias);
+  Bf16Copy g16;
+  const uint16_t *pg = (dgrad16 || wgrad16) ? g16.make_rows(d_out, ld_g, (long long)C->n, c_out, s) : nullptr;
   // dgrad: d_in[child[k][p]] = d_out[p] * W[k]^T  (scatter; each fine row has one parent)
-  run_up(F, C, d_out, weight, false, d_in, c_out, c_in, precision, s, nullptr, &h->m);
+  run_up(F, C, d_out, weight, false, d_in, c_out, c_in, precision, s, dgrad16 ? pg : nullptr, &h->m);
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
   w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = F->n; w.g_rows = F->n; w.s_rows = C->n;
-  run_wgrad(w, F->child_pairs, precision, s, take_bf16_hint(&h->m, in, (long long)F->n * c_in, s));
+  run_wgrad(w, F->child_pairs, precision, s, take_bf16_hint(&h->m, in, (long long)F->n * c_in, s), wgrad16 ? pg : nullptr);
+  g16.release(s);
   if (d_bias) bias_grad(d_out, d_bias, C->n, c_out, s);
   SCN_CATCH
 }
@@ -664,15 +702,20 @@ int scn_deconv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
   ConvArgs a;
   a.in = d_out; a.out = d_in;
   a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_out; a.c_out = c_in; a.n_rules = F->n; a.in_rows = F->n;
+  const bool dgrad16 = bf16_conv_shape(c_out, c_in, precision), wgrad16 = bf16_wgrad_shape(c_out, c_in, precision);
+  const long long ld_g = take_grad_ld(&h->m, c_out, dgrad16 && wgrad16, d_bias);
+  Bf16Copy g16;
+  const uint16_t *pg = (dgrad16 || wgrad16) ? g16.make_rows(d_out, ld_g, (long long)F->n, c_out, s) : nullptr;
   BnbScratch scr;
   apply_bnb_hint(&h->m, a, precision, scr, s);
-  run_conv(a, weight, false, precision, s);
+  run_conv(a, weight, false, precision, s, dgrad16 ? pg : nullptr);
   scr.release(s);
   // dW[k] = sum_p in[p]^T d_out[child[k][p]]
   WgradArgs w;
   w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = F->child.p; w.tbl_stride = C->n_pad; w.n_rows = C->n; w.V = 8;
   w.c_a = c_in; w.c_b = c_out; w.table_on_a = false; w.n_rules = F->n; w.g_rows = F->n; w.s_rows = C->n;
-  run_wgrad(w, F->child_pairs, precision, s, take_bf16_hint(&h->m, in, (long long)C->n * c_in, s));
+  run_wgrad(w, F->child_pairs, precision, s, take_bf16_hint(&h->m, in, (long long)C->n * c_in, s), wgrad16 ? pg : nullptr);
+  g16.release(s);
   if (d_bias) bias_grad(d_out, d_bias, F->n, c_out, s);
   SCN_CATCH
 }
@@ -703,11 +746,19 @@ int scn_bn_bwd_fusable(int c_in, int c_out, int precision) {
 }
 
 int scn_bn_bwd_apply(const float *in, const float *d_masked, const double *acc, const float *save_mean, const float *save_invstd,
-                     const float *gamma, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta, int64_t n, int C,
-                     void *stream) {
+                     const float *gamma, const float *d_in_add, int64_t ld_add, float *d_in, float *d_gamma, float *d_beta,
+                     int64_t n, int C, void *stream) {
   SCN_TRY
   ProfScope ps(PK_BN, (d_in_add ? 4.0 : 3.0) * 4.0 * (double)n * C, 0.0, note_stream(stream));
-  bn_bwd_apply(in, d_masked, acc, save_mean, save_invstd, gamma, d_in_add, d_in, d_gamma, d_beta, n, C, note_stream(stream));
+  bn_bwd_apply(in, d_masked, acc, save_mean, save_invstd, gamma, d_in_add, ld_add, d_in, d_gamma, d_beta, n, C,
+               note_stream(stream));
+  SCN_CATCH
+}
+
+int scn_grad_stride(scn_meta *h, int64_t ld) {
+  SCN_TRY
+  SCN_CHECK(h && ld >= 0, "scn_grad_stride: bad argument");
+  h->m.next_grad_ld = ld;
   SCN_CATCH
 }
 

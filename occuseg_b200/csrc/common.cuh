@@ -172,6 +172,7 @@ struct Meta {
   void *hint_bf16 = nullptr;
   int hint_ready = 0;
   int next_dilation = 1;     // scn_subm_dilation(): dilation of the next submanifold entry (one use)
+  long long next_grad_ld = 0;  // scn_grad_stride(): row stride (floats) of d_out of the next backward entry (one use; 0 = dense)
   // scn_bn_bwd_fusion(): the BatchNorm whose backward the next *_bwd entry folds into its dgrad epilogue (one use)
   struct BnBwdHint {
     const float *x = nullptr, *mean = nullptr, *invstd = nullptr, *gamma = nullptr, *beta = nullptr;
@@ -250,6 +251,8 @@ void conv_tma(const ConvArgs &a, cudaStream_t s);
 void transpose_weight(const float *src, float *dst, int V, int c_in, int c_out, cudaStream_t s);
 // bf16 operand copies (round to nearest even): dst[i] = bf16(src[i]); n must be even
 void cast_bf16(const float *src, uint16_t *dst, long long n, cudaStream_t s);
+// the same from a row-strided source (rows `ld` floats apart) into a dense copy
+void cast_bf16_rows(const float *src, long long ld, long long rows, int cols, uint16_t *dst, cudaStream_t s);
 
 // dW[k] = sum_r A[ia(k,r),:]^T * B[ib(k,r),:]    A: [*,c_a], B: [*,c_b], dW: [V][c_a][c_b] (zeroed here)
 //   table_on_a:  ia = tbl[k][r], ib = r      (submanifold / strided conv: A = input, B = d_out)
@@ -300,7 +303,7 @@ void bn_mask_coeffs(const float *save_mean, const float *save_invstd, const floa
 // second half of bn_bwd when a convolution epilogue already produced the masked gradient d' and acc = (sum d', sum d'*x):
 // d_in = (d' - mean(d') - (x - mean) * k) * invstd * gamma (+ d_in_add); d_gamma, d_beta.  d_in may alias d_masked.
 void bn_bwd_apply(const float *in, const float *d_masked, const double *acc, const float *save_mean, const float *save_invstd,
-                  const float *gamma, const float *d_in_add, float *d_in, float *d_gamma, float *d_beta, long long n, int C,
-                  cudaStream_t s);
+                  const float *gamma, const float *d_in_add, long long ld_add, float *d_in, float *d_gamma, float *d_beta,
+                  long long n, int C, cudaStream_t s);
 
 }  // namespace scn

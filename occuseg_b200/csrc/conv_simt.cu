@@ -279,6 +279,38 @@ __global__ void k_cast_bf16(const float *__restrict__ src, uint16_t *__restrict_
   }
 }
 
+// rows of `cols` floats `ld` floats apart -> dense bf16 [rows, cols]  (cols % 8 == 0)
+__global__ void k_cast_bf16_rows(const float *__restrict__ src, long long ld, int cols8, long long n8,
+                                 uint16_t *__restrict__ dst) {
+  auto cvt2 = [](float lo, float hi) -> uint32_t {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  };
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols8;
+    const int c = (int)(i - r * cols8);
+    const float4 *p = reinterpret_cast<const float4 *>(src + r * ld) + 2 * c;
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    uint4 o;
+    o.x = cvt2(a.x, a.y); o.y = cvt2(a.z, a.w); o.z = cvt2(b.x, b.y); o.w = cvt2(b.z, b.w);
+    reinterpret_cast<uint4 *>(dst)[i] = o;
+  }
+}
+
+void cast_bf16_rows(const float *src, long long ld, long long rows, int cols, uint16_t *dst, cudaStream_t s) {
+  if (ld == cols || ld == 0) { cast_bf16(src, dst, rows * cols, s); return; }
+  if (rows == 0) return;
+  SCN_CHECK(cols % 8 == 0 && ld % 4 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0,
+            "cast_bf16_rows: strided rows need cols % 8 == 0 and 16-byte aligned rows");
+  const long long n8 = rows * (cols / 8);
+  long long g = (n8 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (g > cap) g = cap;
+  k_cast_bf16_rows<<<(int)g, 256, 0, s>>>(src, ld, cols / 8, n8, dst);
+  SCN_LAUNCH_CHECK();
+}
+
 void cast_bf16(const float *src, uint16_t *dst, long long n, cudaStream_t s) {
   if (n == 0) return;
   SCN_CHECK((uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0, "cast_bf16: unaligned buffers");

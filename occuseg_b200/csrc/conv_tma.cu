@@ -239,6 +239,13 @@ __device__ __forceinline__ void tmem_zero32(uint32_t taddr) {
       "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z)
       : "memory");
 }
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void red_add_v4(float *dst, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -264,8 +271,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 // disable-output-lane mask; taps with no row in the group are passed as empty items.
 // =====================================================================================================
 // warp 0: TMEM + MMA issuer; warps 1 .. nprod*ni: producers (item owner = (warp-1)/ni, share of the item's copies =
-// (warp-1)%ni); the last 4 warps: epilogue (TMEM quarter = warp & 3)
-constexpr int CONV_MAX_THREADS = 32 + 16 * 32 + 128;
+// (warp-1)%ni); the last 8 warps: epilogue, two per TMEM quarter (quarter = warp & 3), alternating 16-column chunks
+constexpr int CONV_MAX_THREADS = 32 + 16 * 32 + 256;
+constexpr int EPI_WARPS = 8;
 constexpr int MAX_MT = 2;
 
 struct ConvParams {
@@ -307,14 +315,14 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (base - raw);
   uint4 *s_masks = reinterpret_cast<uint4 *>(smem + p.stages * p.stage_bytes);        // [stages][MAX_MT] present-row bits
-  int4 *s_rows = reinterpret_cast<int4 *>(s_masks + 8 * MAX_MT);                       // [16 producer warps][MT][32] rows to fetch
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_rows + 16 * p.MT * 32);
+  int4 *s_rows = reinterpret_cast<int4 *>(s_masks + 8 * MAX_MT);                       // [producer warps][MT*32/ni] gather groups each warp issues
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_rows + p.nprod * p.MT * 32);
   const uint32_t full_bar = smem_u32(bars);
   const uint32_t empty_bar = full_bar + 8 * p.stages;
   const uint32_t accf_bar = empty_bar + 8 * p.stages;       // [2] accumulator buffer complete
   const uint32_t acce_bar = accf_bar + 16;                  // [2] accumulator buffer drained and zeroed
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 4);
-  float4 *s_tile = reinterpret_cast<float4 *>(s_tmem + 4);                              // [4 epilogue warps][32 rows][4] transpose tiles (8 KB)
+  float4 *s_tile = reinterpret_cast<float4 *>(s_tmem + 4);                              // [8 epilogue warps][32 rows][4] transpose tiles (16 KB)
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler
@@ -342,7 +350,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf_bar + 8 * b, 1);
-      mbar_init(acce_bar + 8 * b, 4);
+      mbar_init(acce_bar + 8 * b, EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -416,9 +424,9 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
     // enough (tools/ubench_pipe.cu); share 0 also posts the byte count, the masks and the weight tile.
     const int pw = (warp - 1) / p.ni, part = (warp - 1) % p.ni;
     {
-      int4 *my_rows = s_rows + (warp - 1) * p.MT * 32;
       const int chunks = p.MT * 4 / p.ni;            // 8-group chunks of this share
       const int chunk0 = part * chunks;
+      int4 *my_rows = s_rows + (warp - 1) * chunks * 8 - chunk0 * 8;     // indexed by the item's gather-group number; only this share's groups are stored
       // share 0 needs every row tile of the item (it publishes the masks and the byte count); the others only the
       // row tile(s) their copies come from
       const int m_lo = part == 0 ? 0 : chunk0 >> 2, m_hi = part == 0 ? p.MT - 1 : (chunk0 + chunks - 1) >> 2;
@@ -515,7 +523,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
             t.y = t.y >= 0 ? t.y : rep;
             t.z = t.z >= 0 ? t.z : rep;
             t.w = t.w >= 0 ? t.w : rep;
-            my_rows[m * 32 + lane] = t;
+            if (m * 4 + (lane >> 3) >= chunk0 && m * 4 + (lane >> 3) < chunk0 + chunks) my_rows[m * 32 + lane] = t;
             any |= gm[m];
           }
         }
@@ -592,8 +600,10 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
   } else {
     // =========================== epilogue warps ===========================
     const int quarter = warp & 3;                     // TMEM lanes 32*quarter .. +31 belong to this warp
+    const int half = (warp - 1 - p.nprod * p.ni) >> 2; // two warps per quarter: this one takes the 16-column chunks c0/16 % 2 == half
     const uint32_t tq = tmem + ((uint32_t)(quarter * 32) << 16);
-    for (int c = 0; c < 2 * acc_cols; c += 32) tmem_zero32(tq + c);
+    const float *aux = p.residual ? p.residual : p.bnb_x;   // the per-row fp32 operand of the epilogue (never both)
+    for (int c = 32 * half; c < 2 * acc_cols; c += 64) tmem_zero32(tq + c);
     tmem_wait_st();
     tc_fence_before();
     __syncwarp();
@@ -605,6 +615,24 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
     TRC(long long e_wait = 0; const long long e_begin = clock64();)
     for (int tg = blockIdx.x; tg < p.n_groups; tg += G, ++gi) {
       const int buf = gi & 1;
+      // rows of this group (lane = row), resolved BEFORE the wait so that the lines of the per-row operand of the epilogue
+      // (residual or BatchNorm input: fp32 rows that nobody has touched recently) can be pulled into L2 while the
+      // accumulators are still being computed: the dependent loads below then cost an L2 hit, not an HBM round trip
+      int r_m[MAX_MT];
+#pragma unroll
+      for (int m = 0; m < MAX_MT; ++m) {
+        int r = (tg * p.MT + m) * TM + quarter * 32 + lane;
+        bool live = m < p.MT && r < p.n_rows;
+        if (live && p.out_rows) {         // scattered result rows (each written exactly once)
+          r = __ldg(&p.out_rows[r]);
+          live = r >= 0 && r < p.out_limit;
+        }
+        r_m[m] = live ? r : -1;
+        if (aux && live && half == 0) {
+          const char *line = reinterpret_cast<const char *>(aux + (long long)r * p.c_out + n0);
+          for (int b = 0; b < p.TN * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(line + b));
+        }
+      }
       TRC(const long long ew = clock64();)
       mbar_wait_warp(accf_bar + 8 * buf, (uint32_t)(gi >> 1) & 1u, lane);
       TRC(e_wait += clock64() - ew;)
@@ -617,21 +645,10 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
       // and the result stores are coalesced.  The column statistics fall out of this layout for free: a lane keeps the
       // same 4 columns for all its rows, so it sums them in registers and only the 8 lanes that share a column group
       // are folded with shuffles, once per chunk.
-      float4 *my_t = s_tile + quarter * 128;                 // [32 rows][4 chunks of 16 B], chunk index XOR-swizzled by row
+      float4 *my_t = s_tile + (half * 4 + quarter) * 128;    // [32 rows][4 chunks of 16 B], chunk index XOR-swizzled by row
       const int cj = lane & 3, rg = lane >> 2;                // after the transpose: this lane's column chunk and row slot
-      int r_m[MAX_MT];
-#pragma unroll
-      for (int m = 0; m < MAX_MT; ++m) {
-        int r = (tg * p.MT + m) * TM + quarter * 32 + lane;
-        bool live = m < p.MT && r < p.n_rows;
-        if (live && p.out_rows) {         // scattered result rows (each written exactly once)
-          r = __ldg(&p.out_rows[r]);
-          live = r >= 0 && r < p.out_limit;
-        }
-        r_m[m] = live ? r : -1;
-      }
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.TN; c0 += 16) {
+      for (int c0 = 16 * half; c0 < p.TN; c0 += 32) {
         const int col = n0 + c0 + 4 * cj;                     // first of this lane's 4 columns
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc = bias4, sh = bias4, wv = bias4, bv = bias4;
         if (p.bias) bias4 = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
@@ -647,6 +664,15 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
 #pragma unroll
         for (int m = 0; m < MAX_MT; ++m) {
           if (m >= p.MT) break;
+          // this lane's 4 rows of the tile and their per-row operand: all four loads are in flight before anything waits
+          int r4[4];
+          float4 a4[4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            r4[it] = __shfl_sync(0xffffffffu, r_m[m], 8 * it + rg);
+            a4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (aux && r4[it] >= 0) a4[it] = __ldg(reinterpret_cast<const float4 *>(aux + (long long)r4[it] * p.c_out + col));
+          }
           float v[16];
           tmem_ld16(tq + buf * acc_cols + m * p.TN + c0, v);
 #pragma unroll
@@ -656,13 +682,13 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int row = 8 * it + rg;
-            const int r = __shfl_sync(0xffffffffu, r_m[m], row);
+            const int r = r4[it];
             float4 o = my_t[row * 4 + (cj ^ ((row >> 1) & 3))];
             if (r >= 0) {
               const long long at = (long long)r * p.c_out + col;
               if (p.bias) { o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w; }
               if (p.residual) {
-                const float4 rv = __ldg(reinterpret_cast<const float4 *>(p.residual + at));
+                const float4 rv = a4[it];
                 o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
               }
               if (p.ep_scale) {
@@ -673,7 +699,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
               float4 sq = make_float4(o.x * o.x, o.y * o.y, o.z * o.z, o.w * o.w);       // second statistic
               if (p.bnb_x) {
                 // BatchNorm backward: mask recomputed from the BatchNorm's input exactly as its forward pass evaluated it
-                const float4 xv = __ldg(reinterpret_cast<const float4 *>(p.bnb_x + at));
+                const float4 xv = a4[it];
                 o.x = fmaf(wv.x, xv.x, bv.x) > 0.f ? o.x : o.x * p.bnb_leak;
                 o.y = fmaf(wv.y, xv.y, bv.y) > 0.f ? o.y : o.y * p.bnb_leak;
                 o.z = fmaf(wv.z, xv.z, bv.z) > 0.f ? o.z : o.z * p.bnb_leak;
@@ -710,13 +736,13 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
           }
         }
       }
-      for (int c = 0; c < acc_cols; c += 32) tmem_zero32(tq + buf * acc_cols + c);
+      for (int c = 16 * half; c < acc_cols; c += 32) tmem_zero16(tq + buf * acc_cols + c);     // exactly the columns this warp read
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce_bar + 8 * buf);
     }
-    TRC(if (p.trace && lane == 0 && quarter == 0) {
+    TRC(if (p.trace && lane == 0 && quarter == 0 && half == 0) {
       atomicAdd(p.trace + 41, (unsigned long long)(clock64() - e_begin));
       atomicAdd(p.trace + 42, (unsigned long long)e_wait);
     })
@@ -956,6 +982,7 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   p.ep_scale = a.ep_scale; p.ep_shift = a.ep_shift; p.ep_leak = a.ep_leak; p.out_bf16 = a.out_bf16;
   p.bnb_x = a.bnb_x; p.bnb_coef = a.bnb_coef; p.bnb_leak = a.bnb_leak;
   SCN_CHECK(!a.bnb_x || a.stats, "conv_tma: the fused BatchNorm backward needs the statistics buffer");
+  SCN_CHECK(!(a.bnb_x && a.residual), "conv_tma: residual and fused BatchNorm backward are mutually exclusive");
   p.stats = a.stats;
   if (a.stats) SCN_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(double) * 2 * (size_t)a.c_out, s));
   p.in = a.in; p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
@@ -976,8 +1003,9 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   if (tiles < mt * sm_count()) mt = 1;                 // small levels: more, smaller groups keep every SM busy
   p.MT = mt;
   p.stage_bytes = p.MT * A_STAGE + p.b_stage;
-  const int fixed = 1024 + 8 * MAX_MT * 16 + 16 * p.MT * 32 * 16 + 8 * (2 * 8 + 4) + 64 + 4 * 2 * 256 * 4;
-  int st = (225 * 1024 - fixed) / p.stage_bytes;
+  // alignment slack + masks + producers' gather groups (4 owner slots x MT x 32 int4) + barriers + transpose tiles of the epilogue warps
+  const int fixed = 1024 + 8 * MAX_MT * 16 + 4 * p.MT * 32 * 16 + 8 * (2 * 8 + 4) + 64 + EPI_WARPS * 2048;
+  int st = (227 * 1024 - fixed) / p.stage_bytes;
   if (st > 8) st = 8;
   SCN_CHECK(st >= 2, "conv_tma: shared memory budget");
   p.stages = st;
@@ -1012,7 +1040,7 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
     SCN_CUDA(cudaMemset(p.trace, 0, 8 * 64));
   }
 #endif
-  k_conv_tma<<<grid, 32 + 32 * p.nprod * p.ni + 128, smem, s>>>(mx, mw, p);
+  k_conv_tma<<<grid, 32 + 32 * p.nprod * p.ni + 32 * EPI_WARPS, smem, s>>>(mx, mw, p);
   SCN_LAUNCH_CHECK();
   if (p.trace) {
     unsigned long long h[64];

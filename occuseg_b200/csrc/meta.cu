@@ -274,6 +274,8 @@ void build_pair_list(PairList &out, const int *tbl, int V, int stride, long long
   if (out.item_off.p) return;
   out.unit = unit;
   const long long n_flat = (long long)V * stride;
+  // table read twice (rank scan + scatter, 4 B each) + the ranks (4 B written, 4 B read) + 8 B per rule written
+  ProfScope ps(PK_RULEBOOK, 16.0 * (double)n_flat + 8.0 * (double)n_rules, 0.0, s);
   SCN_CHECK(n_flat > 0 && n_flat < (1ll << 31), "rule table too large for 32-bit ranks");
   out.n_items_ub = (n_rules + (long long)(unit - 1) * V) / unit + 1;
   out.gi.alloc((size_t)out.n_items_ub * unit, s);
@@ -321,6 +323,8 @@ void build_input_level(Meta *m, const int64_t size[3], const int64_t *coords, bo
   m->batch = batch;
   m->mode = mode;
   m->n_points = P;
+  // coordinates read (32 B per point), keys sorted with the point index (12 B in, 12 B out), row of every point + grouped list (8 B)
+  ProfScope ps(PK_RULEBOOK, (32.0 + 24 + 8) * (double)P, 0.0, s);
 
   DevBuf<int64_t> dcoords;
   const int64_t *dc = coords;
@@ -430,6 +434,8 @@ __global__ void k_tile_masks(const unsigned long long *__restrict__ row_key, con
 void ensure_sorted_table(Level *L, cudaStream_t s) {
   if (L->tile_mask.p || !L->row_key.p || L->n == 0) return;
   const int n = L->n;
+  // pattern keys read + sorted (8+4 B in, 4 B out), table gathered into tile order (27 x 4 B read + written), tile masks
+  ProfScope ps(PK_RULEBOOK, (tile_sort_enabled() ? 16.0 + 2 * 27.0 * 4 + 8 : 8.0) * (double)n, 0.0, s);
   L->tile_mask.alloc((size_t)(L->n_pad / 128), s);
   if (!tile_sort_enabled()) {          // natural order: only the per-tile tap masks
     k_tile_masks<<<L->n_pad / 128, 128, 0, s>>>(L->row_key.p, nullptr, n, L->tile_mask.p);
@@ -469,6 +475,8 @@ void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
   (void)m;
   if (L->nbr.p) return;
   Level *K = L->base ? L->base : L;       // the scale whose rows and hash this table is built on
+  // algorithmic bytes: 27 key probes x 8 B + 12 B of coordinates + 27 x 4 B of table per row, + the hash insert
+  ProfScope ps(PK_RULEBOOK, (27.0 * 8 + 12 + 27.0 * 4 + (K->hkeys.p ? 0.0 : 8 + 12)) * (double)L->n, 0.0, s);
   build_hash(K, s);
   L->nbr.alloc((size_t)27 * L->n_pad, s);
   DevBuf<unsigned long long> cnt;
@@ -519,6 +527,8 @@ Level *ensure_coarse_level(Meta *m, Level *F, const int64_t coarse_size[3], cuda
   for (int d = 0; d < 3; ++d)
     SCN_CHECK((coarse_size[d] - 1) * 2 + 2 == F->size[d], "Convolution: only filter size 2 / stride 2 is supported (reference FastDownSampleMode)");
   SCN_CHECK(find_level(m, coarse_size) == nullptr, "Convolution: output scale already exists in this handle");
+  // fine keys read (8 B), coarse keys sorted with their fine row (12 B in, 12 B out), parent + offset written (5 B); child table below
+  ProfScope ps(PK_RULEBOOK, (8.0 + 24 + 5 + 4) * (double)F->n, 0.0, s);
   DevBuf<uint64_t> ckeys;
   DevBuf<int> idx;
   ckeys.alloc(F->n, s);

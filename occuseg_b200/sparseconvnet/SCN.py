@@ -97,6 +97,28 @@ def _cuda_f32(t, name):
     return t.contiguous()
 
 
+def _rows_f32(t, name):
+    """A CUDA float32 matrix whose rows may be a column slice of a wider one (stride(1) == 1): returned as it is with its row
+    stride, anything else is made contiguous.  -> (tensor, ld)"""
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise TypeError(f"{name}: expected a CUDA float32 tensor (there is no CPU path), got {t.device} {t.dtype}")
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) > t.size(1) and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0 \
+            and t.size(1) % 8 == 0:
+        return t, t.stride(0)
+    t = t.contiguous()
+    return t, 0
+
+
+def _grad_operand(m, d_output_features, strided_ok):
+    """d_out of a backward entry; a row-strided slice is registered with scn_grad_stride when the entry can read it in place"""
+    if not strided_ok:
+        return _cuda_f32(d_output_features, "grad")
+    g, ld = _rows_f32(d_output_features, "grad")
+    if ld:
+        _lib.check(_lib.lib().scn_grad_stride(m._handle(), int(ld)))
+    return g
+
+
 def _opt(t):
     """optionalTensor convention of the reference (utils.py:23-24): an empty tensor means 'absent'."""
     return t if (t is not None and t.numel()) else None
@@ -332,7 +354,8 @@ def SubmanifoldConvolutionBN_updateOutput(spatial_size, filter_size, m, input_fe
 
 def SubmanifoldConvolution_backward(spatial_size, filter_size, m, input_features, d_input_features, d_output_features,
                                     weight, d_weight, d_bias, dilated_rate=1, input_bf16=None):
-    x, g, w = _conv_input(m, input_features, input_bf16), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 27)
+    x, w = _conv_input(m, input_features, input_bf16), _check_weight(weight, 27)
+    g = _grad_operand(m, d_output_features, input_bf16 is not None and _opt(d_bias) is None)
     with torch.cuda.device(x.device):
         if d_input_features is not None:      # None: the caller does not need the input gradient (first layer)
             d_input_features.resize_(x.size(0), x.size(1))
@@ -366,7 +389,8 @@ def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, i
 
 def Convolution_backward(in_size, out_size, filter_size, filter_stride, m, input_features, d_input_features,
                          d_output_features, weight, d_weight, d_bias, input_bf16=None):
-    x, g, w = _conv_input(m, input_features, input_bf16), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 8)
+    x, w = _conv_input(m, input_features, input_bf16), _check_weight(weight, 8)
+    g = _grad_operand(m, d_output_features, input_bf16 is not None and _opt(d_bias) is None)
     with torch.cuda.device(x.device):
         d_input_features.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_conv_bwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(g),
@@ -392,7 +416,8 @@ def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m,
 
 def Deconvolution_backward(in_size, out_size, filter_size, filter_stride, m, input_features, d_input_features,
                            d_output_features, weight, d_weight, d_bias, input_bf16=None):
-    x, g, w = _conv_input(m, input_features, input_bf16), _cuda_f32(d_output_features, "grad"), _check_weight(weight, 8)
+    x, w = _conv_input(m, input_features, input_bf16), _check_weight(weight, 8)
+    g = _grad_operand(m, d_output_features, input_bf16 is not None and _opt(d_bias) is None)
     with torch.cuda.device(x.device):
         d_input_features.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_deconv_bwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(g),
@@ -448,12 +473,13 @@ def BatchNormalization_backwardApply(input_features, d_masked, acc, saveMean, sa
                                      d_bias, d_input_add=None):
     """(extension) second half of BatchNormalization_backward after a fused dgrad epilogue (scn_bn_bwd_apply)."""
     x, g = _cuda_f32(input_features, "input"), _cuda_f32(d_masked, "grad")
+    ld_add = 0
     if d_input_add is not None:
-        d_input_add = _cuda_f32(d_input_add, "d_input_add")
+        d_input_add, ld_add = _rows_f32(d_input_add, "d_input_add")      # may be a column slice of a joined gradient
     with torch.cuda.device(x.device):
         d_input_features.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_bn_bwd_apply(_ptr(x), _ptr(g), _ptr(acc), _ptr(saveMean), _ptr(saveInvStd), _ptr(_opt(weight)),
-                                               _ptr(d_input_add), _ptr(d_input_features), _ptr(_opt(d_weight)),
+                                               _ptr(d_input_add), int(ld_add), _ptr(d_input_features), _ptr(_opt(d_weight)),
                                                _ptr(_opt(d_bias)), x.size(0), x.size(1), _stream()))
 
 

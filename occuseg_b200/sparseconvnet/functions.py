@@ -179,7 +179,7 @@ class BatchNormConvFunction(Function):
         (x, bn_weight, bn_bias, save_mean, save_invstd, y16, conv_weight, conv_bias, in_size, out_size, filter_size,
          filter_stride) = ctx.saved_tensors
         m, kind = ctx.scn_meta, ctx.kind
-        g = grad_out.contiguous()
+        g = grad_out          # may be a column slice of a JoinTable's gradient: read in place (SCN._grad_operand)
         acc = torch.empty((2, x.size(1)), dtype=torch.float64, device=x.device)      # zeroed by the convolution entry
         d_masked = g.new_empty(0)
         gw, gb = torch.zeros_like(conv_weight), torch.zeros_like(conv_bias)
@@ -191,7 +191,7 @@ class BatchNormConvFunction(Function):
             bwd(in_size, out_size, filter_size, filter_stride, m, None, d_masked, g, conv_weight, gw, gb, input_bf16=y16)
         gx = g.new_empty(0)
         g_gamma, g_beta = torch.zeros_like(bn_weight), torch.zeros_like(bn_bias)
-        add = grad_alias.contiguous() if grad_alias is not None and grad_alias.numel() == x.numel() else None
+        add = grad_alias if grad_alias is not None and grad_alias.numel() == x.numel() else None
         SCN.BatchNormalization_backwardApply(x, d_masked, acc, save_mean, save_invstd, bn_weight, gx, g_gamma, g_beta, add)
         del ctx.scn_meta
         return (gx, optionalTensorReturn(g_gamma), optionalTensorReturn(g_beta), None, None, None, None, None, gw,
@@ -210,7 +210,8 @@ class NetworkInNetworkFunction(Function):
     @staticmethod
     def backward(ctx, grad_out):
         x, weight, bias = ctx.saved_tensors
-        grad_out = grad_out.contiguous()
+        if grad_out.stride(-1) != 1:
+            grad_out = grad_out.contiguous()       # row-strided slices are fine for the GEMMs as they are
         gx, gw = grad_out.new_empty(0), torch.zeros_like(weight)
         gb = torch.zeros_like(bias) if bias is not None and bias.numel() else None
         SCN.NetworkInNetwork_updateGradInput(gx, grad_out, weight)
