@@ -80,6 +80,12 @@ int scn_output_layer_fwd(scn_meta *m, const float *in, int channels, float *out_
 /* OutputLayer_updateGradInput (CUDA/IOLayers.cpp:131-154): d_in[N,C] = sum over the voxel's points of d_out[p] */
 int scn_output_layer_bwd(scn_meta *m, const float *d_out_points, int channels, float *d_in, void *stream);
 int64_t scn_n_points(scn_meta *m);
+/* The step before the InputLayer, on the device: float point cloud xyz [P,3] (already augmented and scaled to voxel units)
+ * -> coords int64 [P,4] = (trunc(x - offset), batch_index), the list scn_input_layer_build takes with coords_on_device = 1;
+ * keep[P] (may be NULL) = 1 where the shifted point lies inside [0, full_scale)^3.  Replaces the host-side shift / crop /
+ * LongTensor conversion of examples/ScanNet/datasets/scannet.py:133-137,160,210 and sparseconvnet/ioLayers.py:56. */
+int scn_float_coords(const float *xyz, int64_t n_points, const float offset[3], int batch_index, float full_scale,
+                     int64_t *coords, uint8_t *keep, void *stream);
 
 /* ---- scale queries: Metadata::getNActive / getSpatialLocations (Metadata.cpp:89-92, :724-748) -- */
 int64_t scn_nactive(scn_meta *m, const int64_t spatial_size[3]); /* -1 if the scale does not exist */

@@ -30,6 +30,7 @@ PROTOTYPES = {
     "scn_input_layer_bwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "scn_output_layer_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "scn_output_layer_bwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "scn_float_coords": (C.c_int, [_vp, C.c_int64, C.POINTER(C.c_float), C.c_int, C.c_float, _vp, _vp, _vp]),
     "scn_n_points": (C.c_int64, [_vp]),
     "scn_nactive": (C.c_int64, [_vp, _i64p]),
     "scn_spatial_locations": (C.c_int, [_vp, _i64p, _vp]),

@@ -453,6 +453,15 @@ int scn_output_layer_bwd(scn_meta *h, const float *d_out, int C, float *d_in, vo
   output_layer_bwd(&h->m, d_out, C, d_in, note_stream(stream));
   SCN_CATCH
 }
+int scn_float_coords(const float *xyz, int64_t n_points, const float offset[3], int batch_index, float full_scale,
+                     int64_t *coords, uint8_t *keep, void *stream) {
+  SCN_TRY
+  SCN_CHECK(xyz && offset && coords, "scn_float_coords: null argument");
+  ProfScope ps(PK_IO, (12.0 + 32 + 1) * (double)n_points, 0.0, note_stream(stream));
+  float_coords(xyz, n_points, offset, batch_index, full_scale, (long long *)coords, keep, note_stream(stream));
+  SCN_CATCH
+}
+
 int64_t scn_n_points(scn_meta *h) { return h ? h->m.n_points : -1; }
 
 int64_t scn_nactive(scn_meta *h, const int64_t size[3]) {

@@ -200,6 +200,8 @@ void input_layer_fwd(Meta *m, const float *feats, int C, float *out, cudaStream_
 void input_layer_bwd(Meta *m, const float *d_out, int C, float *d_feats, cudaStream_t s);
 void output_layer_fwd(Meta *m, const float *in, int C, float *out, cudaStream_t s);
 void output_layer_bwd(Meta *m, const float *d_out, int C, float *d_in, cudaStream_t s);
+void float_coords(const float *xyz, long long n, const float offset[3], int batch_index, float full_scale, long long *coords,
+                  uint8_t *keep, cudaStream_t s);
 
 // conv_simt.cu / conv_small.cu / conv_tma.cu ---------------------------------------------------------------------------
 // Generic "table convolution".  tbl is [V][stride] (row index or -1).

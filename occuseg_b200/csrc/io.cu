@@ -97,4 +97,31 @@ void output_layer_bwd(Meta *m, const float *d_out, int C, float *d_in, cudaStrea
   rows_from_points(m, d_out, d_in, C, false, s);
 }
 
+// Float point cloud -> the InputLayer's integer coordinate list, on the device.  The reference does this on the host:
+// the data loader shifts the augmented cloud so that it starts at (10,10,10) plus a random sub-voxel offset, drops points
+// outside [0, full_scale) (examples/ScanNet/datasets/scannet.py:133-137,160), appends the sample index as 4th column
+// (:210) and InputLayer truncates the float list with .type(torch.LongTensor) (sparseconvnet/ioLayers.py:56).
+__global__ void k_float_coords(const float *__restrict__ xyz, long long n, float ox, float oy, float oz, int batch_index,
+                               float full_scale, long long *__restrict__ coords, uint8_t *__restrict__ keep) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = xyz[3 * i] - ox, y = xyz[3 * i + 1] - oy, z = xyz[3 * i + 2] - oz;
+  const float lo = fminf(x, fminf(y, z)), hi = fmaxf(x, fmaxf(y, z));
+  const bool ok = lo >= 0.f && hi < full_scale;            // idxs = (a.min(1) >= 0) * (a.max(1) < full_scale)
+  if (keep) keep[i] = ok ? 1 : 0;
+  longlong2 a, b;
+  a.x = (long long)x; a.y = (long long)y;                  // truncation toward zero, as LongTensor conversion does
+  b.x = (long long)z; b.y = batch_index;
+  reinterpret_cast<longlong2 *>(coords)[2 * i] = a;
+  reinterpret_cast<longlong2 *>(coords)[2 * i + 1] = b;
+}
+
+void float_coords(const float *xyz, long long n, const float offset[3], int batch_index, float full_scale, long long *coords,
+                  uint8_t *keep, cudaStream_t s) {
+  if (n == 0) return;
+  k_float_coords<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(xyz, n, offset[0], offset[1], offset[2], batch_index, full_scale,
+                                                             coords, keep);
+  SCN_LAUNCH_CHECK();
+}
+
 }  // namespace scn

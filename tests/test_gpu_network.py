@@ -400,3 +400,48 @@ def test_dilated_submanifold_convolution(rate, precision, c):
     tol = FP32_TOL if precision == "fp32" else TC_TOL
     assert rel_err(y.detach().cpu().numpy(), y0) < tol and rel_err(xin.grad.cpu().numpy(), gx0) < tol
     assert rel_err(conv.weight.grad.cpu().numpy(), gw0) < tol
+
+
+# ------------------------------------------------------------------------------------------- device-side data path
+def test_device_side_augmentation_and_coordinates():
+    """occuseg_b200.data: the elastic distortion against scipy's convolve + RegularGridInterpolator exactly as
+    datasets/scannet.py:49-70 composes them (same noise grids), and scn_float_coords against the host shift / crop / LongTensor
+    conversion; the device coordinate list goes straight into scn.InputLayer and builds the same voxels."""
+    import scipy.ndimage
+    import scipy.interpolate
+    from occuseg_b200 import data
+    rng = np.random.default_rng(5)
+    pts = (rng.random((20000, 3)) * np.array([300.0, 220.0, 120.0]) - np.array([150.0, 110.0, 60.0])).astype(np.float32)
+    gran, mag = 6, 23.0
+    bb = np.abs(pts).max(0).astype(np.int32) // gran + 3
+    noise = [rng.standard_normal(tuple(bb)).astype("float32") for _ in range(3)]
+    b0, b1, b2 = (np.ones(s, "float32") / 3 for s in ((3, 1, 1), (1, 3, 1), (1, 1, 3)))
+    ref = noise
+    for _ in range(2):
+        for b in (b0, b1, b2):
+            ref = [scipy.ndimage.convolve(n, b, mode="constant", cval=0) for n in ref]
+    ax = [np.linspace(-(b - 1) * gran, (b - 1) * gran, b) for b in bb]
+    interp = [scipy.interpolate.RegularGridInterpolator(ax, n, bounds_error=0, fill_value=0) for n in ref]
+    want = pts + np.hstack([i(pts)[:, None] for i in interp]) * mag
+    got = data.elastic(cu(pts), gran, mag, noise=[torch.from_numpy(n) for n in noise]).cpu().numpy()
+    assert np.abs(got - want).max() < 2e-3 * mag
+    # shift / crop / truncate
+    a = got.astype(np.float32)
+    offr = np.array([0.25, 0.5, 0.75], np.float32)
+    coords, keep = data.to_input_coords(cu(a), 3, 256, offset_rand=offr)
+    off = a.min(0) - 10 + offr
+    sh = a - off
+    keep0 = (sh.min(1) >= 0) & (sh.max(1) < 256)
+    frac = np.abs(sh - np.round(sh)).min(1)
+    safe = frac > 1e-3                                  # away from integer / crop boundaries the two must agree exactly
+    assert np.array_equal(keep.cpu().numpy()[safe], keep0[safe])
+    both = keep0 & keep.cpu().numpy() & safe
+    got_c = np.zeros((len(a), 4), np.int64)
+    got_c[keep.cpu().numpy()] = coords.cpu().numpy()
+    assert np.array_equal(got_c[both, :3], sh[both].astype(np.int64)) and (got_c[keep.cpu().numpy(), 3] == 3).all()
+    # device-resident coordinates feed the InputLayer directly
+    c0 = coords.clone()
+    c0[:, 3] = 0
+    t = scn.InputLayer(3, SIZE, mode=4)([c0, torch.ones(len(c0), 3, device="cuda"), None, 1])
+    vox = rb.voxelize(c0.cpu().numpy(), 1)
+    assert np.array_equal(t.metadata.getSpatialLocations(lt(SIZE)).numpy(), vox["locs"])
