@@ -154,7 +154,7 @@ def run_ours(args):
     import occuseg_b200.sparseconvnet as scn
     from occuseg_b200 import _lib, scenes
     from occuseg_b200.backbone import SparseBackbone
-    from occuseg_b200.ddp import BucketedGradAllReduce
+    from occuseg_b200.ddp import BucketedGradAllReduce, FlatGradAllReduce
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -165,8 +165,15 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        if os.environ.get("SCN_BENCH_BACKEND") == "gloo":      # debugging aid: isolate NCCL's effect on the device-timed step
+            dist.init_process_group("gloo")
+        elif os.environ.get("SCN_BENCH_LAZY_NCCL"):
+            dist.init_process_group("nccl")
+        else:
+            dist.init_process_group("nccl", device_id=dev)
     scn.set_precision(args.precision)
+    if os.environ.get("SCN_BENCH_VERBOSE"):
+        sys.stderr.write(f"[rank {rank}] cpu affinity after init: {len(os.sched_getaffinity(0))} cpus {sorted(os.sched_getaffinity(0))[:8]}...\n")
 
     torch.manual_seed(1234)                       # identical initial weights on every rank
     net = SparseBackbone(m=args.m, levels=6).to(dev)
@@ -174,10 +181,12 @@ def run_ours(args):
     if inference:
         net.eval()
     opt = None if inference else torch.optim.Adam(net.parameters(), lr=1e-3, fused=True)
-    reducer = BucketedGradAllReduce(net.parameters(), world) if (world > 1 and not inference) else None
+    Reducer = FlatGradAllReduce if os.environ.get("SCN_DDP", "bucketed") == "flat" else BucketedGradAllReduce
+    reducer = Reducer(net.parameters(), world) if (world > 1 and not inference and os.environ.get("SCN_DDP") != "none") else None
 
     # ---- synthetic batch: rank r gets seeds r*scenes .. r*scenes+scenes-1 (weak scaling)
-    seeds = tuple(rank * args.scenes + i for i in range(args.scenes))
+    seed0 = int(os.environ.get("SCN_BENCH_SEED0", "0"))          # debugging aid: run another rank's scenes on one GPU
+    seeds = tuple(seed0 + rank * args.scenes + i for i in range(args.scenes))
     coords_np, feats_np = scenes.make_batch(args.preset, seeds)
     coords_host = torch.from_numpy(coords_np).pin_memory()
     feats_host = torch.from_numpy(feats_np).pin_memory()
@@ -204,13 +213,17 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    host_ms = []
+
     def timed(fn, steps):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             fn()
         e1.record()
+        host_ms.append((time.perf_counter() - t0) * 1e3 / steps)     # host time to ENQUEUE a step (no device wait inside)
         sync_all()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -241,6 +254,10 @@ def run_ours(args):
     ms_prof = timed(lambda: step(coords_dev, feats_dev), args.steps)
     prof = _lib.profile_read()
     _lib.profile(False)
+
+    if os.environ.get("SCN_BENCH_VERBOSE"):      # per-rank view (debugging aid; the JSON line is rank 0's)
+        sys.stderr.write(f"[rank {rank}] ms/step {ms / args.steps:.2f} instrumented {ms_prof / args.steps:.2f} "
+                         + " ".join(f"{k}={v['ms'] / args.steps:.2f}" for k, v in prof.items() if v["launches"]) + "\n")
 
     # ---- timed region 2: end to end from pinned host buffers, loss read back every step.  Every step's inputs are
     # copied host->device inside the timed region; the copy of step i+1 is issued on a copy stream while step i
@@ -360,7 +377,7 @@ def run_ours(args):
         "e2e": {"value": total_voxels * args.steps / (ms_e2e * 1e-3), "unit": "voxels/s",
                 "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "precision_ms": precision_ms,
+        "precision_ms": precision_ms, "host_enqueue_ms_per_step": host_ms[0] if host_ms else None,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

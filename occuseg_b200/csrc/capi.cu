@@ -26,6 +26,9 @@ int sm_count() {
   if (!n) {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev < 0 ? 0 : dev);
     if (n <= 0) n = 148;
+    // SCN_SM_RESERVE: SMs left to other resident kernels (e.g. a communication library's); the persistent kernels size their
+    // grids to the rest, so none of their CTAs has to wait for an SM
+    if (const char *e = getenv("SCN_SM_RESERVE")) n = n - atoi(e) > 8 ? n - atoi(e) : n;
     if (dev >= 0 && dev < MAX_DEVICES) cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
@@ -153,7 +156,8 @@ static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, 
   const float *use = w;
   const int wv = a.n_taps ? a.n_taps : a.V;        // weight taps (the one-tap-per-row form has V = 1 table row, n_taps weights)
   const size_t wn = (size_t)wv * a.c_in * a.c_out;
-  if (want_kn != native_kn) {
+  const bool fused_prep = tcore && a.bf16 && want_kn != native_kn;    // bf16 tiles: transpose + rounding in one kernel
+  if (want_kn != native_kn && !fused_prep) {
     tmp.alloc(wn, s);
     // source rows/cols: native_kn -> [c_in][c_out], else [c_out][c_in]
     if (native_kn) transpose_weight(w, tmp.p, wv, a.c_in, a.c_out, s);
@@ -164,14 +168,15 @@ static void run_conv(ConvArgs a, const float *w, bool native_kn, int precision, 
   // algorithmic work (gather/scatter model): R*Cin*s + N*Cout*4 + 4*R + V*Cin*Cout*s
   // + the per-row fp32 operand an epilogue fusion reads in the same pass (residual shortcut, or the BatchNorm input of a fused
   //   BatchNorm backward): N*Cout*4 -- algorithmic traffic of the fused elementwise layer, which no longer has a pass of its own
-  const double out_rows = (double)(a.scatter || a.out_rows ? a.n_rules : a.n_rows);
+  const double out_rows = (double)(a.scatter || a.item_off ? a.n_rules : a.n_rows);    // one-rule-per-row forms write n_rules rows
   const double bytes = es * (double)a.n_rules * a.c_in + 4.0 * out_rows * a.c_out + 4.0 * (double)a.n_rules +
                        es * (double)wv * a.c_in * a.c_out + ((a.residual || a.bnb_x) ? 4.0 * out_rows * a.c_out : 0.0) +
                        (a.out_bf16 ? 2.0 * out_rows * a.c_out : 0.0);
   const double flops = 2.0 * (double)a.n_rules * a.c_in * a.c_out;
   if (a.bf16) {
     w16.alloc(wn, s);
-    cast_bf16(use, w16.p, (long long)wn, s);
+    if (fused_prep) transpose_weight_bf16(w, w16.p, wv, a.c_in, a.c_out, s);      // native [K][N] -> [N][K] bf16
+    else cast_bf16(use, w16.p, (long long)wn, s);
     if (!in16) in16 = x16.make(a.in, (long long)a.in_rows * a.c_in, s);
   }
   {
@@ -210,10 +215,9 @@ static void apply_bnb_hint(Meta *m, ConvArgs &a, int precision, BnbScratch &scr,
   if (probe.n_rows == 0) probe.n_rows = 1;
   SCN_CHECK(precision != SCN_FP32 && conv_tma_supported(probe) && a.out != nullptr && (uintptr_t)h.x % 16 == 0,
             "fused BatchNorm backward: this layer's dgrad does not run on the tensor-core path (see scn_bn_bwd_fusable)");
-  scr.coef.alloc(2 * (size_t)a.c_out, s);
-  bn_mask_coeffs(h.mean, h.invstd, h.gamma, h.beta, a.c_out, scr.coef.p, s);
+  (void)scr;
   a.bnb_x = h.x;
-  a.bnb_coef = scr.coef.p;
+  a.bnb_mean = h.mean; a.bnb_invstd = h.invstd; a.bnb_gamma = h.gamma; a.bnb_beta = h.beta;
   a.bnb_leak = h.leak;
   a.stats = h.acc;
 }

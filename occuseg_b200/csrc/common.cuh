@@ -222,8 +222,9 @@ struct ConvArgs {
   float ep_leak = 1.f;
   uint16_t *out_bf16 = nullptr;
   // tensor-core kernel only (dgrad products): fused backward of the BatchNorm that produced this product's input operand --
-  // see ConvParams in conv_tma.cu.  bnb_x [n_rows, c_out] fp32, bnb_coef [2][c_out] (w, b); `stats` receives (sum d', sum d'*x)
-  const float *bnb_x = nullptr, *bnb_coef = nullptr;
+  // see ConvParams in conv_tma.cu.  bnb_x [n_rows, c_out] fp32 + the BatchNorm's saved statistics and affine parameters;
+  // `stats` receives (sum d', sum d'*x)
+  const float *bnb_x = nullptr, *bnb_mean = nullptr, *bnb_invstd = nullptr, *bnb_gamma = nullptr, *bnb_beta = nullptr;
   float bnb_leak = 0.f;
   float *out = nullptr;
   const int *tbl = nullptr;
@@ -251,6 +252,8 @@ void conv_tma(const ConvArgs &a, cudaStream_t s);
 
 // weight preparation: dst[k][co][ci] = src[k][ci][co]   (per-tap transpose, used by every dgrad)
 void transpose_weight(const float *src, float *dst, int V, int c_in, int c_out, cudaStream_t s);
+// dst[k][co][ci] = bf16(src[k][ci][co]): transpose and operand rounding in one pass
+void transpose_weight_bf16(const float *src, uint16_t *dst, int V, int c_in, int c_out, cudaStream_t s);
 // bf16 operand copies (round to nearest even): dst[i] = bf16(src[i]); n must be even
 void cast_bf16(const float *src, uint16_t *dst, long long n, cudaStream_t s);
 // the same from a row-strided source (rows `ld` floats apart) into a dense copy

@@ -252,6 +252,33 @@ __global__ void k_transpose_weight(const float *__restrict__ src, float *__restr
   }
 }
 
+// the same with the bf16 rounding of the tensor-core operand folded in: dst[k][co][ci] = bf16(src[k][ci][co])
+__global__ void k_transpose_weight_bf16(const float *__restrict__ src, uint16_t *__restrict__ dst, int c_in, int c_out) {
+  __shared__ float tile[32][33];
+  const float *s = src + (long long)blockIdx.z * c_in * c_out;
+  uint16_t *d = dst + (long long)blockIdx.z * c_in * c_out;
+  int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int ci = ci0 + i, co = co0 + threadIdx.x;
+    tile[i][threadIdx.x] = (ci < c_in && co < c_out) ? s[(long long)ci * c_out + co] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int co = co0 + i, ci = ci0 + threadIdx.x;
+    if (co < c_out && ci < c_in) {
+      uint32_t r;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(0.f), "f"(tile[threadIdx.x][i]));
+      d[(long long)co * c_in + ci] = (uint16_t)(r & 0xFFFFu);
+    }
+  }
+}
+
+void transpose_weight_bf16(const float *src, uint16_t *dst, int V, int c_in, int c_out, cudaStream_t s) {
+  dim3 grid((c_out + 31) / 32, (c_in + 31) / 32, V);
+  k_transpose_weight_bf16<<<grid, dim3(32, 8), 0, s>>>(src, dst, c_in, c_out);
+  SCN_LAUNCH_CHECK();
+}
+
 void transpose_weight(const float *src, float *dst, int V, int c_in, int c_out, cudaStream_t s) {
   dim3 grid((c_out + 31) / 32, (c_in + 31) / 32, V);
   k_transpose_weight<<<grid, dim3(32, 8), 0, s>>>(src, dst, c_in, c_out);

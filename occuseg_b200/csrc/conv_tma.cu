@@ -271,9 +271,12 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 // disable-output-lane mask; taps with no row in the group are passed as empty items.
 // =====================================================================================================
 // warp 0: TMEM + MMA issuer; warps 1 .. nprod*ni: producers (item owner = (warp-1)/ni, share of the item's copies =
-// (warp-1)%ni); the last 8 warps: epilogue, two per TMEM quarter (quarter = warp & 3), alternating 16-column chunks
-constexpr int CONV_MAX_THREADS = 32 + 16 * 32 + 256;
-constexpr int EPI_WARPS = 8;
+// (warp-1)%ni); the last EPI_WARPS warps: epilogue, EPI_WARPS/4 per TMEM quarter (quarter = warp & 3), alternating 16-column chunks
+// EPI_WARPS = 4 (one per TMEM quarter).  8 (two per quarter, alternating chunks) is supported by the code below but measured
+// the same step time within noise, and 800 threads leave only 72 registers per thread
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_SPLIT = EPI_WARPS / 4;
+constexpr int CONV_MAX_THREADS = 32 + 16 * 32 + 32 * EPI_WARPS;
 constexpr int MAX_MT = 2;
 
 struct ConvParams {
@@ -286,10 +289,10 @@ struct ConvParams {
   float ep_leak;
   uint16_t *out_bf16;
   // optional fused BatchNorm BACKWARD of the layer that produced this product's input operand (dgrad products): the result
-  // row r is the gradient w.r.t. that BatchNorm's output; bnb_x = the BatchNorm's input [rows, c_out], bnb_coef = [2][c_out]
-  // (w = invstd*gamma, b = beta - mean*w).  The epilogue applies the activation mask recomputed from x, writes the masked
+  // row r is the gradient w.r.t. that BatchNorm's output; bnb_x = the BatchNorm's input [rows, c_out], bnb_mean / bnb_invstd its
+  // saved statistics, bnb_gamma / bnb_beta its affine parameters (w = invstd*gamma, b = beta - mean*w as its forward evaluated them).  The epilogue applies the activation mask recomputed from x, writes the masked
   // gradient d', and accumulates the column sums of d' and d'*x into `stats` instead of (sum, sum of squares).
-  const float *bnb_x, *bnb_coef;
+  const float *bnb_x, *bnb_mean, *bnb_invstd, *bnb_gamma, *bnb_beta;     // gamma / beta may be NULL (no affine)
   float bnb_leak;
   float *out;
   const int *tbl;
@@ -322,7 +325,8 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
   const uint32_t accf_bar = empty_bar + 8 * p.stages;       // [2] accumulator buffer complete
   const uint32_t acce_bar = accf_bar + 16;                  // [2] accumulator buffer drained and zeroed
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 4);
-  float4 *s_tile = reinterpret_cast<float4 *>(s_tmem + 4);                              // [8 epilogue warps][32 rows][4] transpose tiles (16 KB)
+  float4 *s_tile = reinterpret_cast<float4 *>(s_tmem + 4);                              // [EPI_WARPS][32 rows][4] transpose tiles (2 KB each)
+  float *s_stat = reinterpret_cast<float *>(s_tile + EPI_WARPS * 128);                  // [EPI_WARPS][2][256] column statistics of this CTA
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler
@@ -603,7 +607,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
     const int half = (warp - 1 - p.nprod * p.ni) >> 2; // two warps per quarter: this one takes the 16-column chunks c0/16 % 2 == half
     const uint32_t tq = tmem + ((uint32_t)(quarter * 32) << 16);
     const float *aux = p.residual ? p.residual : p.bnb_x;   // the per-row fp32 operand of the epilogue (never both)
-    for (int c = 32 * half; c < 2 * acc_cols; c += 64) tmem_zero32(tq + c);
+    for (int c = 32 * half; c < 2 * acc_cols; c += 32 * EPI_SPLIT) tmem_zero32(tq + c);
     tmem_wait_st();
     tc_fence_before();
     __syncwarp();
@@ -611,6 +615,9 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
       mbar_arrive(acce_bar);
       mbar_arrive(acce_bar + 8);
     }
+    float *my_stat = s_stat + (half * 4 + quarter) * 512;
+    for (int c = lane; c < 512; c += 32) my_stat[c] = 0.f;
+    __syncwarp();
     int gi = 0;
     TRC(long long e_wait = 0; const long long e_begin = clock64();)
     for (int tg = blockIdx.x; tg < p.n_groups; tg += G, ++gi) {
@@ -648,7 +655,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
       float4 *my_t = s_tile + (half * 4 + quarter) * 128;    // [32 rows][4 chunks of 16 B], chunk index XOR-swizzled by row
       const int cj = lane & 3, rg = lane >> 2;                // after the transpose: this lane's column chunk and row slot
 #pragma unroll 1
-      for (int c0 = 16 * half; c0 < p.TN; c0 += 32) {
+      for (int c0 = 16 * half; c0 < p.TN; c0 += 16 * EPI_SPLIT) {
         const int col = n0 + c0 + 4 * cj;                     // first of this lane's 4 columns
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sc = bias4, sh = bias4, wv = bias4, bv = bias4;
         if (p.bias) bias4 = __ldg(reinterpret_cast<const float4 *>(p.bias + col));
@@ -657,8 +664,15 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
           sh = __ldg(reinterpret_cast<const float4 *>(p.ep_shift + col));
         }
         if (p.bnb_x) {
-          wv = __ldg(reinterpret_cast<const float4 *>(p.bnb_coef + col));
-          bv = __ldg(reinterpret_cast<const float4 *>(p.bnb_coef + p.c_out + col));
+          // w = invstd*gamma, b = beta - mean*w: the very expressions (and roundings) of the BatchNorm forward kernel
+          const float4 mu = __ldg(reinterpret_cast<const float4 *>(p.bnb_mean + col));
+          wv = __ldg(reinterpret_cast<const float4 *>(p.bnb_invstd + col));
+          if (p.bnb_gamma) {
+            const float4 g = __ldg(reinterpret_cast<const float4 *>(p.bnb_gamma + col));
+            wv.x *= g.x; wv.y *= g.y; wv.z *= g.z; wv.w *= g.w;
+          }
+          if (p.bnb_beta) bv = __ldg(reinterpret_cast<const float4 *>(p.bnb_beta + col));
+          bv.x = -mu.x * wv.x + bv.x; bv.y = -mu.y * wv.y + bv.y; bv.z = -mu.z * wv.z + bv.z; bv.w = -mu.w * wv.w + bv.w;
         }
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;   // column statistics of this lane's 4 columns
 #pragma unroll
@@ -728,19 +742,30 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
             s2.x += __shfl_xor_sync(0xffffffffu, s2.x, sft); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, sft);
             s2.z += __shfl_xor_sync(0xffffffffu, s2.z, sft); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, sft);
           }
+          // this warp's slice of the CTA's running totals (fp32: ~50 additions per column per CTA); one fp64 atomic per column
+          // per CTA at the very end -- per-group global atomics on 2*C addresses from 148 CTAs were a serialisation point
           if (lane < 4) {
-            double *t = p.stats + col;
-            atomicAdd(t, (double)s1.x); atomicAdd(t + 1, (double)s1.y); atomicAdd(t + 2, (double)s1.z); atomicAdd(t + 3, (double)s1.w);
-            t += p.c_out;
-            atomicAdd(t, (double)s2.x); atomicAdd(t + 1, (double)s2.y); atomicAdd(t + 2, (double)s2.z); atomicAdd(t + 3, (double)s2.w);
+            float4 *t1 = reinterpret_cast<float4 *>(my_stat + c0 + 4 * cj), *t2 = reinterpret_cast<float4 *>(my_stat + 256 + c0 + 4 * cj);
+            float4 a = *t1, b = *t2;
+            a.x += s1.x; a.y += s1.y; a.z += s1.z; a.w += s1.w;
+            b.x += s2.x; b.y += s2.y; b.z += s2.z; b.w += s2.w;
+            *t1 = a; *t2 = b;
           }
         }
       }
-      for (int c = 16 * half; c < acc_cols; c += 32) tmem_zero16(tq + buf * acc_cols + c);     // exactly the columns this warp read
+      for (int c = 16 * half; c < acc_cols; c += 16 * EPI_SPLIT) tmem_zero16(tq + buf * acc_cols + c);     // exactly the columns this warp read
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce_bar + 8 * buf);
+    }
+    if (p.stats) {
+      __syncwarp();
+      for (int c = lane; c < p.TN; c += 32) {
+        if (((c >> 4) % EPI_SPLIT) != half) continue;          // the chunks this warp accumulated
+        atomicAdd(p.stats + n0 + c, (double)my_stat[c]);
+        atomicAdd(p.stats + p.c_out + n0 + c, (double)my_stat[256 + c]);
+      }
     }
     TRC(if (p.trace && lane == 0 && quarter == 0 && half == 0) {
       atomicAdd(p.trace + 41, (unsigned long long)(clock64() - e_begin));
@@ -980,7 +1005,8 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   p.tile_mask = a.tile_mask;
   p.residual = a.residual;
   p.ep_scale = a.ep_scale; p.ep_shift = a.ep_shift; p.ep_leak = a.ep_leak; p.out_bf16 = a.out_bf16;
-  p.bnb_x = a.bnb_x; p.bnb_coef = a.bnb_coef; p.bnb_leak = a.bnb_leak;
+  p.bnb_x = a.bnb_x; p.bnb_mean = a.bnb_mean; p.bnb_invstd = a.bnb_invstd; p.bnb_gamma = a.bnb_gamma; p.bnb_beta = a.bnb_beta;
+  p.bnb_leak = a.bnb_leak;
   SCN_CHECK(!a.bnb_x || a.stats, "conv_tma: the fused BatchNorm backward needs the statistics buffer");
   SCN_CHECK(!(a.bnb_x && a.residual), "conv_tma: residual and fused BatchNorm backward are mutually exclusive");
   p.stats = a.stats;
@@ -1004,8 +1030,9 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   p.MT = mt;
   p.stage_bytes = p.MT * A_STAGE + p.b_stage;
   // alignment slack + masks + producers' gather groups (4 owner slots x MT x 32 int4) + barriers + transpose tiles of the epilogue warps
-  const int fixed = 1024 + 8 * MAX_MT * 16 + 4 * p.MT * 32 * 16 + 8 * (2 * 8 + 4) + 64 + EPI_WARPS * 2048;
-  int st = (227 * 1024 - fixed) / p.stage_bytes;
+  const int fixed = 1024 + 8 * MAX_MT * 16 + 4 * p.MT * 32 * 16 + 8 * (2 * 8 + 4) + 64 + EPI_WARPS * 2048 + EPI_WARPS * 2048;
+  static const int smem_kb = env_int("SCN_CONV_SMEM_KB", 227);
+  int st = (smem_kb * 1024 - fixed) / p.stage_bytes;
   if (st > 8) st = 8;
   SCN_CHECK(st >= 2, "conv_tma: shared memory budget");
   p.stages = st;
@@ -1064,6 +1091,11 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
 bool wgrad_tma_supported(const WgradArgs &a) {
   const int cg = a.table_on_a ? a.c_a : a.c_b, cs = a.table_on_a ? a.c_b : a.c_a;
   const int cpb = a.bf16 ? 64 : 32;
+  // two pipeline stages of (all G blocks + one S block) must fit shared memory: tf32 with more than ~416 gathered channels
+  // does not (e.g. the 640 -> 320 block of UNet m=64), and takes the exact-fp32 kernel instead
+  const long long min_stage = (long long)(cg / cpb + 1) * tma::SUB;
+  const long long tail = ((cg + 127) / 128) * 128 > cg ? (128 / cpb) * tma::SUB : 0;
+  if (2 * min_stage + tail + 4096 > 225 * 1024) return false;
   return a.gi != nullptr && a.g_rows > 0 && a.s_rows > 0 && cg >= cpb && cg % cpb == 0 && cs >= cpb && cs % cpb == 0 &&
          a.V <= 32 && ((uintptr_t)a.a % 16 == 0) && ((uintptr_t)a.b % 16 == 0);
 }

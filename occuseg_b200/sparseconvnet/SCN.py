@@ -35,7 +35,26 @@ def get_precision():
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw handle of the current stream of the current device (torch.cuda.current_stream() builds a Stream object: ~15 us)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+
+
+class _NoSwitch:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on(device):
+    """`with _on(device)`, skipped when that device is already current (the usual case: one process per GPU)"""
+    if device.index is None or device.index == torch._C._cuda_getDevice():
+        return _NO_SWITCH
+    return torch.cuda.device(device)
 
 
 # ---- bf16 operand copies (precision 'bf16') ---------------------------------------------------------------------
@@ -229,7 +248,7 @@ def ResolutionBasedScattering(m, points_lr, points_hr, stride):
     lr = lr[:, :3].to(torch.int32).contiguous()
     hr = hr[:, :3].to(torch.int32).contiguous()
     out = torch.empty(hr.size(0), dtype=torch.int32, device=hr.device)
-    with torch.cuda.device(hr.device):
+    with _on(hr.device):
         _lib.check(_lib.lib().scn_resolution_scatter(_ptr(lr), lr.size(0), _ptr(hr), hr.size(0), int(stride), _ptr(out),
                                                      _stream()))
     return out
@@ -250,7 +269,7 @@ def InputLayer_updateOutput(m, spatial_size, input_coords, input_features, outpu
     on_dev = coords.is_cuda
     n = C.c_int64(0)
     h = m._handle(feats.device.index)
-    with torch.cuda.device(feats.device):
+    with _on(feats.device):
         _lib.check(_lib.lib().scn_input_layer_build(h, _lib.size3(spatial_size), _ptr(coords), int(on_dev),
                                                     coords.size(0), int(batch_size), int(mode), _stream(), C.byref(n)))
         m._input_size = _lib.size3(spatial_size)[:]
@@ -260,21 +279,21 @@ def InputLayer_updateOutput(m, spatial_size, input_coords, input_features, outpu
 
 def InputLayer_updateGradInput(m, d_input_features, d_output_features):
     g = _cuda_f32(d_output_features, "InputLayer grad")
-    with torch.cuda.device(g.device):
+    with _on(g.device):
         d_input_features.resize_(int(_lib.lib().scn_n_points(m._handle())), g.size(1))
         _lib.check(_lib.lib().scn_input_layer_bwd(m._handle(), _ptr(g), g.size(1), _ptr(d_input_features), _stream()))
 
 
 def OutputLayer_updateOutput(m, input_features, output_features):
     x = _cuda_f32(input_features, "OutputLayer input")
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         output_features.resize_(int(_lib.lib().scn_n_points(m._handle())), x.size(1))
         _lib.check(_lib.lib().scn_output_layer_fwd(m._handle(), _ptr(x), x.size(1), _ptr(output_features), _stream()))
 
 
 def OutputLayer_updateGradInput(m, d_input_features, d_output_features):
     g = _cuda_f32(d_output_features, "OutputLayer grad")
-    with torch.cuda.device(g.device):
+    with _on(g.device):
         n = int(_lib.lib().scn_nactive(m._handle(), _lib.size3(m._input_size)))
         d_input_features.resize_(n, g.size(1))
         _lib.check(_lib.lib().scn_output_layer_bwd(m._handle(), _ptr(g), g.size(1), _ptr(d_input_features), _stream()))
@@ -307,7 +326,7 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
         if residual.shape != (x.size(0), w.size(2)):
             raise ValueError(f"SubmanifoldConvolution: residual is {tuple(residual.shape)}")
     macs = C.c_double(0.0)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         n = m.getNActive(spatial_size)
         if x.size(0) != n or x.size(1) != w.size(1):
             raise ValueError(f"SubmanifoldConvolution: input is {tuple(x.shape)}, scale has {n} rows, nIn={w.size(1)}")
@@ -324,7 +343,7 @@ def BatchNormalization_evalCoefficients(runningMean, runningVar, weight, bias, e
     BatchNormalization_updateOutput(train=False) evaluates them."""
     c = runningMean.numel()
     scale, shift = torch.empty_like(runningMean), torch.empty_like(runningMean)
-    with torch.cuda.device(runningMean.device):
+    with _on(runningMean.device):
         _lib.check(_lib.lib().scn_bn_eval_coeffs(_ptr(runningMean), _ptr(runningVar), _ptr(_opt(weight)), _ptr(_opt(bias)), c,
                                                  float(eps), _ptr(scale), _ptr(shift), _stream()))
     return scale, shift
@@ -338,7 +357,7 @@ def SubmanifoldConvolutionBN_updateOutput(spatial_size, filter_size, m, input_fe
         raise NotImplementedError("SubmanifoldConvolution: only 3x3x3 is on this path")
     x, w, b = _cuda_f32(input_features, "input"), _check_weight(weight, 27), _opt(bias)
     macs = C.c_double(0.0)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         n = m.getNActive(spatial_size)
         if x.size(0) != n or x.size(1) != w.size(1):
             raise ValueError(f"SubmanifoldConvolution: input is {tuple(x.shape)}, scale has {n} rows, nIn={w.size(1)}")
@@ -356,7 +375,7 @@ def SubmanifoldConvolution_backward(spatial_size, filter_size, m, input_features
                                     weight, d_weight, d_bias, dilated_rate=1, input_bf16=None):
     x, w = _conv_input(m, input_features, input_bf16), _check_weight(weight, 27)
     g = _grad_operand(m, d_output_features, input_bf16 is not None and _opt(d_bias) is None)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         if d_input_features is not None:      # None: the caller does not need the input gradient (first layer)
             d_input_features.resize_(x.size(0), x.size(1))
         _dilation(m, dilated_rate)
@@ -376,7 +395,7 @@ def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, i
     _check_2s2(filter_size, filter_stride)
     w, b = _check_weight(weight, 8), _opt(bias)
     macs, nc = C.c_double(0.0), C.c_int64(0)
-    with torch.cuda.device(weight.device):
+    with _on(weight.device):
         _lib.check(_lib.lib().scn_strided_rulebook(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _stream(),
                                                    C.byref(nc)))
         x = _conv_input(m, input_features, input_bf16)
@@ -391,7 +410,7 @@ def Convolution_backward(in_size, out_size, filter_size, filter_stride, m, input
                          d_output_features, weight, d_weight, d_bias, input_bf16=None):
     x, w = _conv_input(m, input_features, input_bf16), _check_weight(weight, 8)
     g = _grad_operand(m, d_output_features, input_bf16 is not None and _opt(d_bias) is None)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         d_input_features.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_conv_bwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(g),
                                            _ptr(w), _ptr(d_input_features), _ptr(d_weight), _ptr(_opt(d_bias)),
@@ -403,7 +422,7 @@ def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m,
     _check_2s2(filter_size, filter_stride)
     x, w, b = _conv_input(m, input_features, input_bf16), _check_weight(weight, 8), _opt(bias)
     macs = C.c_double(0.0)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         n = m.getNActive(out_size)
         if n < 0:
             raise _lib.ScnError("Deconvolution: output scale does not exist (no matching Convolution ran on this batch)")
@@ -418,7 +437,7 @@ def Deconvolution_backward(in_size, out_size, filter_size, filter_stride, m, inp
                            d_output_features, weight, d_weight, d_bias, input_bf16=None):
     x, w = _conv_input(m, input_features, input_bf16), _check_weight(weight, 8)
     g = _grad_operand(m, d_output_features, input_bf16 is not None and _opt(d_bias) is None)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         d_input_features.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_deconv_bwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(g),
                                              _ptr(w), _ptr(d_input_features), _ptr(d_weight), _ptr(_opt(d_bias)),
@@ -433,7 +452,7 @@ def BatchNormalization_updateOutput(input_features, output_features, saveMean, s
     stats (extension): float64 [2, C] column sums / sums of squares of the input, made by the convolution that
     produced it (attach_stats); the training-mode reduction pass is skipped."""
     x = _cuda_f32(input_features, "input")
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         if output_features is not None:        # None (extension): only the bf16 operand is written
             output_features.resize_(x.size(0), x.size(1))
         if output_bf16 is not None:
@@ -453,7 +472,7 @@ def BatchNormalization_backward(input_features, d_input_features, output_feature
     x, g = _cuda_f32(input_features, "input"), _cuda_f32(d_output_features, "grad")
     if d_input_add is not None:
         d_input_add = _cuda_f32(d_input_add, "d_input_add")
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         d_input_features.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_bn_bwd(_ptr(x), _ptr(output_features), _ptr(g), _ptr(saveMean), _ptr(saveInvStd),
                                          _ptr(_opt(weight)), _ptr(_opt(bias)), _ptr(d_input_add), _ptr(d_input_features),
@@ -476,7 +495,7 @@ def BatchNormalization_backwardApply(input_features, d_masked, acc, saveMean, sa
     ld_add = 0
     if d_input_add is not None:
         d_input_add, ld_add = _rows_f32(d_input_add, "d_input_add")      # may be a column slice of a joined gradient
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         d_input_features.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_bn_bwd_apply(_ptr(x), _ptr(g), _ptr(acc), _ptr(saveMean), _ptr(saveInvStd), _ptr(_opt(weight)),
                                                _ptr(d_input_add), int(ld_add), _ptr(d_input_features), _ptr(_opt(d_weight)),

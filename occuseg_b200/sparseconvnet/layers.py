@@ -114,11 +114,12 @@ class Sequential(torch.nn.Sequential):
         self._modules[str(len(self._modules))] = module
         return self
 
-    def forward(self, input):
+    def forward(self, input, start=0):
         # same as torch.nn.Sequential, except that at inference a SubmanifoldConvolution directly followed by a
-        # BatchNorm(+ReLU) runs as one kernel (fused BatchNorm+ReLU epilogue)
+        # BatchNorm(+ReLU) runs as one kernel (fused BatchNorm+ReLU epilogue), and in training a BatchNorm(+ReLU) directly
+        # followed by a convolution runs as one autograd node; `start` skips modules a caller has already applied
         mods = list(self._modules.values())
-        i = 0
+        i = start
         while i < len(mods):
             if i + 1 < len(mods) and isinstance(input, SparseConvNetTensor) and _fusable_inference_pair(mods[i], mods[i + 1], input):
                 input = _conv_bn_inference(mods[i], mods[i + 1], input)
@@ -143,7 +144,18 @@ class ConcatTable(torch.nn.Sequential):
         return self
 
     def forward(self, input):
-        return [m(input) for m in self._modules.values()]
+        mods = list(self._modules.values())
+        # The UNet's skip connection, ConcatTable(Identity, Sequential(BN, Convolution, ...)) (networkArchitectures.py:246-260):
+        # the input feeds both branches, so autograd would add the two gradients in a separate pass.  When the inner
+        # branch starts with a fusable BatchNorm -> convolution pair, the Identity branch receives the input re-issued by that
+        # node (a view), and whatever gradient returns through it is added inside the BatchNorm's backward kernel.
+        if (len(mods) == 2 and isinstance(mods[0], Identity) and isinstance(mods[1], Sequential)
+                and isinstance(input, SparseConvNetTensor) and len(mods[1]._modules) >= 2):
+            inner = list(mods[1]._modules.values())
+            if _fusable_training_pair(inner[0], inner[1], input):
+                t, alias = _bn_conv_training(inner[0], inner[1], input, with_alias=True)
+                return [alias, mods[1].forward(t, start=2)]
+        return [m(input) for m in mods]
 
     def input_spatial_size(self, out_size):
         return self._modules["0"].input_spatial_size(out_size)

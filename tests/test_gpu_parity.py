@@ -449,8 +449,9 @@ def test_epilogue_statistics_and_residual_match_torch():
         SCN.SubmanifoldConvolution_updateOutput(lt(SIZE), lt(3), m, x, y1, w, torch.empty(0), 1, r, st)
         assert torch.equal(y1, y0 + r)
         s0, s1 = y1.double().sum(0), (y1.double() ** 2).sum(0)
-        assert float((st[0] - s0).abs().max() / s0.abs().max()) < 1e-6
-        assert float((st[1] - s1).abs().max() / s1.abs().max()) < 1e-6
+        # fp32 partial sums per CTA (about 50 additions per column), merged in fp64: 5e-6
+        assert float((st[0] - s0).abs().max() / s0.abs().max()) < 5e-6
+        assert float((st[1] - s1).abs().max() / s1.abs().max()) < 5e-6
 
 
 def test_runs_on_a_non_default_stream():
@@ -548,7 +549,7 @@ def test_pattern_sorted_tile_order_is_bit_identical(precision, cin, cout):
         _lib.tile_sort(prev)
     for y, dx, st in res[1:]:
         assert torch.equal(y, res[0][0]) and torch.equal(dx, res[0][1])
-        assert float((st - res[0][2]).abs().max() / res[0][2].abs().max()) < 1e-6      # fp32 partial sums regroup
+        assert float((st - res[0][2]).abs().max() / res[0][2].abs().max()) < 5e-6      # fp32 partial sums regroup
 
 
 @pytest.mark.parametrize("kind", ["subm", "conv", "deconv"])
