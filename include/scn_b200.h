@@ -218,6 +218,10 @@ int scn_bn_bwd_apply(const float *in, const float *d_masked, const double *acc, 
  * so the slice is read where it lies (by the bf16 cast every product of that entry works from) instead of being copied out
  * first.  One use; needs the SCN_BF16 path for all of the entry's products (the entry fails otherwise) and no bias gradient. */
 int scn_grad_stride(scn_meta *m, int64_t ld);
+/* Column statistics from the strided layers: scn_out_stats registers a [2][Cout] fp64 buffer that the NEXT scn_conv_fwd /
+ * scn_deconv_fwd on the handle fills with the column sums / sums of squares of its result (as the `stats` argument of scn_subm_fwd
+ * does), for the BatchNorm that consumes it.  One use; tensor-core shapes only (scn_fuses_residual). */
+int scn_out_stats(scn_meta *m, double *stats);
 
 #ifdef __cplusplus
 }

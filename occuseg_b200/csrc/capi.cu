@@ -223,7 +223,8 @@ static void apply_bnb_hint(Meta *m, ConvArgs &a, int precision, BnbScratch &scr,
 }
 
 static void run_up(Level *F, Level *C, const float *in, const float *w, bool native_kn, float *out, int c_in, int c_out,
-                   int precision, cudaStream_t s, const uint16_t *in16 = nullptr, Meta *bnb_from = nullptr) {
+                   int precision, cudaStream_t s, const uint16_t *in16 = nullptr, Meta *bnb_from = nullptr,
+                   double *stats = nullptr) {
   // tensor cores: the fine rows grouped by tap (whole 256-row tile groups per tap), one gathered row and one weight tap
   // per row -- no work is spent on the 7 taps a row does not have
   ConvArgs g;
@@ -243,10 +244,12 @@ static void run_up(Level *F, Level *C, const float *in, const float *w, bool nat
     g.out_limit = F->n;
     BnbScratch scr;
     if (bnb_from) apply_bnb_hint(bnb_from, g, precision, scr, s);
+    if (stats) g.stats = stats;
     run_conv(g, w, native_kn, precision, s, in16);
     scr.release(s);
     return;
   }
+  SCN_CHECK(!stats, "column statistics need the tensor-core path");
   SCN_CHECK(!bnb_from || !bnb_from->bnb.x, "fused BatchNorm backward: this layer's dgrad does not run on the tensor-core path");
   ConvArgs a;
   a.in = in; a.out = out; a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8;
@@ -478,7 +481,9 @@ int scn_spatial_locations(scn_meta *h, const int64_t size[3], int64_t *out) {
   SCN_TRY
   Level *L = need_level(&h->m, size, "getSpatialLocations");
   std::vector<uint64_t> keys(L->n);
-  SCN_CUDA(cudaMemcpy(keys.data(), L->keys.p, sizeof(uint64_t) * L->n, cudaMemcpyDeviceToHost));
+  // on the stream the handle last worked on (the caller's, possibly non-blocking): ordered behind the kernels that built the keys
+  SCN_CUDA(cudaMemcpyAsync(keys.data(), L->keys.p, sizeof(uint64_t) * L->n, cudaMemcpyDeviceToHost, h->m.last_stream));
+  SCN_CUDA(cudaStreamSynchronize(h->m.last_stream));
   for (int i = 0; i < L->n; ++i) {
     uint64_t k = keys[i];
     out[4 * i + 0] = (int64_t)(k & 0xFFFF);
@@ -515,8 +520,9 @@ int scn_subm_neighbour_table(scn_meta *h, const int64_t size[3], int32_t *out) {
     L = D;
   }
   SCN_CHECK(L->nbr.p, "neighbour table not built yet (call scn_subm_rulebook)");
-  SCN_CUDA(cudaMemcpy2D(out, sizeof(int) * L->n, L->nbr.p, sizeof(int) * L->n_pad, sizeof(int) * L->n, 27,
-                        cudaMemcpyDeviceToHost));
+  SCN_CUDA(cudaMemcpy2DAsync(out, sizeof(int) * L->n, L->nbr.p, sizeof(int) * L->n_pad, sizeof(int) * L->n, 27,
+                             cudaMemcpyDeviceToHost, h->m.last_stream));
+  SCN_CUDA(cudaStreamSynchronize(h->m.last_stream));
   SCN_CATCH
 }
 
@@ -538,8 +544,9 @@ int scn_strided_table(scn_meta *h, const int64_t fine[3], int32_t *parent, uint8
   SCN_TRY
   Level *F = need_level(&h->m, fine, "Convolution");
   SCN_CHECK(F->coarse, "strided rulebook not built yet (call scn_strided_rulebook)");
-  SCN_CUDA(cudaMemcpy(parent, F->parent.p, sizeof(int) * F->n, cudaMemcpyDeviceToHost));
-  SCN_CUDA(cudaMemcpy(off, F->off8.p, F->n, cudaMemcpyDeviceToHost));
+  SCN_CUDA(cudaMemcpyAsync(parent, F->parent.p, sizeof(int) * F->n, cudaMemcpyDeviceToHost, h->m.last_stream));
+  SCN_CUDA(cudaMemcpyAsync(off, F->off8.p, F->n, cudaMemcpyDeviceToHost, h->m.last_stream));
+  SCN_CUDA(cudaStreamSynchronize(h->m.last_stream));
   SCN_CATCH
 }
 
@@ -654,6 +661,13 @@ int scn_conv_fwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   ConvArgs a;
   a.in = in; a.bias = bias; a.out = out;
   a.tbl = F->child.p; a.tbl_stride = C->n_pad; a.n_rows = C->n; a.V = 8; a.c_in = c_in; a.c_out = c_out; a.n_rules = F->n; a.in_rows = F->n;
+  a.stats = h->m.next_stats;
+  h->m.next_stats = nullptr;
+  if (a.stats) {
+    ConvArgs probe = a;
+    probe.bf16 = bf16_conv_shape(c_in, c_out, precision);
+    SCN_CHECK(precision != SCN_FP32 && conv_tma_supported(probe), "scn_out_stats: this layer does not run on the tensor-core path");
+  }
   run_conv(a, weight, true, precision, s, take_bf16_hint(&h->m, in, (long long)F->n * c_in, s));
   if (macs) *macs = (double)F->n * c_in * c_out;   // every fine row has exactly one rule
   SCN_CATCH
@@ -696,7 +710,9 @@ int scn_deconv_fwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
   Level *C = F->coarse;
   SCN_CHECK(bias == nullptr, "Deconvolution: bias is not supported on this path (the UNet uses bias=False)");
   // out[child[k][p]] = in[p] * W[k]
-  run_up(F, C, in, weight, true, out, c_in, c_out, precision, s, take_bf16_hint(&h->m, in, (long long)C->n * c_in, s));
+  double *stats = h->m.next_stats;
+  h->m.next_stats = nullptr;
+  run_up(F, C, in, weight, true, out, c_in, c_out, precision, s, take_bf16_hint(&h->m, in, (long long)C->n * c_in, s), nullptr, stats);
   if (macs) *macs = (double)F->n * c_in * c_out;
   SCN_CATCH
 }
@@ -765,6 +781,13 @@ int scn_bn_bwd_apply(const float *in, const float *d_masked, const double *acc, 
   ProfScope ps(PK_BN, (d_in_add ? 4.0 : 3.0) * 4.0 * (double)n * C, 0.0, note_stream(stream));
   bn_bwd_apply(in, d_masked, acc, save_mean, save_invstd, gamma, d_in_add, ld_add, d_in, d_gamma, d_beta, n, C,
                note_stream(stream));
+  SCN_CATCH
+}
+
+int scn_out_stats(scn_meta *h, double *stats) {
+  SCN_TRY
+  SCN_CHECK(h, "null handle");
+  h->m.next_stats = stats;
   SCN_CATCH
 }
 

@@ -171,6 +171,7 @@ struct Meta {
   const float *hint_src = nullptr;
   void *hint_bf16 = nullptr;
   int hint_ready = 0;
+  double *next_stats = nullptr;   // scn_out_stats(): column statistics wanted from the next scn_conv_fwd / scn_deconv_fwd (one use)
   int next_dilation = 1;     // scn_subm_dilation(): dilation of the next submanifold entry (one use)
   long long next_grad_ld = 0;  // scn_grad_stride(): row stride (floats) of d_out of the next backward entry (one use; 0 = dense)
   // scn_bn_bwd_fusion(): the BatchNorm whose backward the next *_bwd entry folds into its dgrad epilogue (one use)

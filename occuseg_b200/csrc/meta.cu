@@ -56,20 +56,33 @@ __global__ void k_coarse_keys(const uint64_t *__restrict__ fine, int n, uint64_t
 }
 
 // rows = runs of equal keys in the sorted list; fan the row id back out to the members of each run
-__global__ void k_rows_of_points(const int *__restrict__ run_ptr, const int *__restrict__ sorted_idx, int n_runs,
+// run (= row) holding sorted position j: the last r with run_ptr[r] <= j
+__device__ __forceinline__ int run_of(const int *__restrict__ run_ptr, int n_runs, int j) {
+  int lo = 0, hi = n_runs;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(&run_ptr[mid]) <= j) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// One thread per POINT (a binary search for its run), so a voxel holding thousands of duplicate points costs no more than any other
+__global__ void k_rows_of_points(const int *__restrict__ run_ptr, const int *__restrict__ sorted_idx, int n_runs, int n_points,
                                  int *__restrict__ row_of_point) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_runs) return;
-  for (int j = run_ptr[r]; j < run_ptr[r + 1]; ++j) row_of_point[sorted_idx[j]] = r;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_points) return;
+  row_of_point[sorted_idx[j]] = run_of(run_ptr, n_runs, j);
 }
 
 // stride-2 link: parent / offset of every fine row, child table of every coarse row
 __global__ void k_link_levels(const int *__restrict__ run_ptr, const int *__restrict__ sorted_idx,
-                              const uint64_t *__restrict__ fine_keys, int n_runs, int child_stride,
+                              const uint64_t *__restrict__ fine_keys, int n_runs, int n_fine, int child_stride,
                               int *__restrict__ parent, uint8_t *__restrict__ off8, int *__restrict__ child) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_runs) return;
-  for (int j = run_ptr[r]; j < run_ptr[r + 1]; ++j) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;          // one thread per fine row (sorted position)
+  if (j >= n_fine) return;
+  {
+    const int r = run_of(run_ptr, n_runs, j);
     int i = sorted_idx[j];
     uint64_t k = fine_keys[i];
     // offset index ((x&1)*2 + (y&1))*2 + (z&1): SubmanifoldRules_cuda.cu:549-554
@@ -357,7 +370,7 @@ void build_input_level(Meta *m, const int64_t size[3], const int64_t *coords, bo
   m->levels.push_back(L);
 
   m->row_of_point.alloc(P, s);
-  k_rows_of_points<<<grid_for(L->n, 256), 256, 0, s>>>(runs.ptr.p, runs.sorted_idx.p, L->n, m->row_of_point.p);
+  k_rows_of_points<<<grid_for(P, 256), 256, 0, s>>>(runs.ptr.p, runs.sorted_idx.p, L->n, (int)P, m->row_of_point.p);
   SCN_LAUNCH_CHECK();
   m->rule_ptr.alloc(L->n + 1, s);
   SCN_CUDA(cudaMemcpyAsync(m->rule_ptr.p, runs.ptr.p, sizeof(int) * (L->n + 1), cudaMemcpyDeviceToDevice, s));
@@ -548,7 +561,7 @@ Level *ensure_coarse_level(Meta *m, Level *F, const int64_t coarse_size[3], cuda
   F->off8.alloc(F->n, s);
   F->child.alloc((size_t)8 * C->n_pad, s);
   SCN_CUDA(cudaMemsetAsync(F->child.p, 0xFF, sizeof(int) * (size_t)8 * C->n_pad, s));      // -1 = no child at this offset
-  k_link_levels<<<grid_for(C->n, 256), 256, 0, s>>>(runs.ptr.p, runs.sorted_idx.p, F->keys.p, C->n, C->n_pad,
+  k_link_levels<<<grid_for(F->n, 256), 256, 0, s>>>(runs.ptr.p, runs.sorted_idx.p, F->keys.p, C->n, F->n, C->n_pad,
                                                     F->parent.p, F->off8.p, F->child.p);
   SCN_LAUNCH_CHECK();
   F->coarse = C;

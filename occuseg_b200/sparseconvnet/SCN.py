@@ -391,7 +391,7 @@ def _check_2s2(filter_size, filter_stride):
 
 
 def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, input_features, output_features, weight,
-                             bias, input_bf16=None):
+                             bias, input_bf16=None, stats=None):
     _check_2s2(filter_size, filter_stride)
     w, b = _check_weight(weight, 8), _opt(bias)
     macs, nc = C.c_double(0.0), C.c_int64(0)
@@ -400,6 +400,8 @@ def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, i
                                                    C.byref(nc)))
         x = _conv_input(m, input_features, input_bf16)
         output_features.resize_(nc.value, w.size(2))
+        if stats is not None:
+            _lib.check(_lib.lib().scn_out_stats(m._handle(), _ptr(stats)))
         _lib.check(_lib.lib().scn_conv_fwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(w),
                                            _ptr(b), _ptr(output_features), w.size(1), w.size(2), _precision, _stream(),
                                            C.byref(macs)))
@@ -418,7 +420,7 @@ def Convolution_backward(in_size, out_size, filter_size, filter_stride, m, input
 
 
 def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, input_features, output_features,
-                               weight, bias, input_bf16=None):
+                               weight, bias, input_bf16=None, stats=None):
     _check_2s2(filter_size, filter_stride)
     x, w, b = _conv_input(m, input_features, input_bf16), _check_weight(weight, 8), _opt(bias)
     macs = C.c_double(0.0)
@@ -427,6 +429,8 @@ def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m,
         if n < 0:
             raise _lib.ScnError("Deconvolution: output scale does not exist (no matching Convolution ran on this batch)")
         output_features.resize_(n, w.size(2))
+        if stats is not None:
+            _lib.check(_lib.lib().scn_out_stats(m._handle(), _ptr(stats)))
         _lib.check(_lib.lib().scn_deconv_fwd(m._handle(), _lib.size3(in_size), _lib.size3(out_size), _ptr(x), _ptr(w),
                                              _ptr(b), _ptr(output_features), w.size(1), w.size(2), _precision,
                                              _stream(), C.byref(macs)))

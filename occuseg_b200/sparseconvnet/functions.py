@@ -166,7 +166,7 @@ class BatchNormConvFunction(Function):
                        stats if want_stats else None, input_bf16=y16)
         else:
             macs = fwd(in_size, out_size, filter_size, filter_stride, metadata, None, out, conv_weight, conv_bias,
-                       input_bf16=y16)
+                       input_bf16=y16, stats=stats if want_stats else None)
         _count(macs, out)
         ctx.scn_meta, ctx.kind, ctx.leakiness = metadata, kind, leakiness
         ctx.save_for_backward(x, bn_weight, bn_bias, save_mean, save_invstd, y16, conv_weight, conv_bias, in_size, out_size,

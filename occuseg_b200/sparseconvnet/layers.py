@@ -98,7 +98,7 @@ def _bn_conv_training(bn, conv, input, residual=None, with_alias=False):
     else:
         kind, in_size, stride = "deconv", input.spatial_size, conv.filter_stride
         out_size = (in_size - 1) * stride + conv.filter_size
-    want_stats = kind == "subm" and SCN.fuses_residual(conv.nIn, conv.nOut)
+    want_stats = SCN.fuses_residual(conv.nIn, conv.nOut)      # the epilogue also leaves the statistics for the next BatchNorm
     out, stats, alias = F.BatchNormConvFunction.apply(
         input.features, optionalTensor(bn, "weight"), optionalTensor(bn, "bias"), bn.running_mean, bn.running_var, bn.eps,
         bn.momentum, bn.leakiness, conv.weight, optionalTensor(conv, "bias"), input.metadata, kind, in_size, out_size,
@@ -153,7 +153,10 @@ class ConcatTable(torch.nn.Sequential):
                 and isinstance(input, SparseConvNetTensor) and len(mods[1]._modules) >= 2):
             inner = list(mods[1]._modules.values())
             if _fusable_training_pair(inner[0], inner[1], input):
+                held = SCN.held_stats(input.features)
                 t, alias = _bn_conv_training(inner[0], inner[1], input, with_alias=True)
+                if held is not None:
+                    SCN.attach_stats(alias.features, held)       # the re-issued view carries its producer's column statistics on
                 return [alias, mods[1].forward(t, start=2)]
         return [m(input) for m in mods]
 
@@ -203,7 +206,12 @@ class AddTable(torch.nn.Sequential):
 
 class JoinTable(torch.nn.Sequential):
     def forward(self, input):
-        return _same(input[0], torch.cat([t.features for t in input], 1))
+        feats = torch.cat([t.features for t in input], 1)
+        # column statistics concatenate like the columns do: the BatchNorm behind the join skips its reduction pass
+        st = [SCN.held_stats(t.features) if t.features.is_cuda else None for t in input]
+        if all(s is not None for s in st):
+            SCN.attach_stats(feats, torch.cat(st, 1))
+        return _same(input[0], feats)
 
     def input_spatial_size(self, out_size):
         return out_size
