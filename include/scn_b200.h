@@ -71,6 +71,22 @@ int scn_tile_sort(int block_rows);
  * earlier samples.  *n_active receives the row count (one host sync). mode must be 3 (sum) or 4 (mean). */
 int scn_input_layer_build(scn_meta *m, const int64_t spatial_size[3], const int64_t *coords, int coords_on_device,
                           int64_t n_points, int batch_size, int mode, void *stream, int64_t *n_active);
+/* Normal-guided kernels (OccuSeg's `use_normal`; InputLayer_updateOutput's `normals` argument, CUDA/IOLayers.cpp:39-66).
+ * Call BEFORE scn_input_layer_build: point_normals float [P,3] in DEVICE memory, one per point of that call.  Every voxel gets
+ * the normalised mean of its points' normals and the orientation class OrientedFilter(normal) in {0,2,4}
+ * (Metadata/RectangularRegions.h:12-31); submanifold rules of a scale that carries normals use, for every OUTPUT row, the tap
+ * permutation of its class (remap_rules_with_normal, Metadata/SubmanifoldConvolutionRules.h:213-245, table
+ * SubmanifoldRules_cuda.cu:8-15), forward, dgrad and wgrad.  Strided layers whose INPUT scale is >= normal_guide_scale
+ * (Metadata::setNormalGuideScale, ConvolutionRules.h:774) hand the coarse scale the normalised mean of the children's normals
+ * and permute their 8 taps by the coarse row's class, as the reference's CPU builder does (ConvolutionRules.h:18-92; its GPU
+ * variant, :139-236, advances its query index twice per rule and is not reproduced); below that scale the plain rules are used
+ * and the coarse scale carries no normals.  Not combined with dilation or with the fused training BatchNorm backward. */
+int scn_input_normals(scn_meta *m, const float *point_normals, int normal_guide_scale);
+int scn_guided(scn_meta *m, const int64_t spatial_size[3]);       /* 1 when the scale carries normals */
+/* parity access: the guided forward table int32 [27, N] (HOST) and the orientation class of every row (uint8 [N], may be NULL) */
+int scn_subm_guided_table(scn_meta *m, const int64_t spatial_size[3], void *stream, int32_t *out_host, uint8_t *ori_host);
+/* parity access: the per-voxel normals float [N,3] (HOST) of a scale that carries them (Metadata::normals, Metadata.h) */
+int scn_normals(scn_meta *m, const int64_t spatial_size[3], void *stream, float *out_host);
 /* feature part of InputLayer_updateOutput (CUDA/IOLayers.cu:16-43): out[N,C] = sum/mean of the points of each voxel */
 int scn_input_layer_fwd(scn_meta *m, const float *point_feats, int channels, float *out, void *stream);
 /* InputLayer_updateGradInput (CUDA/IOLayers.cpp:81-105): d_point[P,C] = (1/n) * d_out[row(p)] */

@@ -25,6 +25,10 @@ PROTOTYPES = {
     "scn_meta_destroy": (None, [_vp]),
     "scn_pool_trim": (C.c_int, [C.c_int, C.c_int64]),
     "scn_tile_sort": (C.c_int, [C.c_int]),
+    "scn_input_normals": (C.c_int, [_vp, _vp, C.c_int]),
+    "scn_guided": (C.c_int, [_vp, _i64p]),
+    "scn_subm_guided_table": (C.c_int, [_vp, _i64p, _vp, _vp, _vp]),
+    "scn_normals": (C.c_int, [_vp, _i64p, _vp, _vp]),
     "scn_input_layer_build": (C.c_int, [_vp, _i64p, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _i64p]),
     "scn_input_layer_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "scn_input_layer_bwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),

@@ -423,6 +423,43 @@ static void prebuild_scales(Meta *m, cudaStream_t s) {
   }
 }
 
+int scn_input_normals(scn_meta *h, const float *point_normals, int normal_guide_scale) {
+  SCN_TRY
+  SCN_CHECK(h && point_normals, "scn_input_normals: null argument");
+  h->m.point_normals = point_normals;
+  h->m.normal_guide_scale = normal_guide_scale > 0 ? normal_guide_scale : (1 << 30);
+  SCN_CATCH
+}
+
+int scn_guided(scn_meta *h, const int64_t size[3]) {
+  if (!h) return 0;
+  Level *L = find_level(&h->m, size);
+  return L && L->guided ? 1 : 0;
+}
+
+int scn_subm_guided_table(scn_meta *h, const int64_t size[3], void *stream, int32_t *out, uint8_t *ori_out) {
+  SCN_TRY
+  cudaStream_t s = note_stream(stream);
+  Level *L = need_level(&h->m, size, "SubmanifoldConvolution");
+  SCN_CHECK(L->guided, "this scale carries no normals (scn_input_normals)");
+  ensure_guided_tables(&h->m, L, s);
+  SCN_CUDA(cudaMemcpy2DAsync(out, sizeof(int) * L->n, L->nbr_g.p, sizeof(int) * L->n_pad, sizeof(int) * L->n, 27,
+                             cudaMemcpyDeviceToHost, s));
+  if (ori_out) SCN_CUDA(cudaMemcpyAsync(ori_out, L->ori.p, L->n, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));
+  SCN_CATCH
+}
+
+int scn_normals(scn_meta *h, const int64_t size[3], void *stream, float *out) {
+  SCN_TRY
+  cudaStream_t s = note_stream(stream);
+  Level *L = need_level(&h->m, size, "normals");
+  SCN_CHECK(L->guided && out, "this scale carries no normals (scn_input_normals)");
+  SCN_CUDA(cudaMemcpyAsync(out, L->normal.p, sizeof(float) * 3 * L->n, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));
+  SCN_CATCH
+}
+
 int scn_input_layer_build(scn_meta *h, const int64_t size[3], const int64_t *coords, int on_device, int64_t P,
                           int batch, int mode, void *stream, int64_t *n_active) {
   SCN_TRY
@@ -581,7 +618,12 @@ int scn_subm_fwd_bn(scn_meta *h, const int64_t size[3], const float *in, const f
   ConvArgs probe = a;
   probe.bf16 = bf16_conv_shape(c_in, c_out, precision);
   SCN_CHECK(precision != SCN_FP32 && conv_tma_supported(probe), "scn_subm_fwd_bn needs the tensor-core path (see scn_fuses_residual)");
-  use_sorted_tiles(a, L, precision, s);
+  if (L->guided) {
+    ensure_guided_tables(&h->m, L, s);
+    a.tbl = L->nbr_g.p;
+  } else {
+    use_sorted_tiles(a, L, precision, s);
+  }
   run_conv(a, weight, true, precision, s, take_bf16_hint(&h->m, in, (long long)L->n * c_in, s));
   if (macs) *macs = (double)L->n_rules * c_in * c_out;
   SCN_CATCH
@@ -605,7 +647,12 @@ int scn_subm_fwd(scn_meta *h, const int64_t size[3], const float *in, const floa
     SCN_CHECK(precision != SCN_FP32 && conv_tma_supported(probe) && (uintptr_t)residual % 16 == 0,
               "SubmanifoldConvolution: fused residual / statistics need the tensor-core path (see scn_fuses_residual)");
   }
-  use_sorted_tiles(a, L, precision, s);
+  if (L->guided) {          // normal-guided taps: the forward table with every output row's taps permuted by its class
+    ensure_guided_tables(&h->m, L, s);
+    a.tbl = L->nbr_g.p;
+  } else {
+    use_sorted_tiles(a, L, precision, s);
+  }
   run_conv(a, weight, true, precision, s, take_bf16_hint(&h->m, in, (long long)L->n * c_in, s));
   if (macs) *macs = (double)L->n_rules * c_in * c_out;   // flops += nRules*ip*op, CPU/Convolution.cpp:134
   SCN_CATCH
@@ -630,7 +677,35 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   a.in = d_out; a.out = d_in;
   a.tbl = L->nbr.p; a.tbl_stride = L->n_pad; a.n_rows = L->n; a.V = 27; a.c_in = c_out; a.c_out = c_in; a.mirror = true; a.n_rules = L->n_rules; a.in_rows = L->n;
   BnbScratch scr;
-  if (d_in) {
+  if (d_in && L->guided) {
+    // the taps an input row feeds depend on the class of each OUTPUT row, so the transposed relation is one table per class
+    // (a tap is used at most once per class); the three partial sums are accumulated through the epilogue's residual operand
+    SCN_CHECK(!h->m.bnb.x, "fused BatchNorm backward is not available on normal-guided scales");
+    ensure_guided_tables(&h->m, L, s);
+    a.mirror = false;
+    for (int c = 0; c < 3; ++c) {
+      ConvArgs ac = a;
+      ac.tbl = L->nbr_t[c].p;
+      ConvArgs probe = ac;
+      probe.bf16 = bf16_conv_shape(ac.c_in, ac.c_out, precision);
+      const bool tc = precision != SCN_FP32 && conv_tma_supported(probe);
+      if (c > 0) {
+        if (tc) {
+          ac.residual = d_in;
+          run_conv(ac, weight, false, precision, s, dgrad16 ? pg : nullptr);
+        } else {           // exact-fp32 kernels have no residual operand: accumulate through a temporary
+          DevBuf<float> part;
+          part.alloc((size_t)L->n * c_in, s);
+          ac.out = part.p;
+          run_conv(ac, weight, false, precision, s, nullptr);
+          axpy(part.p, d_in, (long long)L->n * c_in, s);
+          part.release(s);
+        }
+      } else {
+        run_conv(ac, weight, false, precision, s, dgrad16 ? pg : nullptr);
+      }
+    }
+  } else if (d_in) {
     use_sorted_tiles(a, L, precision, s);
     apply_bnb_hint(&h->m, a, precision, scr, s);
     run_conv(a, weight, false, precision, s, dgrad16 ? pg : nullptr);
@@ -638,10 +713,11 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
     SCN_CHECK(!h->m.bnb.x, "fused BatchNorm backward needs d_in");
   }
   scr.release(s);
+  if (L->guided) ensure_guided_tables(&h->m, L, s);
   WgradArgs w;
-  w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = L->nbr.p; w.tbl_stride = L->n_pad; w.n_rows = L->n; w.V = 27;
+  w.a = in; w.b = d_out; w.dw = d_weight; w.tbl = L->guided ? L->nbr_g.p : L->nbr.p; w.tbl_stride = L->n_pad; w.n_rows = L->n; w.V = 27;
   w.c_a = c_in; w.c_b = c_out; w.table_on_a = true; w.n_rules = L->n_rules; w.g_rows = L->n; w.s_rows = L->n;
-  run_wgrad(w, L->nbr_pairs, precision, s, px, pg);
+  run_wgrad(w, L->guided ? L->nbr_g_pairs : L->nbr_pairs, precision, s, px, pg);
   g16.release(s);
   x16.release(s);
   if (d_bias) bias_grad(d_out, d_bias, L->n, c_out, s);

@@ -154,6 +154,15 @@ struct Level {
   DevBuf<int> child;         // [8][coarse->n_pad] fine row or -1
   PairList child_pairs;      // 8 compacted (fine, coarse) lists
   PairList up_pairs;         // the same lists padded to whole 256-row tile groups (-1), for the one-tap-per-row products
+  // Normal-guided kernels (OccuSeg's `use_normal`): every voxel carries an averaged surface normal; its orientation class
+  // OrientedFilter(normal) in {0, 2, 4} (Metadata/RectangularRegions.h:12-31) permutes the weight taps its OUTPUT row uses
+  // (SubmanifoldConvolutionRules.h:213-245 remap_rules_with_normal; strided: ConvolutionRules.h:27-90).
+  bool guided = false;
+  DevBuf<float> normal;      // [n][3]
+  DevBuf<uint8_t> ori;       // [n] orientation class
+  DevBuf<int> nbr_g;         // [27][n_pad] forward table with the taps of every output row permuted by its class
+  DevBuf<int> nbr_t[3];      // [27][n_pad] per class c: tap k' -> the output row of class c this INPUT row feeds through weight tap k' (dgrad)
+  PairList nbr_g_pairs;      // rule lists of the guided table (weight gradients)
 };
 
 struct Meta {
@@ -171,6 +180,8 @@ struct Meta {
   const float *hint_src = nullptr;
   void *hint_bf16 = nullptr;
   int hint_ready = 0;
+  const float *point_normals = nullptr;   // scn_input_normals(): [P,3] normals of the points of the next scn_input_layer_build
+  int normal_guide_scale = 1 << 30;        // strided layers propagate normals / permute taps only from scales >= this size
   double *next_stats = nullptr;   // scn_out_stats(): column statistics wanted from the next scn_conv_fwd / scn_deconv_fwd (one use)
   int next_dilation = 1;     // scn_subm_dilation(): dilation of the next submanifold entry (one use)
   long long next_grad_ld = 0;  // scn_grad_stride(): row stride (floats) of d_out of the next backward entry (one use; 0 = dense)
@@ -190,6 +201,7 @@ void build_input_level(Meta *m, const int64_t size[3], const int64_t *coords, bo
                        int mode, cudaStream_t s);
 void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s);
 Level *dilated_level(Meta *m, Level *L, int rate, cudaStream_t s);    // rate 1 = L itself; table built on return
+void ensure_guided_tables(Meta *m, Level *L, cudaStream_t s);          // nbr_g / nbr_t of a scale that carries normals
 constexpr int SORT_BLOCK_DEFAULT = 262144;
 bool tile_sort_enabled();
 int set_tile_sort(int block);   // returns the previous setting
@@ -257,6 +269,7 @@ void transpose_weight(const float *src, float *dst, int V, int c_in, int c_out, 
 void transpose_weight_bf16(const float *src, uint16_t *dst, int V, int c_in, int c_out, cudaStream_t s);
 // bf16 operand copies (round to nearest even): dst[i] = bf16(src[i]); n must be even
 void cast_bf16(const float *src, uint16_t *dst, long long n, cudaStream_t s);
+void axpy(const float *x, float *y, long long n, cudaStream_t s);     // y += x
 // the same from a row-strided source (rows `ld` floats apart) into a dense copy
 void cast_bf16_rows(const float *src, long long ld, long long rows, int cols, uint16_t *dst, cudaStream_t s);
 

@@ -285,6 +285,18 @@ void transpose_weight(const float *src, float *dst, int V, int c_in, int c_out, 
   SCN_LAUNCH_CHECK();
 }
 
+// y += x
+__global__ void k_axpy(const float *__restrict__ x, float *__restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += x[i];
+}
+void axpy(const float *x, float *y, long long n, cudaStream_t s) {
+  if (n == 0) return;
+  long long g = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  k_axpy<<<(int)(g > cap ? cap : g), 256, 0, s>>>(x, y, n);
+  SCN_LAUNCH_CHECK();
+}
+
 // fp32 -> bf16 (round to nearest even), 8 elements per thread
 __global__ void k_cast_bf16(const float *__restrict__ src, uint16_t *__restrict__ dst, long long n8, long long n) {
   auto cvt2 = [](float lo, float hi) -> uint32_t {

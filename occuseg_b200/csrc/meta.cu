@@ -94,6 +94,110 @@ __global__ void k_link_levels(const int *__restrict__ run_ptr, const int *__rest
 }
 
 // -----------------------------------------------------------------------------------------------------
+// normal-guided rules
+// -----------------------------------------------------------------------------------------------------
+// tap permutations per orientation class: SubmanifoldRules_cuda.cu:8-15 (27 taps), ConvolutionRules.h:28-33 (8 taps)
+__device__ __constant__ unsigned char c_rot27[27 * 6] = {
+    0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,
+    24,25,26,21,22,23,18,19,20,15,16,17,12,13,14,9,10,11,6,7,8,3,4,5,0,1,2,
+    6,7,8,15,16,17,24,25,26,3,4,5,12,13,14,21,22,23,0,1,2,9,10,11,18,19,20,
+    18,19,20,9,10,11,0,1,2,21,22,23,12,13,14,3,4,5,24,25,26,15,16,17,6,7,8,
+    2,11,20,5,14,23,8,17,26,1,10,19,4,13,22,7,16,25,0,9,18,3,12,21,6,15,24,
+    18,9,0,21,12,3,24,15,6,19,10,1,22,13,4,25,16,7,20,11,2,23,14,5,26,17,8};
+__device__ __constant__ unsigned char c_rot8[8 * 6] = {0,1,2,3,4,5,6,7, 6,7,4,5,2,3,0,1, 2,3,6,7,0,1,4,5,
+                                                       4,5,0,1,6,7,2,3, 1,5,3,7,0,4,2,6, 4,0,6,2,5,1,7,3};
+
+// OrientedFilter, Metadata/RectangularRegions.h:12-31: the dominant axis of the normal -> class 0 (x), 2 (y), 4 (z)
+__device__ __forceinline__ int oriented_filter(float nx, float ny, float nz) {
+  const float x = fabsf(nx), y = fabsf(ny), z = fabsf(nz);
+  if (x >= y && x >= z) return 0;
+  if (y >= x && y >= z) return 2;
+  if (z >= x && z >= y) return 4;
+  return 0;
+}
+__device__ __forceinline__ void normalize3(float &x, float &y, float &z) {      // Float3::normalize, Metadata.h:94-100
+  // no fused multiply-add: the host code this mirrors rounds every product and sum
+  float mag = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+  if (mag < 1e-8f) return;
+  mag = __fdiv_rn(1.f, mag);
+  x *= mag; y *= mag; z *= mag;
+}
+
+// per-voxel normal = normalised mean of its points' normals, summed in rule order (CUDA/IOLayers.cpp:39-66)
+__global__ void k_voxel_normals(const float *__restrict__ pn, const int *__restrict__ rule_ptr, const int *__restrict__ rule_pts,
+                                int n, float *__restrict__ normal, uint8_t *__restrict__ ori) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  float x = 0.f, y = 0.f, z = 0.f;
+  const int b = rule_ptr[r], e = rule_ptr[r + 1];
+  for (int j = b; j < e; ++j) {
+    const float *q = pn + 3ll * rule_pts[j];
+    x += q[0]; y += q[1]; z += q[2];
+  }
+  if (e > b) { x = __fdiv_rn(x, (float)(e - b)); y = __fdiv_rn(y, (float)(e - b)); z = __fdiv_rn(z, (float)(e - b)); }
+  normalize3(x, y, z);
+  normal[3 * r] = x; normal[3 * r + 1] = y; normal[3 * r + 2] = z;
+  ori[r] = (uint8_t)oriented_filter(x, y, z);
+}
+
+// coarse normal = normalised mean of the children's normals (ConvolutionRules.h:56-72); then the 8 taps of the coarse row are
+// permuted by its class (:80-88) -- in place in the child table, with the offsets of the children updated to match
+__global__ void k_coarse_normals_and_taps(const float *__restrict__ fine_normal, int nc, int child_stride, int *__restrict__ child,
+                                          uint8_t *__restrict__ off8, float *__restrict__ normal, uint8_t *__restrict__ ori) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nc) return;
+  int c[8];
+  float x = 0.f, y = 0.f, z = 0.f;
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    c[k] = child[k * child_stride + p];
+    if (c[k] >= 0) {
+      x += fine_normal[3 * c[k]]; y += fine_normal[3 * c[k] + 1]; z += fine_normal[3 * c[k] + 2];
+      ++cnt;
+    }
+  }
+  if (cnt > 0) { x = __fdiv_rn(x, (float)cnt); y = __fdiv_rn(y, (float)cnt); z = __fdiv_rn(z, (float)cnt); }
+  normalize3(x, y, z);
+  normal[3 * p] = x; normal[3 * p + 1] = y; normal[3 * p + 2] = z;
+  const int o = oriented_filter(x, y, z);
+  ori[p] = (uint8_t)o;
+  int t[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t[k] = -1;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int k2 = c_rot8[o * 8 + k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j == k2) t[j] = c[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    child[k * child_stride + p] = t[k];
+    if (t[k] >= 0) off8[t[k]] = (uint8_t)k;
+  }
+}
+
+// guided tables of a scale: forward nbr_g[rot[ori(o)][k]][o] = nbr[k][o]; dgrad, per class c, nbr_t[c][rot[c][k]][i] = the output
+// row o = nbr[26-k][i] (the row for which i sits at offset k) if ori(o) == c
+__global__ void k_guide_tables(const int *__restrict__ nbr, const uint8_t *__restrict__ ori, int n, int stride,
+                               int *__restrict__ nbr_g, int *__restrict__ t0, int *__restrict__ t1, int *__restrict__ t2) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int c = ori[r];
+  for (int k = 0; k < 27; ++k) {
+    nbr_g[(long long)c_rot27[c * 27 + k] * stride + r] = nbr[(long long)k * stride + r];
+    const int o = nbr[(long long)(26 - k) * stride + r];
+    if (o >= 0) {
+      const int co = ori[o];
+      int *t = co == 0 ? t0 : co == 2 ? t1 : t2;
+      t[(long long)c_rot27[co * 27 + k] * stride + r] = o;
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------
 // open-addressing hash (linear probing, load <= 0.5).  Replaces cudpp's cuckoo tables
 // (extra/cudpp/src/cudpp_hash/hash_table.cuh:94-295): no stash, no rebuild loop, one CAS per insert.
 // -----------------------------------------------------------------------------------------------------
@@ -380,6 +484,14 @@ void build_input_level(Meta *m, const int64_t size[3], const int64_t *coords, bo
   runs.sorted_idx.p = nullptr;
   runs.sorted_idx.n = 0;
 
+  if (m->point_normals) {          // scn_input_normals(): this batch carries surface normals
+    L->normal.alloc((size_t)3 * L->n, s);
+    L->ori.alloc((size_t)L->n, s);
+    k_voxel_normals<<<grid_for(L->n, 256), 256, 0, s>>>(m->point_normals, m->rule_ptr.p, m->rule_pts.p, L->n, L->normal.p, L->ori.p);
+    SCN_LAUNCH_CHECK();
+    L->guided = true;
+    m->point_normals = nullptr;
+  }
   keys.release(s);
   idx.release(s);
   err.release(s);
@@ -511,6 +623,24 @@ void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
   cnt.release(s);
 }
 
+void ensure_guided_tables(Meta *m, Level *L, cudaStream_t s) {
+  if (L->nbr_g.p || !L->guided) return;
+  ensure_neighbour_table(m, L, s);
+  const size_t sz = (size_t)27 * L->n_pad;
+  ProfScope ps(PK_RULEBOOK, (2.0 * 27 * 4 + 4.0 * 27 * 4 + 1) * (double)L->n, 0.0, s);
+  L->nbr_g.alloc(sz, s);
+  SCN_CUDA(cudaMemsetAsync(L->nbr_g.p, 0xFF, sizeof(int) * sz, s));
+  for (int c = 0; c < 3; ++c) {
+    L->nbr_t[c].alloc(sz, s);
+    SCN_CUDA(cudaMemsetAsync(L->nbr_t[c].p, 0xFF, sizeof(int) * sz, s));
+  }
+  if (L->n) {
+    k_guide_tables<<<grid_for(L->n, 256), 256, 0, s>>>(L->nbr.p, L->ori.p, L->n, L->n_pad, L->nbr_g.p, L->nbr_t[0].p,
+                                                       L->nbr_t[1].p, L->nbr_t[2].p);
+    SCN_LAUNCH_CHECK();
+  }
+}
+
 Level *dilated_level(Meta *m, Level *L, int rate, cudaStream_t s) {
   SCN_CHECK(rate >= 1 && rate < 4096, "SubmanifoldConvolution: bad dilation rate");
   Level *D = L;
@@ -564,6 +694,14 @@ Level *ensure_coarse_level(Meta *m, Level *F, const int64_t coarse_size[3], cuda
   k_link_levels<<<grid_for(F->n, 256), 256, 0, s>>>(runs.ptr.p, runs.sorted_idx.p, F->keys.p, C->n, F->n, C->n_pad,
                                                     F->parent.p, F->off8.p, F->child.p);
   SCN_LAUNCH_CHECK();
+  if (F->guided && F->size[0] >= m->normal_guide_scale) {     // ConvolutionRules.h:774: below the guide scale the plain rules are used
+    C->normal.alloc((size_t)3 * C->n, s);
+    C->ori.alloc((size_t)C->n, s);
+    k_coarse_normals_and_taps<<<grid_for(C->n, 256), 256, 0, s>>>(F->normal.p, C->n, C->n_pad, F->child.p, F->off8.p, C->normal.p,
+                                                                C->ori.p);
+    SCN_LAUNCH_CHECK();
+    C->guided = true;
+  }
   F->coarse = C;
   m->levels.push_back(C);
   ckeys.release(s);

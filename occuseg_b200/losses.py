@@ -75,3 +75,129 @@ def cluster_regression_losses(displacements, displacements_gt, occupancy, occupa
     per_sample_o = ((occ_err + occ_std).view(batch_size, n_inst) * fg).sum(1) / k.clamp_min(1)
     has = (k > 0).to(disp_err.dtype)
     return (per_sample_d * has).sum() / batch_size, (per_sample_o * has).sum() / batch_size
+
+
+# ---- the embedding losses of examples/ScanNet/discriminative.py, torch_scatter-free and without per-instance Python loops -----
+class DiscriminativeLoss(torch.nn.Module):
+    """discriminative.py:117-226 (the paths `forward` takes: _new_centroids, _new_variance, _distance, _regularization).
+    forward(embedded [B,P,E], instance_mask [B,P] long, dense 0-based ids) -> alpha*L_v + beta*L_d + gamma*L_r.
+    Same constructor and the same value as the reference; centroids come from one index_add per sample instead of
+    torch_scatter.scatter_mean."""
+
+    def __init__(self, delta_d, delta_v, alpha=1.0, beta=1.0, gamma=0.001, reduction='mean'):
+        super().__init__()
+        self.alpha, self.beta, self.gamma = alpha, beta, gamma
+        self.delta_d, self.delta_v = delta_d, delta_v
+
+    def forward(self, embedded, instance_mask):
+        B = embedded.size(0)
+        l_v = embedded.new_zeros(())
+        l_d = embedded.new_zeros(())
+        l_r = embedded.new_zeros(())
+        k_all = int(instance_mask.max().item()) + 1          # scatter_mean sizes every sample's centroid table alike (torch.stack)
+        for i in range(B):
+            e, ids = embedded[i], instance_mask[i].view(-1)
+            mu = segment_mean(e, ids, k_all)
+            n = int(ids.max().item()) + 1                    # size = max(instance_mask) + 1, :134
+            dev = (e - mu[ids]).norm(2, dim=1)
+            l_v = l_v + (torch.clamp(dev - self.delta_v, min=0.0) ** 2).mean()                       # :174-181
+            c = mu[:n]
+            if n > 1:                                                                                # :200-216
+                norm = (c.unsqueeze(1) - c.unsqueeze(0)).norm(2, dim=2)
+                margin = 2 * self.delta_d * (1.0 - torch.eye(n, device=c.device, dtype=c.dtype))
+                l_d = l_d + torch.sum(torch.clamp(margin - norm, min=0.0) ** 2) / float(n * (n - 1))
+            l_r = l_r + c.norm(2, dim=1).mean()                                                      # :218-226
+        return self.alpha * l_v + self.beta * (l_d / B) + self.gamma * (l_r / B)
+
+
+def ClassificationLoss(embedded, bw, regressed_pose, pose, instance_mask, pred_semantics, min_points=30):
+    """discriminative.py:41-114, same arguments ([B,P,*] tensors, instance_mask [B,P], pred_semantics [P] = the class of every
+    point of the -- single -- sample the caller passes), returns (loss [1], mean instance IoU).
+
+    Per instance with at least 30 points whose first point's class is > -1: the points closer to the instance's mean position than
+    4x its radius are classified as inside / outside by exp(-(|e - mu| * s1)^2 - (|q - c| * s2)^2) (mu, c = instance means of the
+    embedding / the position, s1, s2 = instance means of the two bandwidth channels, q = regressed position) with a BCE loss;
+    loss = 10 * mean over instances.  The reference loops over instances in Python; here every sample is one [K,P] problem."""
+    B = embedded.size(0)
+    dev = embedded.device
+    total = embedded.new_zeros(1)
+    miou = 0.0
+    count = 0
+    E = embedded.size(2)
+    for i in range(B):
+        ids = instance_mask[i].view(-1)
+        K = int(ids.max().item()) + 1
+        P = ids.numel()
+        volume = torch.cat((embedded[i], pose[i], bw[i], regressed_pose[i]), dim=1)
+        mean = segment_mean(volume, ids, K)
+        mu, centre, s1, s2 = mean[:, :E], mean[:, E:E + 3], mean[:, E + 3], mean[:, E + 4]
+        n_pts = segment_count(ids, K)
+        first = torch.full((K,), P, dtype=torch.long, device=dev).scatter_reduce(0, ids, torch.arange(P, device=dev), "amin")
+        cls = pred_semantics[first.clamp_max(P - 1)]
+        valid = (n_pts >= min_points) & (cls > -1) & (first < P)
+        if not bool(valid.any()):
+            continue
+        vk = torch.nonzero(valid).view(-1)
+        exact = "donot_use_mm_for_euclid_dist"
+        dist = torch.cdist(centre[vk], pose[i], compute_mode=exact)                                   # [k,P] |pose - mean_pose|
+        own = ids.view(1, -1) == vk.view(-1, 1)                                                       # [k,P] instance_indices
+        radius = torch.where(own, dist, dist.new_full((), float("-inf"))).max(dim=1).values
+        samples = dist < (radius * 4).view(-1, 1)
+        d1 = torch.cdist(mu[vk], embedded[i], compute_mode=exact) * s1[vk].view(-1, 1)
+        d2 = torch.cdist(centre[vk], regressed_pose[i], compute_mode=exact) * s2[vk].view(-1, 1)
+        prob = torch.exp(-d1 * d1 - d2 * d2)
+        bce = torch.nn.functional.binary_cross_entropy(prob, own.to(prob.dtype), reduction="none")
+        w = samples.to(prob.dtype)
+        total = total + ((bce * w).sum(1) / w.sum(1)).sum()
+        with torch.no_grad():
+            u = (prob > 0.5) & samples
+            tp = (u & own).sum(1).to(torch.float64)
+            fp = (u & ~own).sum(1).to(torch.float64)
+            tot = (own & samples).sum(1).to(torch.float64)
+            miou += float((tp / (tot + fp)).sum().item())
+        count += int(vk.numel())
+    if count > 0:
+        total = total / count * 10
+        miou = miou / count
+    return total, miou
+
+
+def calculate_cost(predictions, embeddings, offsets, displacements, bw, criterion, batch, occupancy, config):
+    """calculate_cost of examples/ScanNet/train_instance.py:186-255 on this module's pieces: same arguments (+ `config` for
+    'scale', 'dimension', 'regress_weight', 'displacement_weight', a module global there), same dictionary of losses.
+    `batch` as the reference's data loader builds it: 'x' = [coords [P,4], feats], 'y' [P,2] (semantic, instance), 'id',
+    'instance_masks' [P], 'instance_sizes' [P], 'displacements' [P,3], 'offsets' [P,...]."""
+    dev = predictions.device
+    y = batch['y'].to(dev)
+    sem = y[:, 0]
+    coords = batch['x'][0].to(dev)
+    sample = coords[:, config['dimension']].long()
+    B = len(batch['id'])
+    inst = batch['instance_masks'].to(dev).long()
+    pose = coords[:, 0:3].to(displacements.dtype) / config['scale']
+    regressed_pose = pose - displacements
+    displacements_gt = batch['displacements'].to(dev)
+    occupancy_gt = batch['instance_sizes'].to(dev).view(-1, 1)
+    out = {}
+    out['semantic_loss'] = criterion['nll'](predictions, sem)
+    emb = predictions.new_zeros(1)
+    cls_loss = predictions.new_zeros(1)
+    iou = predictions.new_zeros(1)
+    for b in range(B):
+        idx = sample == b
+        e = embeddings[idx].unsqueeze(0)
+        im = inst[idx].view(1, -1)
+        emb = emb + criterion['discriminative'](e, im)
+        lc, ii = ClassificationLoss(e, bw[idx].view(1, -1, 2), regressed_pose[idx].unsqueeze(0), pose[idx].unsqueeze(0), im, sem[idx])
+        cls_loss = cls_loss + lc
+        iou = iou + ii
+    d_loss, o_loss = cluster_regression_losses(displacements, displacements_gt, occupancy, occupancy_gt, inst, sample, sem, B)
+    fg = sem > 1
+    out['embedding_loss'] = emb / B
+    out['regression_loss'] = criterion['regression'](offsets[fg], batch['offsets'].to(dev)[fg]) * config['regress_weight']
+    out['displacement_loss'] = d_loss.view(1)
+    out['classification_loss'] = cls_loss / B
+    out['drift_loss'] = predictions.new_zeros(1)
+    out['instance_iou'] = iou / B
+    out['occupancy_loss'] = o_loss.view(1)
+    return out

@@ -194,8 +194,28 @@ class Metadata_3:
     def clear(self):
         self.__del__()
 
-    def setNormalGuideScale(self, v):          # normal-guided kernels are out of scope
+    def setNormalGuideScale(self, v):          # Metadata::setNormalGuideScale (Metadata.cpp:87, ConvolutionRules.h:774)
         self.normal_guide_scale = v
+
+    def guided(self, spatial_size):
+        """True when the scale carries per-voxel normals, i.e. its rules are tap-permuted by orientation class."""
+        return self._h is not None and bool(_lib.lib().scn_guided(self._h, _lib.size3(spatial_size)))
+
+    def normalsOf(self, spatial_size):
+        """(parity) float32 [N,3] CPU tensor: the per-voxel normals of a guided scale (Metadata::normals)."""
+        n = self.getNActive(spatial_size)
+        out = torch.empty((n, 3), dtype=torch.float32)
+        _lib.check(_lib.lib().scn_normals(self._handle(), _lib.size3(spatial_size), _stream(), _ptr(out)))
+        return out
+
+    def submanifoldGuidedTable(self, spatial_size):
+        """(parity) int32 [27,N] CPU tensor = the forward table with every output row's taps permuted by its orientation class,
+        and the classes uint8 [N]."""
+        n = self.getNActive(spatial_size)
+        out = torch.empty((27, n), dtype=torch.int32)
+        ori = torch.empty(n, dtype=torch.uint8)
+        _lib.check(_lib.lib().scn_subm_guided_table(self._handle(), _lib.size3(spatial_size), _stream(), _ptr(out), _ptr(ori)))
+        return out, ori
 
     def getNActive(self, spatial_size):
         return int(_lib.lib().scn_nactive(self._handle(), _lib.size3(spatial_size)))
@@ -269,7 +289,16 @@ def InputLayer_updateOutput(m, spatial_size, input_coords, input_features, outpu
     on_dev = coords.is_cuda
     n = C.c_int64(0)
     h = m._handle(feats.device.index)
+    # use_normal of CUDA/IOLayers.cpp:41-42: a 2-D tensor with one row per point switches the normal-guided rules on
+    nrm = None
+    if torch.is_tensor(input_normal) and input_normal.dim() == 2 and input_normal.size(0) == feats.size(0):
+        if input_normal.size(1) != 3:
+            raise ValueError("InputLayer: normals must be [P,3]")
+        nrm = input_normal.to(device=feats.device, dtype=torch.float32).contiguous()
     with _on(feats.device):
+        if nrm is not None:
+            scale = m.normal_guide_scale if m.normal_guide_scale is not None else 0
+            _lib.check(_lib.lib().scn_input_normals(h, _ptr(nrm), int(scale)))
         _lib.check(_lib.lib().scn_input_layer_build(h, _lib.size3(spatial_size), _ptr(coords), int(on_dev),
                                                     coords.size(0), int(batch_size), int(mode), _stream(), C.byref(n)))
         m._input_size = _lib.size3(spatial_size)[:]

@@ -84,7 +84,9 @@ def _fusable_training_pair(bn, conv, input):
             and bn.nPlanes == conv.nIn and getattr(conv, "dilated_rate", 1) == 1
             and conv.filter_volume == (27 if isinstance(conv, SubmanifoldConvolution) else 8)
             and not _has_hooks(bn) and not _has_hooks(conv) and input.features.size(0) > 1
-            and SCN.fuses_bn_conv(conv.nIn, conv.nOut))
+            and SCN.fuses_bn_conv(conv.nIn, conv.nOut)
+            # a normal-guided submanifold dgrad is three passes (one per orientation class): no single epilogue to fuse into
+            and not (isinstance(conv, SubmanifoldConvolution) and input.metadata.guided(input.spatial_size)))
 
 
 def _bn_conv_training(bn, conv, input, residual=None, with_alias=False):
@@ -227,8 +229,8 @@ class Identity(Module):
 
 # ---- IO -------------------------------------------------------------------------------------------------
 class InputLayer(Module):
-    """input = [coords [P,4] (x,y,z,batch; float or long), features [P,C] CUDA float, normals (ignored),
-    batch_size].  mode 3 sums, mode 4 averages the features of points sharing a voxel."""
+    """input = [coords [P,4] (x,y,z,batch; float or long), features [P,C] CUDA float, normals ([P,3] float: switches the
+    normal-guided rules on, as in the reference; None or any other shape: plain rules), batch_size].  mode 3 sums, mode 4 averages the features of points sharing a voxel."""
 
     def __init__(self, dimension, spatial_size, mode=3, normal_guide_scale=10240):
         super().__init__()

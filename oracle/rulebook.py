@@ -222,3 +222,92 @@ def resolution_scatter(points_lr, points_hr, stride):
     pos_c = np.minimum(pos, max(len(uk) - 1, 0))
     hit = (uk[pos_c] == q) if len(uk) else np.zeros(len(q), bool)
     return np.where(hit, pos_c, NOT_FOUND).astype(np.int32)
+
+
+# ---- normal-guided rules (OccuSeg's `use_normal`) --------------------------------------------------------------------
+# tap permutation per orientation class: Metadata/SubmanifoldConvolutionRules.h:217-223 (27 taps, x-outermost numbering) and
+# Metadata/ConvolutionRules.h:28-33 (8 taps); row = class (only 0, 2, 4 are ever produced by OrientedFilter)
+ROT27 = np.array([
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26,
+    24, 25, 26, 21, 22, 23, 18, 19, 20, 15, 16, 17, 12, 13, 14, 9, 10, 11, 6, 7, 8, 3, 4, 5, 0, 1, 2,
+    6, 7, 8, 15, 16, 17, 24, 25, 26, 3, 4, 5, 12, 13, 14, 21, 22, 23, 0, 1, 2, 9, 10, 11, 18, 19, 20,
+    18, 19, 20, 9, 10, 11, 0, 1, 2, 21, 22, 23, 12, 13, 14, 3, 4, 5, 24, 25, 26, 15, 16, 17, 6, 7, 8,
+    2, 11, 20, 5, 14, 23, 8, 17, 26, 1, 10, 19, 4, 13, 22, 7, 16, 25, 0, 9, 18, 3, 12, 21, 6, 15, 24,
+    18, 9, 0, 21, 12, 3, 24, 15, 6, 19, 10, 1, 22, 13, 4, 25, 16, 7, 20, 11, 2, 23, 14, 5, 26, 17, 8], np.int64).reshape(6, 27)
+ROT8 = np.array([0, 1, 2, 3, 4, 5, 6, 7, 6, 7, 4, 5, 2, 3, 0, 1, 2, 3, 6, 7, 0, 1, 4, 5,
+                 4, 5, 0, 1, 6, 7, 2, 3, 1, 5, 3, 7, 0, 4, 2, 6, 4, 0, 6, 2, 5, 1, 7, 3], np.int64).reshape(6, 8)
+
+
+def oriented_filter(normals):
+    """OrientedFilter, Metadata/RectangularRegions.h:12-31: class 0 / 2 / 4 = dominant axis x / y / z of the normal, ties
+    resolved in that order.  Vectorised over [N,3]."""
+    a = np.abs(np.asarray(normals, np.float32).reshape(-1, 3))
+    x, y, z = a[:, 0], a[:, 1], a[:, 2]
+    return np.where((x >= y) & (x >= z), 0, np.where((y >= x) & (y >= z), 2, np.where((z >= x) & (z >= y), 4, 0))).astype(np.uint8)
+
+
+def _normalize(v):
+    """Float3::normalize, Metadata/Metadata.h:94-100, in fp32 step by step (no fused multiply-add)."""
+    v = np.asarray(v, np.float32)
+    mag = np.sqrt(((v[:, 0] * v[:, 0]).astype(np.float32) + (v[:, 1] * v[:, 1]).astype(np.float32)).astype(np.float32)
+                  + (v[:, 2] * v[:, 2]).astype(np.float32)).astype(np.float32)
+    ok = ~(mag < 1e-8)
+    inv = np.ones_like(mag)
+    inv[ok] = np.float32(1) / mag[ok]
+    return np.where(ok[:, None], (v * inv[:, None]).astype(np.float32), v).astype(np.float32)
+
+
+def voxel_normals(point_normals, vox):
+    """Per-voxel normal of InputLayer_updateOutput, CUDA/IOLayers.cpp:39-66: the points' normals summed in rule order (fp32),
+    divided by the count, normalised."""
+    pn = np.asarray(point_normals, np.float32).reshape(-1, 3)
+    ptr, pts = vox["rule_ptr"], vox["rule_pts"]
+    N = len(ptr) - 1
+    cnt = np.diff(ptr)
+    acc = np.zeros((N, 3), np.float32)
+    for j in range(int(cnt.max()) if N else 0):
+        m = cnt > j
+        acc[m] = (acc[m] + pn[pts[ptr[:-1][m] + j]]).astype(np.float32)
+    nz = cnt > 0
+    acc[nz] = (acc[nz] / cnt[nz, None].astype(np.float32)).astype(np.float32)
+    return _normalize(acc)
+
+
+def guided_submanifold_rules(rule_lists, normals):
+    """remap_rules_with_normal, Metadata/SubmanifoldConvolutionRules.h:213-245, applied to the GPU builder's lists (the GPU
+    path, :486-490): the rule (in, out) of tap k moves to tap ROT27[class(normal[out])][k]; lists are visited in tap order, so
+    every new list keeps (old tap, out) order."""
+    ori = oriented_filter(normals)
+    new = [[] for _ in range(27)]
+    for k, r in enumerate(rule_lists):
+        r = np.asarray(r, np.int32).reshape(-1, 2)
+        tgt = ROT27[ori[r[:, 1]], k]
+        for t in np.unique(tgt):
+            new[int(t)].append(r[tgt == t])
+    return [np.concatenate(l, 0) if l else np.zeros((0, 2), np.int32) for l in new]
+
+
+def guided_strided_rules(locs, normals, batch_size=None):
+    """Normal-guided size-2 / stride-2 rules, Metadata/ConvolutionRules.h:18-92 (the CPU builder; its GPU variant, :139-236,
+    advances its query index twice per rule and is not restated): coarse normal = normalised mean of the children's normals
+    (:56,:74-75), the rule (fine, coarse) of tap k moves to tap ROT8[class(coarse normal)][k] (:80-88).  The reference sums the
+    children in hash-map iteration order (unspecified); here, and in the CUDA builder, in ascending tap order.
+
+    Returns (coarse_locs, 8 rule lists, coarse normals float32 [Nc,3])."""
+    coarse_locs, lists = strided_rules(locs, batch_size)
+    nrm = np.asarray(normals, np.float32).reshape(-1, 3)
+    nc = len(coarse_locs)
+    acc = np.zeros((nc, 3), np.float32)
+    cnt = np.zeros(nc, np.int64)
+    for r in lists:                                 # a coarse voxel has at most one child per tap: no repeated index in one step
+        acc[r[:, 1]] = (acc[r[:, 1]] + nrm[r[:, 0]]).astype(np.float32)
+        cnt[r[:, 1]] += 1
+    acc = (acc / np.maximum(cnt, 1)[:, None].astype(np.float32)).astype(np.float32)
+    cn = _normalize(acc)
+    ori = oriented_filter(cn)
+    new = [[] for _ in range(8)]
+    for k, r in enumerate(lists):
+        tgt = ROT8[ori[r[:, 1]], k]
+        for t in np.unique(tgt):
+            new[int(t)].append(r[tgt == t])
+    return coarse_locs, [np.concatenate(l, 0) if l else np.zeros((0, 2), np.int32) for l in new], cn

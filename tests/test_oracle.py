@@ -223,3 +223,68 @@ def test_dilated_rules_pinned_to_reference_compiled_builder(rate):
     assert not np.array_equal(plain, mine)
     off = mine[:, 1:4] - mine[:, 4:7]
     assert set(np.unique(np.abs(off)).tolist()) <= {0, rate}
+
+
+def _dyadic_normals(rng, n):
+    """Normals with small integer components: every partial sum is exact in fp32, so the summation order (hash-map iteration
+    order in the reference's strided builder) cannot matter, and ties |x| == |y| are frequent (the tie rule is exercised)."""
+    v = rng.integers(-3, 4, (n, 3)).astype(np.float32)
+    v[(v == 0).all(1)] = (0, 0, 1)
+    return v
+
+
+def test_normal_guided_restatement_pinned_to_reference_builders():
+    """oracle/rulebook.py's normal-guided rules == the reference's remap_rules_with_normal applied to GPU-ordered lists
+    (SubmanifoldConvolutionRules.h:213-245,486-490), == its CPU normal-guided builder (:159-209), and the guided 2/2 rules ==
+    Convolution_InputSgToRulesAndOutputSg with normals (ConvolutionRules.h:18-92), coarse normals included."""
+    from oracle import rules_ref as rr
+    if not rr.available():
+        pytest.skip("oracle/_ref/scn_rules_ref.so not available")
+    from occuseg_b200 import scenes
+    rng = np.random.default_rng(5)
+    c, _ = scenes.make_batch("tiny", (2, 3))
+    c = np.concatenate([c, c[:11]], 0)
+    c = c[np.argsort(c[:, 3], kind="stable")]
+    B = 2
+    v = rb.voxelize(c, B)
+    locs = v["locs"]
+    pn = _dyadic_normals(rng, len(c))
+    vn = rb.voxel_normals(pn, v)
+    sc = rr.Scene(c, B, 4)
+    row_of = {tuple(l): i for i, l in enumerate(locs.tolist())}
+    mine_of_ref = np.array([row_of[tuple(l)] for l in sc.locs.tolist()])
+    vn_ref_order = vn[mine_of_ref]
+    # the orientation classes agree with the reference's OrientedFilter
+    ori = rb.oriented_filter(vn)
+    assert all(rr.oriented_filter(vn[i]) == ori[i] for i in range(0, len(vn), 7))
+    assert set(np.unique(ori).tolist()) == {0, 2, 4}
+    guided = rb.guided_submanifold_rules(rb.submanifold_rules(locs, B), vn)
+    mine = rr.relation_of_lists(guided, locs)
+    assert np.array_equal(sc.submanifold(3, normals=vn_ref_order), mine)
+    assert np.array_equal(sc.submanifold(1, normals=vn_ref_order), mine)
+    assert not np.array_equal(sc.submanifold(0), mine)              # the permutation does something
+    # strided.  The reference sums the children's normals in hash-map iteration order, so with general (normalised) fine
+    # normals the last bits of a coarse normal -- and with them the class of a coarse voxel whose two largest components tie
+    # -- depend on that order: (a) integer-valued fine normals (every sum exact) must agree bit for bit, (b) general ones agree
+    # to 1e-6 and on every coarse voxel that is not within 1e-5 of a tie
+    crow = None
+    for fine_normals, exact in ((_dyadic_normals(rng, len(locs)), True), (vn, False)):
+        cl, lists, cn = rb.guided_strided_rules(locs, fine_normals, B)
+        rel, rcl, rcn = sc.strided(normals=fine_normals[mine_of_ref])
+        mine = rr.relation_of_lists(lists, locs, cl)
+        crow = {tuple(l): i for i, l in enumerate(cl.tolist())}
+        order = np.array([crow[tuple(l)] for l in rcl.tolist()])
+        if exact:
+            assert np.array_equal(rel, mine)
+            assert np.array_equal(rcn, cn[order])                    # coarse normals bit-identical
+            assert len(np.unique(rb.oriented_filter(cn))) == 3
+        else:
+            assert np.allclose(rcn, cn[order], rtol=0, atol=1e-6)
+            a = np.sort(np.abs(cn), 1)
+            tie = (a[:, 2] - a[:, 1]) < 1e-5
+            key = lambda r: r[np.lexsort(r[:, 1:].T[::-1])]          # the (fine, coarse) pairs are the same; only taps can differ
+            ra, rm = key(rel), key(mine)
+            assert np.array_equal(ra[:, 1:], rm[:, 1:])
+            coarse_row = np.array([crow[tuple(l)] for l in ra[:, 4:8].tolist()])
+            assert np.array_equal(ra[~tie[coarse_row], 0], rm[~tie[coarse_row], 0])
+            assert tie.sum() < 0.1 * len(cn)     # integer point normals make exact ties common (5 %)
