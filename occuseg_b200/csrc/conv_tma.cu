@@ -82,33 +82,25 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Waits pass a suspend-time hint to mbarrier.try_wait: the thread is parked by the hardware until the phase completes (or the
+// hint, 10 ms, runs out) instead of re-issuing the instruction.  Without it try_wait returns after a few cycles, and the spinning
+// waiters -- 110 M try_wait + branch pairs per level-0 launch (ncu source page, profiles/r01_ncu_l0_stalls.txt) -- took about
+// 30 % of the issue slots away from the producers' single-thread instruction chains.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
-      "}" ::"r"(bar), "r"(parity)
+      "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
       : "memory");
 }
-// long waits (epilogue warps): one lane polls with a back-off, the rest of the warp sleeps at the warp barrier
+// long waits (epilogue warps): one lane waits, the rest of the warp sleeps at the warp barrier
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
-  if (lane == 0) {
-    uint32_t done = 0;
-    while (true) {
-      asm volatile(
-          "{\n\t"
-          ".reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t"
-          "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-      if (done) break;
-      __nanosleep(256);
-    }
-  }
+  if (lane == 0) mbar_wait(bar, parity);
   __syncwarp();
 }
 __device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
@@ -307,6 +299,7 @@ struct ConvParams {
   // never enter the pipeline (NULL: all V taps are walked)
   const uint32_t *tile_mask;
   int n_tiles;
+  int dbg;                     // SCN_CONV_DBG (timing experiments only, results are WRONG): 1 = no weight-tile copies, 2 = MMAs of half the width, 4 = no MMAs, 8 = no epilogue stores, 16 = no row copies
   int prefetch;                // pull the next item's feature rows towards L2 (prefetch.global.L2) while the current one is issued
   unsigned long long *trace;   // SCN_TRACE=1: clock64 totals over all CTAs (debug only): see conv_tma()
 };
@@ -319,7 +312,8 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
   uint8_t *smem = smem_raw + (base - raw);
   uint4 *s_masks = reinterpret_cast<uint4 *>(smem + p.stages * p.stage_bytes);        // [stages][MAX_MT] present-row bits
   int4 *s_rows = reinterpret_cast<int4 *>(s_masks + 8 * MAX_MT);                       // [producer warps][MT*32/ni] gather groups each warp issues
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_rows + p.nprod * p.MT * 32);
+  uint32_t *s_words = reinterpret_cast<uint32_t *>(s_rows + p.nprod * p.MT * 32);      // [16 producer warps][MAX_MT * 4] present-row words of the item being prepared
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_words + 16 * 8);
   const uint32_t full_bar = smem_u32(bars);
   const uint32_t empty_bar = full_bar + 8 * p.stages;
   const uint32_t accf_bar = empty_bar + 8 * p.stages;       // [2] accumulator buffer complete
@@ -368,7 +362,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
   if (warp == 0) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
-      const uint32_t idesc = idesc_make(p.TN, 0, 0, p.bf16 != 0);
+      const uint32_t idesc = idesc_make((p.dbg & 2) ? p.TN / 2 : p.TN, 0, 0, p.bf16 != 0);
       int s = 0, gi = 0;
       uint32_t ph = 0;
       TRC(long long w_full = 0; long long w_acc = 0; long long n_tiles_mma = 0; long long t_mma = 0; long long t_commit = 0; const long long t_begin = clock64();)
@@ -390,7 +384,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
           TRC(const long long tm0 = clock64();)
           for (int m = 0; m < p.MT; ++m) {
             const uint4 pm = s_masks[s * MAX_MT + m];
-            if ((pm.x | pm.y | pm.z | pm.w) == 0u) continue;
+            if ((pm.x | pm.y | pm.z | pm.w) == 0u || (p.dbg & 4)) continue;
             TRC(++n_tiles_mma;)
             const uint64_t ad = desc_k128(st + m * A_STAGE);
             if (p.bf16) {
@@ -428,109 +422,85 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
     // enough (tools/ubench_pipe.cu); share 0 also posts the byte count, the masks and the weight tile.
     const int pw = (warp - 1) / p.ni, part = (warp - 1) % p.ni;
     {
-      const int chunks = p.MT * 4 / p.ni;            // 8-group chunks of this share
-      const int chunk0 = part * chunks;
-      int4 *my_rows = s_rows + (warp - 1) * chunks * 8 - chunk0 * 8;     // indexed by the item's gather-group number; only this share's groups are stored
-      // share 0 needs every row tile of the item (it publishes the masks and the byte count); the others only the
-      // row tile(s) their copies come from
-      const int m_lo = part == 0 ? 0 : chunk0 >> 2, m_hi = part == 0 ? p.MT - 1 : (chunk0 + chunks - 1) >> 2;
-      auto load_tbl = [&](int tg, int trow, int4 *dst) {
-#pragma unroll
-        for (int m = 0; m < MAX_MT; ++m) {
-          if (m >= m_lo && m <= m_hi) {
-            const int row = (tg * p.MT + m) * TM + 4 * lane;
-            dst[m] = row < p.tbl_stride ? __ldg(reinterpret_cast<const int4 *>(p.tbl + (long long)trow * p.tbl_stride + row))
-                                        : make_int4(-1, -1, -1, -1);
-          }
+      // Every share is self-contained and lies inside ONE row tile (ni = 4 shares, MT <= 2 tiles: a share owns MT consecutive
+      // 32-row chunks): it reads that tile's table row, publishes the present-row words of its chunks, posts its own byte count
+      // (arrive.expect_tx) and issues its copies; share 0 adds the weight tile.
+      // The loop is written for instruction count: an ncu source-level profile of the level-0 launch (round 2) showed the
+      // producers executing ~600 instructions per share and item -- 76 % of all instructions of the kernel, on single-thread
+      // dependency chains -- and the slots, never blocked on `empty`, setting the pace.  Hence: no division / modulo (the item
+      // iterator is incremental: remaining-taps mask + K-chunk counter), the group's gather list is COMPACTED by the lanes that
+      // own a present group (the elected lane walks a dense list instead of testing 8 x chunks predicates and reading every
+      // slot), and shares no longer read the other tile or build its masks.
+      const int m = (part * p.MT) >> 2;              // the row tile of this share
+      const int lane_lo = ((part * p.MT) & 3) * 8;   // lanes lane_lo .. lane_lo + 8*MT - 1 hold this share's gather groups
+      const bool own = lane >= lane_lo && lane < lane_lo + 8 * p.MT;
+      int4 *my_rows = s_rows + (warp - 1) * 8 * p.MT;                         // [8*MT] compacted gather groups of the item
+      uint32_t *my_words = s_words + (warp - 1) * 8;                          // [4] chunk words, then [16] destination slots (bytes)
+      uint8_t *my_dst = reinterpret_cast<uint8_t *>(my_words + 4);
+      auto load_tbl = [&](int tg_, int trow_) -> int4 {
+        const int row = (tg_ * p.MT + m) * TM + 4 * lane;
+        return row < p.tbl_stride ? __ldg(reinterpret_cast<const int4 *>(p.tbl + (long long)trow_ * p.tbl_stride + row))
+                                  : make_int4(-1, -1, -1, -1);
+      };
+      // ONE iterator, running two items of this slot ahead of the item being issued: tile group, the taps of the group still
+      // to come (lowest set bit = the item's table row), K chunk.  The tap mask of the following group is fetched when a group
+      // is entered, so that stepping into it does not wait for global memory.
+      int tgF = blockIdx.x, kcF = 0;
+      uint32_t gmF = group_mask(tgF), gkN = group_mask(tgF + G);
+      auto skip_empty = [&]() {
+        while (!gmF && tgF < p.n_groups) {
+          tgF += G;
+          gmF = gkN;
+          gkN = group_mask(tgF + G);
         }
       };
-      // item i -> (tile group, index inside the group); this slot's items are i = pw, pw + nprod, ...
-      auto settle = [&](int &tg_, int &j_, uint32_t &gm_) {
-        while (tg_ < p.n_groups) {
-          const int n = __popc(gm_) * KC;
-          if (j_ < n) break;
-          j_ -= n;
-          tg_ += G;
-          gm_ = group_mask(tg_);
+      auto step = [&](int n) {           // n items on
+        for (int i = 0; i < n && tgF < p.n_groups; ++i) {
+          if (++kcF < KC) continue;
+          kcF = 0;
+          gmF &= gmF - 1u;
+          skip_empty();
         }
       };
-      auto advance = [&](int &tg_, int &j_, uint32_t &gm_) {
-        j_ += p.nprod;
-        settle(tg_, j_, gm_);
-      };
-      // table row of item j of a group: the (j / KC)-th present tap
-      auto tap_of = [&](uint32_t gm_, int j_) -> int {
-        for (int i = j_ / KC; i > 0; --i) gm_ &= gm_ - 1u;
-        return __ffs((int)gm_) - 1;
-      };
-      int tg = blockIdx.x, j = pw;
-      uint32_t gk = group_mask(tg);
-      settle(tg, j, gk);
+      skip_empty();
+      step(pw);
+      int tg = tgF, kc = kcF, trow = __ffs((int)gmF) - 1;
+      step(p.nprod);
+      int tg1 = tgF, kc1 = kcF, trow1 = __ffs((int)gmF) - 1;
       int s = pw;
       uint32_t ph = 1;                   // parity to wait for on the empty barrier (first pass: already free)
       TRC(long long w_empty = 0; long long t_issue = 0; long long n_items = 0; long long n_copies = 0; long long t_pre = 0;
           long long t_b = 0; long long t_ph[3]; t_ph[0] = t_ph[1] = t_ph[2] = 0; const long long t_begin = clock64();)
-      // Table rows are fetched TWO items ahead (they stream from HBM once per kernel), and the feature rows of the
-      // NEXT item are pulled towards L2 while the current one is issued: a gather that misses L2 holds a TMA
-      // request slot for a full HBM round trip, and the slots, not the bandwidth, are what runs out.
-      int4 cur[MAX_MT], nxt[MAX_MT], far[MAX_MT];
-#pragma unroll
-      for (int m = 0; m < MAX_MT; ++m) cur[m] = nxt[m] = far[m] = make_int4(-1, -1, -1, -1);
-      int tg1 = tg, j1 = j;
-      uint32_t gk1 = gk;
-      advance(tg1, j1, gk1);
-      if (tg < p.n_groups) load_tbl(tg, tap_of(gk, j), cur);
-      if (tg1 < p.n_groups) load_tbl(tg1, tap_of(gk1, j1), nxt);
-      const char *in_bytes = reinterpret_cast<const char *>(p.in);
-      const long long row_bytes = (long long)p.c_in * (p.bf16 ? 2 : 4);
+      int4 cur = make_int4(-1, -1, -1, -1), nxt = cur, far = cur;
+      if (tg < p.n_groups) cur = load_tbl(tg, trow);
+      if (tg1 < p.n_groups) nxt = load_tbl(tg1, trow1);
       while (tg < p.n_groups) {
         TRC(const long long t_top = clock64();)
-        const int trow = tap_of(gk, j), kc = j % KC;
-        int tg2 = tg1, j2 = j1;
-        uint32_t gk2 = gk1;
-        advance(tg2, j2, gk2);
-        if (tg2 < p.n_groups) load_tbl(tg2, tap_of(gk2, j2), far);
-        TRC(const long long t_p1 = clock64(); t_ph[0] += t_p1 - t_top;)
-        if (p.prefetch && tg1 < p.n_groups) {
-          const long long off = (long long)(j1 % KC) * 128;
-#pragma unroll
-          for (int m = 0; m < MAX_MT; ++m) {
-            const int c = m * 4 + (lane >> 3);          // this lane's 8-group chunk: only the share that will issue it prefetches
-            if (m < p.MT && c >= chunk0 && c < chunk0 + chunks) {
-              const int4 t = nxt[m];
-              if (t.x >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_bytes + t.x * row_bytes + off));
-              if (t.y >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_bytes + t.y * row_bytes + off));
-              if (t.z >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_bytes + t.z * row_bytes + off));
-              if (t.w >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(in_bytes + t.w * row_bytes + off));
-            }
-          }
+        step(p.nprod);
+        const int tg2 = tgF, kc2 = kcF, trow2 = __ffs((int)gmF) - 1;
+        if (tg2 < p.n_groups) far = load_tbl(tg2, trow2);
+        TRC(const long long t_p1 = clock64(); t_ph[0] += t_p1 - t_top; const long long t_p2 = t_p1;)
+        // present-row bits; absent rows repeat a present row of their 4-row gather group; groups with a row are compacted
+        int4 t = cur;
+        const uint32_t nib = (t.x >= 0 ? 1u : 0u) | (t.y >= 0 ? 2u : 0u) | (t.z >= 0 ? 4u : 0u) | (t.w >= 0 ? 8u : 0u);
+        const bool have = own && nib != 0u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, have);
+        // word q of the tile's mask = rows 32q .. 32q+31 = lanes 8q .. 8q+7: every lane ends up with the word of ITS chunk
+        uint32_t w8 = nib << (4 * (lane & 7));
+        w8 |= __shfl_xor_sync(0xffffffffu, w8, 1);
+        w8 |= __shfl_xor_sync(0xffffffffu, w8, 2);
+        w8 |= __shfl_xor_sync(0xffffffffu, w8, 4);
+        if (have) {
+          const int rep = t.x >= 0 ? t.x : t.y >= 0 ? t.y : t.z >= 0 ? t.z : t.w;
+          t.x = t.x >= 0 ? t.x : rep;
+          t.y = t.y >= 0 ? t.y : rep;
+          t.z = t.z >= 0 ? t.z : rep;
+          t.w = t.w >= 0 ? t.w : rep;
+          const int pos = __popc(bal & ((1u << lane) - 1u));
+          my_rows[pos] = t;
+          my_dst[pos] = (uint8_t)lane;
         }
-        TRC(const long long t_p2 = clock64(); t_ph[1] += t_p2 - t_p1;)
-        // present-row bits of every row tile; absent rows repeat a present row of their 4-row gather group
-        uint32_t gm[MAX_MT] = {0, 0}, any = 0;
-        uint4 pm[MAX_MT];
-#pragma unroll
-        for (int m = 0; m < MAX_MT; ++m) {
-          if (m >= m_lo && m <= m_hi) {
-            int4 t = cur[m];
-            const uint32_t nib = (t.x >= 0 ? 1u : 0u) | (t.y >= 0 ? 2u : 0u) | (t.z >= 0 ? 4u : 0u) | (t.w >= 0 ? 8u : 0u);
-            gm[m] = __ballot_sync(0xffffffffu, nib != 0u);
-            if (part == 0) {
-              const uint32_t sh = nib << (4 * (lane & 7));
-              pm[m].x = __reduce_or_sync(0xffffffffu, (lane >> 3) == 0 ? sh : 0u);
-              pm[m].y = __reduce_or_sync(0xffffffffu, (lane >> 3) == 1 ? sh : 0u);
-              pm[m].z = __reduce_or_sync(0xffffffffu, (lane >> 3) == 2 ? sh : 0u);
-              pm[m].w = __reduce_or_sync(0xffffffffu, (lane >> 3) == 3 ? sh : 0u);
-            }
-            const int rep = t.x >= 0 ? t.x : t.y >= 0 ? t.y : t.z >= 0 ? t.z : t.w;
-            t.x = t.x >= 0 ? t.x : rep;
-            t.y = t.y >= 0 ? t.y : rep;
-            t.z = t.z >= 0 ? t.z : rep;
-            t.w = t.w >= 0 ? t.w : rep;
-            if (m * 4 + (lane >> 3) >= chunk0 && m * 4 + (lane >> 3) < chunk0 + chunks) my_rows[m * 32 + lane] = t;
-            any |= gm[m];
-          }
-        }
+        if (own && (lane & 7) == 0) my_words[lane >> 3] = w8;
         TRC(const long long t_p3 = clock64(); t_ph[2] += t_p3 - t_p2;)
         __syncwarp();
         if (elect_one()) {          // elect.sync, not lane == 0: ptxas then keeps the copy operands in uniform registers (no vote loops)
@@ -538,57 +508,41 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
           mbar_wait(empty_bar + 8 * s, ph);
           TRC(const long long ti = clock64(); w_empty += ti - tw; ++n_items;)
           const uint32_t st = base + s * p.stage_bytes;
-          if (part == 0) {
-            int groups = 0;
-#pragma unroll
-            for (int m = 0; m < MAX_MT; ++m)
-              if (m < p.MT) {
-                s_masks[s * MAX_MT + m] = pm[m];
-                groups += __popc(gm[m]);
-              }
-            mbar_expect_tx(full_bar + 8 * s, any ? (uint32_t)(p.b_stage + groups * 512) : 0u);
-            if (any) {
-              int wtap = p.mirror ? p.V - 1 - trow : trow;
-              if (p.item_off) {           // tile groups are tap-pure: the tap whose item range holds this group
-                const int item = (tg * p.MT * TM) / p.rows_per_item;
-                wtap = 0;
-                for (int k = 1; k < p.n_taps; ++k) wtap += (__ldg(&p.item_off[k]) <= item) ? 1 : 0;
-              }
-              tma_tile_2d(st + p.MT * A_STAGE, &map_w, kc * p.kelems, wtap * p.c_out + n0, full_bar + 8 * s);
+          int count = __popc(bal);
+          uint32_t *mw = reinterpret_cast<uint32_t *>(s_masks + s * MAX_MT + m);
+          for (int q = lane_lo >> 3; q < (lane_lo >> 3) + p.MT; ++q) mw[q] = my_words[q];
+          if (p.dbg & 16) count = 0;
+          const uint32_t bytes = (uint32_t)(count * 512) + ((part == 0 && !(p.dbg & 1)) ? (uint32_t)p.b_stage : 0u);
+          if (bytes) mbar_expect_tx(full_bar + 8 * s, bytes);
+          else mbar_arrive(full_bar + 8 * s);
+          if (part == 0 && !(p.dbg & 1)) {
+            int wtap = p.mirror ? p.V - 1 - trow : trow;
+            if (p.item_off) {           // tile groups are tap-pure: the tap whose item range holds this group
+              const int item = (tg * p.MT * TM) / p.rows_per_item;
+              wtap = 0;
+              for (int k = 1; k < p.n_taps; ++k) wtap += (__ldg(&p.item_off[k]) <= item) ? 1 : 0;
             }
+            tma_tile_2d(st + p.MT * A_STAGE, &map_w, kc * p.kelems, wtap * p.c_out + n0, full_bar + 8 * s);
             TRC(t_b += clock64() - ti;)
           }
-          for (int c = chunk0; c < chunk0 + chunks; ++c) {
-            const int m = c >> 2, q = c & 3;
-            uint32_t gmm = gm[0];
-#pragma unroll
-            for (int mm = 1; mm < MAX_MT; ++mm)
-              if (mm == m) gmm = gm[mm];
-            const uint32_t g8 = (gmm >> (8 * q)) & 0xFFu;
-            if (!g8) continue;
-            TRC(n_copies += __popc(g8);)
-            int4 r[8];
-#pragma unroll
-            for (int g = 0; g < 8; ++g) r[g] = my_rows[c * 8 + g];
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              if ((g8 >> g) & 1u)
-                tma_gather4(st + c * 8 * 512 + g * 512, &map_x, kc * p.kelems, r[g].x, r[g].y, r[g].z, r[g].w, full_bar + 8 * s);
+          TRC(n_copies += count;)
+          const uint32_t a0 = st + m * A_STAGE;
+          const int col = kc * p.kelems;
+#pragma unroll 2
+          for (int i = 0; i < count; ++i) {
+            const int4 r = my_rows[i];
+            tma_gather4(a0 + (uint32_t)my_dst[i] * 512u, &map_x, col, r.x, r.y, r.z, r.w, full_bar + 8 * s);
           }
-          if (part != 0) mbar_arrive(full_bar + 8 * s);
           TRC(t_issue += clock64() - ti;)
         }
         __syncwarp();
-#pragma unroll
-        for (int m = 0; m < MAX_MT; ++m) {
-          cur[m] = nxt[m];
-          nxt[m] = far[m];
-        }
-        tg = tg1; j = j1; gk = gk1;
-        tg1 = tg2; j1 = j2; gk1 = gk2;
+        cur = nxt;
+        nxt = far;
+        tg = tg1; kc = kc1; trow = trow1;
+        tg1 = tg2; kc1 = kc2; trow1 = trow2;
         s += p.nprod;
         if (s >= p.stages) { s -= p.stages; ph ^= 1u; }
-            }
+      }
       TRC(if (p.trace && lane == 0 && pw == 0) {
         unsigned long long *t = p.trace + 4 + 8 * part;
         atomicAdd(t + 0, (unsigned long long)(clock64() - t_begin));
@@ -698,7 +652,7 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
             const int row = 8 * it + rg;
             const int r = r4[it];
             float4 o = my_t[row * 4 + (cj ^ ((row >> 1) & 3))];
-            if (r >= 0) {
+            if (r >= 0 && !(p.dbg & 8)) {
               const long long at = (long long)r * p.c_out + col;
               if (p.bias) { o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w; }
               if (p.residual) {
@@ -1030,20 +984,20 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   p.MT = mt;
   p.stage_bytes = p.MT * A_STAGE + p.b_stage;
   // alignment slack + masks + producers' gather groups (4 owner slots x MT x 32 int4) + barriers + transpose tiles of the epilogue warps
-  const int fixed = 1024 + 8 * MAX_MT * 16 + 4 * p.MT * 32 * 16 + 8 * (2 * 8 + 4) + 64 + EPI_WARPS * 2048 + EPI_WARPS * 2048;
+  const int fixed = 1024 + 8 * MAX_MT * 16 + 4 * p.MT * 32 * 16 + 512 + 8 * (2 * 8 + 4) + 64 + EPI_WARPS * 2048 + EPI_WARPS * 2048;
   static const int smem_kb = env_int("SCN_CONV_SMEM_KB", 227);
   int st = (smem_kb * 1024 - fixed) / p.stage_bytes;
   if (st > 8) st = 8;
   SCN_CHECK(st >= 2, "conv_tma: shared memory budget");
   p.stages = st;
   p.nprod = st < 4 ? st : 4;
-  static const int force_ni = env_int("SCN_CONV_NI", 0);
-  p.ni = force_ni > 0 ? force_ni : 4;
-  while (p.ni > 1 && ((p.MT * 4) % p.ni != 0 || p.nprod * p.ni > 16)) p.ni >>= 1;
+  p.ni = 4;                          // shares per item: each owns MT consecutive 32-row chunks of one row tile
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.MT * p.TN) p.tmem_cols <<= 1;
   p.n_groups = (tiles + p.MT - 1) / p.MT;
   p.n_tiles = tiles;
+  static const int dbg = env_int("SCN_CONV_DBG", 0);
+  p.dbg = dbg;
   static const int prefetch = env_int("SCN_CONV_PREFETCH", 0);
   p.prefetch = prefetch;
   const size_t smem = (size_t)fixed + (size_t)p.stages * p.stage_bytes;
