@@ -268,7 +268,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
 // the same step time within noise, and 800 threads leave only 72 registers per thread
 constexpr int EPI_WARPS = 4;
 constexpr int EPI_SPLIT = EPI_WARPS / 4;
-constexpr int CONV_MAX_THREADS = 32 + 16 * 32 + 32 * EPI_WARPS;
+constexpr int MAX_PROD_WARPS = 16;     // 4 owner slots x 4 shares (5 slots = 800 threads: 72 registers, spills, measured 25 % slower)
+constexpr int CONV_MAX_THREADS = 32 + MAX_PROD_WARPS * 32 + 32 * EPI_WARPS;
 constexpr int MAX_MT = 2;
 
 struct ConvParams {
@@ -312,8 +313,8 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
   uint8_t *smem = smem_raw + (base - raw);
   uint4 *s_masks = reinterpret_cast<uint4 *>(smem + p.stages * p.stage_bytes);        // [stages][MAX_MT] present-row bits
   int4 *s_rows = reinterpret_cast<int4 *>(s_masks + 8 * MAX_MT);                       // [producer warps][MT*32/ni] gather groups each warp issues
-  uint32_t *s_words = reinterpret_cast<uint32_t *>(s_rows + p.nprod * p.MT * 32);      // [16 producer warps][MAX_MT * 4] present-row words of the item being prepared
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_words + 16 * 8);
+  uint32_t *s_words = reinterpret_cast<uint32_t *>(s_rows + p.nprod * p.MT * 32);      // [producer warps][8] present-row words + destination slots of the item being prepared
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_words + MAX_PROD_WARPS * 8);
   const uint32_t full_bar = smem_u32(bars);
   const uint32_t empty_bar = full_bar + 8 * p.stages;
   const uint32_t accf_bar = empty_bar + 8 * p.stages;       // [2] accumulator buffer complete
@@ -455,11 +456,19 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
         }
       };
       auto step = [&](int n) {           // n items on
-        for (int i = 0; i < n && tgF < p.n_groups; ++i) {
-          if (++kcF < KC) continue;
+        while (tgF < p.n_groups) {       // whole groups first
+          const int avail = __popc(gmF) * KC - kcF;      // items from the current one to the end of its group
+          if (n < avail) break;
+          n -= avail;
           kcF = 0;
+          tgF += G;
+          gmF = gkN;
+          gkN = group_mask(tgF + G);
+        }
+        kcF += n;
+        while (kcF >= KC) {              // at most n taps
+          kcF -= KC;
           gmF &= gmF - 1u;
-          skip_empty();
         }
       };
       skip_empty();
@@ -984,13 +993,15 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   p.MT = mt;
   p.stage_bytes = p.MT * A_STAGE + p.b_stage;
   // alignment slack + masks + producers' gather groups (4 owner slots x MT x 32 int4) + barriers + transpose tiles of the epilogue warps
-  const int fixed = 1024 + 8 * MAX_MT * 16 + 4 * p.MT * 32 * 16 + 512 + 8 * (2 * 8 + 4) + 64 + EPI_WARPS * 2048 + EPI_WARPS * 2048;
+  // alignment slack + masks + producers' gather lists (4 owner slots x MT x 32 int4) + their words + barriers + transpose tiles and
+  // statistics of the epilogue warps
+  const int fixed = 1024 + 8 * MAX_MT * 16 + 4 * p.MT * 32 * 16 + MAX_PROD_WARPS * 32 + 8 * (2 * 8 + 4) + 64 + EPI_WARPS * 2048 + EPI_WARPS * 2048;
   static const int smem_kb = env_int("SCN_CONV_SMEM_KB", 227);
   int st = (smem_kb * 1024 - fixed) / p.stage_bytes;
   if (st > 8) st = 8;
   SCN_CHECK(st >= 2, "conv_tma: shared memory budget");
   p.stages = st;
-  p.nprod = st < 4 ? st : 4;
+  p.nprod = st < 4 ? st : 4;                         // owner slots (<= stages: a parity wait can never be two phases off)
   p.ni = 4;                          // shares per item: each owns MT consecutive 32-row chunks of one row tile
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.MT * p.TN) p.tmem_cols <<= 1;
