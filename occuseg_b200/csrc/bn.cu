@@ -160,24 +160,37 @@ __global__ void __launch_bounds__(256) k_bn_apply_fwd(const float *__restrict__ 
   __syncthreads();
   const int cv = C / VEC;
   const long long total = n * cv;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    int cg = (int)(e % cv);
-    if (VEC == 4) {
-      float4 t = __ldg(reinterpret_cast<const float4 *>(x) + e);
-      float4 w = *reinterpret_cast<const float4 *>(&wb[cg * 4]);
-      float4 b = *reinterpret_cast<const float4 *>(&wb[C + cg * 4]);
-      float4 o;
-      o.x = fmaf(w.x, t.x, b.x); o.y = fmaf(w.y, t.y, b.y); o.z = fmaf(w.z, t.z, b.z); o.w = fmaf(w.w, t.w, b.w);
-      o.x = o.x > 0.f ? o.x : o.x * leak; o.y = o.y > 0.f ? o.y : o.y * leak;
-      o.z = o.z > 0.f ? o.z : o.z * leak; o.w = o.w > 0.f ? o.w : o.w * leak;
-      if (y) reinterpret_cast<float4 *>(y)[e] = o;
-      if (y16) {      // bf16 copy for the tensor-core convolution that consumes y (saves that layer's cast pass)
-        uint2 h;
-        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(o.y), "f"(o.x));
-        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(o.w), "f"(o.z));
-        reinterpret_cast<uint2 *>(y16)[e] = h;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (VEC == 4) {
+    constexpr int U = 2;           // two elements in flight per thread (see k_bn_apply_bwd)
+    for (long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; e0 < total; e0 += stride * U) {
+      float4 t[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (e0 + u * stride < total) t[u] = __ldg(reinterpret_cast<const float4 *>(x) + e0 + u * stride);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long e = e0 + u * stride;
+        if (e >= total) continue;
+        const int cg = (int)(e % cv);
+        const float4 w = *reinterpret_cast<const float4 *>(&wb[cg * 4]);
+        const float4 b = *reinterpret_cast<const float4 *>(&wb[C + cg * 4]);
+        float4 o;
+        o.x = fmaf(w.x, t[u].x, b.x); o.y = fmaf(w.y, t[u].y, b.y); o.z = fmaf(w.z, t[u].z, b.z); o.w = fmaf(w.w, t[u].w, b.w);
+        o.x = o.x > 0.f ? o.x : o.x * leak; o.y = o.y > 0.f ? o.y : o.y * leak;
+        o.z = o.z > 0.f ? o.z : o.z * leak; o.w = o.w > 0.f ? o.w : o.w * leak;
+        if (y) reinterpret_cast<float4 *>(y)[e] = o;
+        if (y16) {      // bf16 copy for the tensor-core convolution that consumes y (saves that layer's cast pass)
+          uint2 h;
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(o.y), "f"(o.x));
+          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(o.w), "f"(o.z));
+          reinterpret_cast<uint2 *>(y16)[e] = h;
+        }
       }
-    } else {
+    }
+  } else {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
+      const int cg = (int)(e % cv);
       float o = fmaf(wb[cg], __ldg(x + e), wb[C + cg]);
       y[e] = o > 0.f ? o : o * leak;
     }
@@ -220,34 +233,52 @@ __global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ 
   __syncthreads();
   const int cv = C / VEC;
   const long long total = n * cv;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    int c0 = (int)(e % cv) * VEC;
-    float xv[VEC], dv[VEC], ov[VEC];
-    if (VEC == 4) {
-      float4 t = __ldg(reinterpret_cast<const float4 *>(x) + e);
-      float4 w = __ldg(reinterpret_cast<const float4 *>(d) + e);
-      xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
-      dv[0] = w.x; dv[1] = w.y; dv[2] = w.z; dv[3] = w.w;
-    } else {
-      xv[0] = __ldg(x + e); dv[0] = __ldg(d + e);
-    }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // U elements per thread and trip, every load issued before the first use: the pass is latency-bound on its 2-3 loads per
+  // element (ncu: long-scoreboard stalls, 0.79 of the copy peak with one element in flight per thread)
+  constexpr int U = VEC == 4 ? 2 : 1;
+  for (long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; e0 < total; e0 += stride * U) {
+    float xv[U][VEC], dv[U][VEC], av[U][VEC];
+    int c0[U];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      int c = c0 + j;
-      float dd = (premasked || fmaf(sm[3 * C + c], xv[j], sm[4 * C + c]) > 0.f) ? dv[j] : dv[j] * leak;
-      ov[j] = (dd - sm[C + c] - (xv[j] - sm[c]) * sm[2 * C + c]) * sm[3 * C + c];
-    }
-    if (add) {          // gradient arriving through the residual shortcut of the same input: accumulated here
-      const long long ea = ld_add == C ? e * VEC : (e / cv) * ld_add + c0;     // rows of `add` may be ld_add floats apart
+    for (int u = 0; u < U; ++u) {
+      const long long e = e0 + u * stride;
+      c0[u] = 0;
+      if (e >= total) continue;
+      c0[u] = (int)(e % cv) * VEC;
       if (VEC == 4) {
-        const float4 av = __ldg(reinterpret_cast<const float4 *>(add + ea));
-        ov[0] += av.x; ov[1] += av.y; ov[2] += av.z; ov[3] += av.w;
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(x) + e);
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(d) + e);
+        xv[u][0] = t.x; xv[u][1] = t.y; xv[u][2] = t.z; xv[u][3] = t.w;
+        dv[u][0] = w.x; dv[u][1] = w.y; dv[u][2] = w.z; dv[u][3] = w.w;
       } else {
-        ov[0] += __ldg(add + ea);
+        xv[u][0] = __ldg(x + e); dv[u][0] = __ldg(d + e);
+      }
+      if (add) {          // gradient arriving through the residual shortcut of the same input: accumulated here
+        const long long ea = ld_add == C ? e * VEC : (e / cv) * ld_add + c0[u];     // rows of `add` may be ld_add floats apart
+        if (VEC == 4) {
+          const float4 a4 = __ldg(reinterpret_cast<const float4 *>(add + ea));
+          av[u][0] = a4.x; av[u][1] = a4.y; av[u][2] = a4.z; av[u][3] = a4.w;
+        } else {
+          av[u][0] = __ldg(add + ea);
+        }
       }
     }
-    if (VEC == 4) reinterpret_cast<float4 *>(dx)[e] = make_float4(ov[0], ov[1], ov[2], ov[3]);
-    else dx[e] = ov[0];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long e = e0 + u * stride;
+      if (e >= total) continue;
+      float ov[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int c = c0[u] + j;
+        const float dd = (premasked || fmaf(sm[3 * C + c], xv[u][j], sm[4 * C + c]) > 0.f) ? dv[u][j] : dv[u][j] * leak;
+        ov[j] = (dd - sm[C + c] - (xv[u][j] - sm[c]) * sm[2 * C + c]) * sm[3 * C + c];
+        if (add) ov[j] += av[u][j];
+      }
+      if (VEC == 4) reinterpret_cast<float4 *>(dx)[e] = make_float4(ov[0], ov[1], ov[2], ov[3]);
+      else dx[e] = ov[0];
+    }
   }
 }
 
