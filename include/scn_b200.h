@@ -226,14 +226,18 @@ int scn_bn_bwd_fusion(scn_meta *m, const float *bn_in, const float *save_mean, c
                       const float *beta, float leakiness, double *acc);
 int scn_bn_bwd_fusable(int c_in, int c_out, int precision);
 int scn_bn_bwd_apply(const float *in, const float *d_masked, const double *acc, const float *save_mean, const float *save_invstd,
-                     const float *gamma, const float *d_in_add, int64_t ld_add, float *d_in, float *d_gamma, float *d_beta,
-                     int64_t n_rows, int channels, void *stream);
-/* ld_add: row stride of d_in_add in floats (0 = dense).
+                     const float *gamma, const float *d_in_add, int64_t ld_add, float *d_in, void *d_in_bf16, float *d_gamma,
+                     float *d_beta, int64_t n_rows, int channels, void *stream);
+/* ld_add: row stride of d_in_add in floats (0 = dense).  d_in_bf16 (optional, [n_rows, channels] bf16): a copy of d_in for the
+ * backward products of the convolution that receives d_in as its d_out -- registered there with scn_grad_bf16(m, d_out, copy)
+ * before the NEXT scn_subm_bwd / scn_conv_bwd / scn_deconv_bwd on the handle (one use, dense rows), it replaces that entry's own
+ * cast pass over d_out.
  * Row-strided gradients: a JoinTable's backward hands its consumers column slices of one [N, 2c] gradient.  scn_grad_stride
  * registers the row stride (floats) of the d_out argument of the NEXT scn_subm_bwd / scn_conv_bwd / scn_deconv_bwd on the handle,
  * so the slice is read where it lies (by the bf16 cast every product of that entry works from) instead of being copied out
  * first.  One use; needs the SCN_BF16 path for all of the entry's products (the entry fails otherwise) and no bias gradient. */
 int scn_grad_stride(scn_meta *m, int64_t ld);
+int scn_grad_bf16(scn_meta *m, const float *d_out, const void *d_out_bf16);
 /* Column statistics from the strided layers: scn_out_stats registers a [2][Cout] fp64 buffer that the NEXT scn_conv_fwd /
  * scn_deconv_fwd on the handle fills with the column sums / sums of squares of its result (as the `stats` argument of scn_subm_fwd
  * does), for the BatchNorm that consumes it.  One use; tensor-core shapes only (scn_fuses_residual). */

@@ -57,7 +57,8 @@ PROTOTYPES = {
     "scn_bn_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, _vp]),
     "scn_bn_bwd_fusion": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_float, _vp]),
     "scn_bn_bwd_fusable": (C.c_int, [C.c_int, C.c_int, C.c_int]),
-    "scn_bn_bwd_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int64, C.c_int, _vp]),
+    "scn_bn_bwd_apply": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int64, C.c_int, _vp]),
+    "scn_grad_bf16": (C.c_int, [_vp, _vp, _vp]),
     "scn_grad_stride": (C.c_int, [_vp, C.c_int64]),
     "scn_out_stats": (C.c_int, [_vp, _vp]),
     "scn_bf16_operand": (C.c_int, [_vp, _vp, _vp, C.c_int]),

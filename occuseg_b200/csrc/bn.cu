@@ -216,7 +216,7 @@ __global__ void k_bn_finalize_bwd(const double *__restrict__ acc, long long n, i
 template <int VEC>
 __global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ x, const float *__restrict__ beta,
                                                       const float *__restrict__ d, const float *__restrict__ add,
-                                                      float *__restrict__ dx,
+                                                      float *__restrict__ dx, uint16_t *__restrict__ dx16,
                                                       const float *__restrict__ save_mean,
                                                       const float *__restrict__ save_invstd,
                                                       const float *__restrict__ gamma, const float *__restrict__ coef,
@@ -278,6 +278,12 @@ __global__ void __launch_bounds__(256) k_bn_apply_bwd(const float *__restrict__ 
       }
       if (VEC == 4) reinterpret_cast<float4 *>(dx)[e] = make_float4(ov[0], ov[1], ov[2], ov[3]);
       else dx[e] = ov[0];
+      if (VEC == 4 && dx16) {      // bf16 copy for the backward products of the convolution that receives dx as its d_out
+        uint2 h;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(ov[1]), "f"(ov[0]));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(ov[3]), "f"(ov[2]));
+        reinterpret_cast<uint2 *>(dx16)[e] = h;
+      }
     }
   }
 }
@@ -362,8 +368,8 @@ void bn_bwd(const float *in, const float *out, const float *d_out, const float *
   k_bn_finalize_bwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, save_invstd, d_gamma, d_beta, coef.p, nullptr);
   SCN_LAUNCH_CHECK();
   size_t smem = sizeof(float) * 5 * C;
-  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness, false, C);
-  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, leakiness, false, C);
+  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, nullptr, save_mean, save_invstd, gamma, coef.p, n, C, leakiness, false, C);
+  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, beta, d_out, d_in_add, d_in, nullptr, save_mean, save_invstd, gamma, coef.p, n, C, leakiness, false, C);
   SCN_LAUNCH_CHECK();
   acc.release(s);
   coef.release(s);
@@ -385,21 +391,22 @@ void bn_mask_coeffs(const float *save_mean, const float *save_invstd, const floa
 }
 
 void bn_bwd_apply(const float *in, const float *d_masked, const double *acc, const float *save_mean, const float *save_invstd,
-                  const float *gamma, const float *d_in_add, long long ld_add, float *d_in, float *d_gamma, float *d_beta,
-                  long long n, int C, cudaStream_t s) {
+                  const float *gamma, const float *d_in_add, long long ld_add, float *d_in, uint16_t *d_in_bf16, float *d_gamma,
+                  float *d_beta, long long n, int C, cudaStream_t s) {
   if (!d_in_add || ld_add == 0) ld_add = C;
   SCN_CHECK(ld_add >= C && (ld_add == C || ld_add % 4 == 0), "BatchNorm: bad row stride of d_in_add");
   SCN_CHECK(C > 0 && C <= 4096, "BatchNorm: channel count out of range");
   if (n == 0) return;
   const bool v4 = (C % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)d_masked % 16 == 0) && ((uintptr_t)d_in % 16 == 0) &&
                   ((uintptr_t)d_in_add % 16 == 0);
+  SCN_CHECK(!d_in_bf16 || (v4 && (uintptr_t)d_in_bf16 % 8 == 0), "BatchNorm: the bf16 gradient copy needs 16-byte aligned rows");
   DevBuf<float> coef;
   coef.alloc(2 * (size_t)C, s);
   k_bn_finalize_bwd<<<(C + 127) / 128, 128, 0, s>>>(acc, n, C, save_invstd, d_gamma, d_beta, coef.p, save_mean);
   SCN_LAUNCH_CHECK();
   const size_t smem = sizeof(float) * 5 * C;
-  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, nullptr, d_masked, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, 0.f, true, ld_add);
-  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, nullptr, d_masked, d_in_add, d_in, save_mean, save_invstd, gamma, coef.p, n, C, 0.f, true, ld_add);
+  if (v4) k_bn_apply_bwd<4><<<stream_grid(n * (C / 4), 256), 256, smem, s>>>(in, nullptr, d_masked, d_in_add, d_in, d_in_bf16, save_mean, save_invstd, gamma, coef.p, n, C, 0.f, true, ld_add);
+  else k_bn_apply_bwd<1><<<stream_grid(n * C, 256), 256, smem, s>>>(in, nullptr, d_masked, d_in_add, d_in, d_in_bf16, save_mean, save_invstd, gamma, coef.p, n, C, 0.f, true, ld_add);
   SCN_LAUNCH_CHECK();
   coef.release(s);
 }

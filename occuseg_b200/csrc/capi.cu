@@ -338,6 +338,17 @@ static const uint16_t *take_bf16_hint(Meta *m, const float *src, long long n, cu
   return p;
 }
 
+// bf16 copy of d_out for the backward products: the one the producer of d_out left (scn_grad_bf16; dense rows only), else a cast pass
+// (the hint is consumed by every backward entry, wanted or not: a stale one could match a later d_out at a recycled address)
+static const uint16_t *grad_bf16(Meta *m, bool wanted, Bf16Copy &g16, const float *d_out, long long ld, long long rows, int cols,
+                                 cudaStream_t s) {
+  const uint16_t *held = (m->ghint_src == d_out && ld == 0) ? (const uint16_t *)m->ghint_bf16 : nullptr;
+  m->ghint_src = nullptr;
+  m->ghint_bf16 = nullptr;
+  if (!wanted) return nullptr;
+  return held ? held : g16.make_rows(d_out, ld, rows, cols, s);
+}
+
 static void check_channels(int c_in, int c_out) {
   SCN_CHECK(c_in > 0 && c_out > 0 && c_in <= 4096 && c_out <= 4096, "channel counts out of range");
 }
@@ -669,7 +680,7 @@ int scn_subm_bwd(scn_meta *h, const int64_t size[3], const float *in, const floa
   const bool dgrad16 = d_in && bf16_conv_shape(c_out, c_in, precision), wgrad16 = bf16_wgrad_shape(c_in, c_out, precision);
   Bf16Copy g16, x16;
   const long long ld_g = take_grad_ld(&h->m, c_out, (!d_in || dgrad16) && wgrad16, d_bias);
-  const uint16_t *pg = (dgrad16 || wgrad16) ? g16.make_rows(d_out, ld_g, (long long)L->n, c_out, s) : nullptr;
+  const uint16_t *pg = grad_bf16(&h->m, dgrad16 || wgrad16, g16, d_out, ld_g, (long long)L->n, c_out, s);
   const uint16_t *px = take_bf16_hint(&h->m, in, (long long)L->n * c_in, s);
   if (!wgrad16) px = nullptr;
   else if (!px) px = x16.make(in, (long long)L->n * c_in, s);
@@ -761,7 +772,7 @@ int scn_conv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size[3
   const bool dgrad16 = bf16_conv_shape(c_out, c_in, precision), wgrad16 = bf16_wgrad_shape(c_in, c_out, precision);
   const long long ld_g = take_grad_ld(&h->m, c_out, dgrad16 && wgrad16, d_bias);
   Bf16Copy g16;
-  const uint16_t *pg = (dgrad16 || wgrad16) ? g16.make_rows(d_out, ld_g, (long long)C->n, c_out, s) : nullptr;
+  const uint16_t *pg = grad_bf16(&h->m, dgrad16 || wgrad16, g16, d_out, ld_g, (long long)C->n, c_out, s);
   // dgrad: d_in[child[k][p]] = d_out[p] * W[k]^T  (scatter; each fine row has one parent)
   run_up(F, C, d_out, weight, false, d_in, c_out, c_in, precision, s, dgrad16 ? pg : nullptr, &h->m);
   WgradArgs w;
@@ -810,7 +821,7 @@ int scn_deconv_bwd(scn_meta *h, const int64_t in_size[3], const int64_t out_size
   const bool dgrad16 = bf16_conv_shape(c_out, c_in, precision), wgrad16 = bf16_wgrad_shape(c_out, c_in, precision);
   const long long ld_g = take_grad_ld(&h->m, c_out, dgrad16 && wgrad16, d_bias);
   Bf16Copy g16;
-  const uint16_t *pg = (dgrad16 || wgrad16) ? g16.make_rows(d_out, ld_g, (long long)F->n, c_out, s) : nullptr;
+  const uint16_t *pg = grad_bf16(&h->m, dgrad16 || wgrad16, g16, d_out, ld_g, (long long)F->n, c_out, s);
   BnbScratch scr;
   apply_bnb_hint(&h->m, a, precision, scr, s);
   run_conv(a, weight, false, precision, s, dgrad16 ? pg : nullptr);
@@ -851,12 +862,20 @@ int scn_bn_bwd_fusable(int c_in, int c_out, int precision) {
 }
 
 int scn_bn_bwd_apply(const float *in, const float *d_masked, const double *acc, const float *save_mean, const float *save_invstd,
-                     const float *gamma, const float *d_in_add, int64_t ld_add, float *d_in, float *d_gamma, float *d_beta,
-                     int64_t n, int C, void *stream) {
+                     const float *gamma, const float *d_in_add, int64_t ld_add, float *d_in, void *d_in_bf16, float *d_gamma,
+                     float *d_beta, int64_t n, int C, void *stream) {
   SCN_TRY
-  ProfScope ps(PK_BN, (d_in_add ? 4.0 : 3.0) * 4.0 * (double)n * C, 0.0, note_stream(stream));
-  bn_bwd_apply(in, d_masked, acc, save_mean, save_invstd, gamma, d_in_add, ld_add, d_in, d_gamma, d_beta, n, C,
-               note_stream(stream));
+  ProfScope ps(PK_BN, ((d_in_add ? 4.0 : 3.0) * 4.0 + (d_in_bf16 ? 2.0 : 0.0)) * (double)n * C, 0.0, note_stream(stream));
+  bn_bwd_apply(in, d_masked, acc, save_mean, save_invstd, gamma, d_in_add, ld_add, d_in, (uint16_t *)d_in_bf16, d_gamma, d_beta,
+               n, C, note_stream(stream));
+  SCN_CATCH
+}
+
+int scn_grad_bf16(scn_meta *h, const float *d_out, const void *bf16) {
+  SCN_TRY
+  SCN_CHECK(h, "null handle");
+  h->m.ghint_src = d_out;
+  h->m.ghint_bf16 = bf16;
   SCN_CATCH
 }
 

@@ -180,6 +180,8 @@ struct Meta {
   const float *hint_src = nullptr;
   void *hint_bf16 = nullptr;
   int hint_ready = 0;
+  const float *ghint_src = nullptr;       // scn_grad_bf16(): a ready bf16 copy of the (dense) d_out of the next backward entry (one use)
+  const void *ghint_bf16 = nullptr;
   const float *point_normals = nullptr;   // scn_input_normals(): [P,3] normals of the points of the next scn_input_layer_build
   int normal_guide_scale = 1 << 30;        // strided layers propagate normals / permute taps only from scales >= this size
   double *next_stats = nullptr;   // scn_out_stats(): column statistics wanted from the next scn_conv_fwd / scn_deconv_fwd (one use)
@@ -322,7 +324,7 @@ void bn_mask_coeffs(const float *save_mean, const float *save_invstd, const floa
 // second half of bn_bwd when a convolution epilogue already produced the masked gradient d' and acc = (sum d', sum d'*x):
 // d_in = (d' - mean(d') - (x - mean) * k) * invstd * gamma (+ d_in_add); d_gamma, d_beta.  d_in may alias d_masked.
 void bn_bwd_apply(const float *in, const float *d_masked, const double *acc, const float *save_mean, const float *save_invstd,
-                  const float *gamma, const float *d_in_add, long long ld_add, float *d_in, float *d_gamma, float *d_beta,
-                  long long n, int C, cudaStream_t s);
+                  const float *gamma, const float *d_in_add, long long ld_add, float *d_in, uint16_t *d_in_bf16, float *d_gamma,
+                  float *d_beta, long long n, int C, cudaStream_t s);
 
 }  // namespace scn

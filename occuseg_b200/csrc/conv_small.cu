@@ -34,23 +34,37 @@ __global__ void __launch_bounds__(SC_ROWS) k_conv_small_cin(ConvArgs a) {
   float acc[SC_TILE];
 #pragma unroll
   for (int c = 0; c < SC_TILE; ++c) acc[c] = 0.f;
-  for (int k = 0; k < a.V; ++k) {
-    const int trow = a.mirror ? a.V - 1 - k : k;
-    const int t = row < a.n_rows ? __ldg(&a.tbl[(long long)trow * a.tbl_stride + row]) : -1;
-    if (!__any_sync(0xffffffffu, t >= 0)) continue;
-    float x[CIN];
+  // Taps in batches of TB: all table entries of a batch are loaded first, then all neighbour inputs, then the FMAs -- TB and
+  // then TB*CIN independent loads in flight per thread instead of a dependent pair per tap (the kernel was bound by that chain,
+  // not by its 81*Cout FMAs per row).
+  constexpr int TB = 9;
+  for (int k0 = 0; k0 < a.V; k0 += TB) {
+    int t[TB];
 #pragma unroll
-    for (int i = 0; i < CIN; ++i) x[i] = t >= 0 ? __ldg(&a.in[(long long)t * CIN + i]) : 0.f;
-    const float4 *wk = reinterpret_cast<const float4 *>(w_s + k * CIN * SC_TILE);
+    for (int j = 0; j < TB; ++j) {
+      const int k = k0 + j;
+      const int trow = a.mirror ? a.V - 1 - k : k;
+      t[j] = (k < a.V && row < a.n_rows) ? __ldg(&a.tbl[(long long)trow * a.tbl_stride + row]) : -1;
+    }
+    float x[TB][CIN];
 #pragma unroll
-    for (int i = 0; i < CIN; ++i) {
+    for (int j = 0; j < TB; ++j)
 #pragma unroll
-      for (int c4 = 0; c4 < SC_TILE / 4; ++c4) {
-        const float4 w = wk[i * (SC_TILE / 4) + c4];
-        acc[c4 * 4 + 0] = fmaf(x[i], w.x, acc[c4 * 4 + 0]);
-        acc[c4 * 4 + 1] = fmaf(x[i], w.y, acc[c4 * 4 + 1]);
-        acc[c4 * 4 + 2] = fmaf(x[i], w.z, acc[c4 * 4 + 2]);
-        acc[c4 * 4 + 3] = fmaf(x[i], w.w, acc[c4 * 4 + 3]);
+      for (int i = 0; i < CIN; ++i) x[j][i] = t[j] >= 0 ? __ldg(&a.in[(long long)t[j] * CIN + i]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < TB; ++j) {
+      if (k0 + j >= a.V || !__any_sync(0xffffffffu, t[j] >= 0)) continue;
+      const float4 *wk = reinterpret_cast<const float4 *>(w_s + (k0 + j) * CIN * SC_TILE);
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) {
+#pragma unroll
+        for (int c4 = 0; c4 < SC_TILE / 4; ++c4) {
+          const float4 w = wk[i * (SC_TILE / 4) + c4];
+          acc[c4 * 4 + 0] = fmaf(x[j][i], w.x, acc[c4 * 4 + 0]);
+          acc[c4 * 4 + 1] = fmaf(x[j][i], w.y, acc[c4 * 4 + 1]);
+          acc[c4 * 4 + 2] = fmaf(x[j][i], w.z, acc[c4 * 4 + 2]);
+          acc[c4 * 4 + 3] = fmaf(x[j][i], w.w, acc[c4 * 4 + 3]);
+        }
       }
     }
   }
@@ -109,30 +123,61 @@ __global__ void __launch_bounds__(SW_THREADS) k_wgrad_small_cin(WgradArgs a, int
   float acc[SW_TAPS * CIN];
 #pragma unroll
   for (int i = 0; i < SW_TAPS * CIN; ++i) acc[i] = 0.f;
-  for (long long r0 = r_begin; r0 < r_end; r0 += SW_ROWS) {
-    // stage neighbour inputs: SW_ROWS x 32 (row, tap) slots
-    for (int e = tid; e < SW_ROWS * 32; e += SW_THREADS) {
+  // Software pipeline through registers: while the FMAs of step i run from shared memory, the neighbour inputs and gradients of
+  // step i+1 and the table entries of step i+2 are in flight (the table -> input dependency is two steps deep), so the
+  // latency of the staging loads no longer alternates with the arithmetic.
+  constexpr int XS = SW_ROWS * 32 / SW_THREADS;          // (row, tap) slots per thread and step
+  constexpr int GS = SW_ROWS * SC_TILE / SW_THREADS;     // gradient elements per thread and step
+  int idx[XS];
+  float xr[XS][CIN], gr[GS];
+  auto load_idx = [&](long long r0) {
+#pragma unroll
+    for (int j = 0; j < XS; ++j) {
+      const int e = tid + j * SW_THREADS;
       const int r = e & (SW_ROWS - 1), k = e / SW_ROWS;        // consecutive threads -> consecutive rows of one tap
       const long long row = r0 + r;
-      int t = -1;
-      if (k < a.V && row < r_end) t = __ldg(&a.tbl[(long long)k * a.tbl_stride + row]);
-      float *dst = &x_s[r][k * CIN];
-#pragma unroll
-      for (int i = 0; i < CIN; ++i) dst[i] = t >= 0 ? __ldg(&a.a[(long long)t * CIN + i]) : 0.f;
+      idx[j] = (k < a.V && row < r_end) ? __ldg(&a.tbl[(long long)k * a.tbl_stride + row]) : -1;
     }
-    for (int e = tid; e < SW_ROWS * SC_TILE; e += SW_THREADS) {
+  };
+  auto load_rows = [&](long long r0) {
+#pragma unroll
+    for (int j = 0; j < XS; ++j)
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) xr[j][i] = idx[j] >= 0 ? __ldg(&a.a[(long long)idx[j] * CIN + i]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < GS; ++j) {
+      const int e = tid + j * SW_THREADS;
       const int r = e / SC_TILE, c = e % SC_TILE;
       const long long row = r0 + r;
-      g_s[r][c] = (row < r_end && n0 + c < a.c_b) ? __ldg(&a.b[row * a.c_b + n0 + c]) : 0.f;
+      gr[j] = (row < r_end && n0 + c < a.c_b) ? __ldg(&a.b[row * a.c_b + n0 + c]) : 0.f;
+    }
+  };
+  load_idx(r_begin);
+  load_rows(r_begin);
+  load_idx(r_begin + SW_ROWS);
+  for (long long r0 = r_begin; r0 < r_end; r0 += SW_ROWS) {
+#pragma unroll
+    for (int j = 0; j < XS; ++j) {
+      const int e = tid + j * SW_THREADS;
+      float *dst = &x_s[e & (SW_ROWS - 1)][(e / SW_ROWS) * CIN];
+#pragma unroll
+      for (int i = 0; i < CIN; ++i) dst[i] = xr[j][i];
+    }
+#pragma unroll
+    for (int j = 0; j < GS; ++j) {
+      const int e = tid + j * SW_THREADS;
+      g_s[e / SC_TILE][e % SC_TILE] = gr[j];
     }
     __syncthreads();
+    load_rows(r0 + SW_ROWS);                   // rows >= r_end read as absent / zero
+    load_idx(r0 + 2 * SW_ROWS);
 #pragma unroll 4
     for (int r = 0; r < SW_ROWS; ++r) {
       const float gv = g_s[r][co];
-      const float4 *xr = reinterpret_cast<const float4 *>(&x_s[r][q * SW_TAPS * CIN]);
+      const float4 *xr4 = reinterpret_cast<const float4 *>(&x_s[r][q * SW_TAPS * CIN]);
 #pragma unroll
       for (int i = 0; i < SW_TAPS * CIN / 4; ++i) {
-        const float4 xv = xr[i];
+        const float4 xv = xr4[i];
         acc[4 * i + 0] = fmaf(xv.x, gv, acc[4 * i + 0]);
         acc[4 * i + 1] = fmaf(xv.y, gv, acc[4 * i + 1]);
         acc[4 * i + 2] = fmaf(xv.z, gv, acc[4 * i + 2]);

@@ -128,13 +128,27 @@ def _rows_f32(t, name):
     return t, 0
 
 
+def held_bf16(t):
+    """The bf16 copy the producer of `t` attached (attach_bf16), if `t` has not changed since."""
+    held = getattr(t, "_scn_bf16", None)
+    if held is not None and held[0] == t._version and held[1] == t.data_ptr() and held[2].shape == t.shape:
+        return held[2]
+    return None
+
+
 def _grad_operand(m, d_output_features, strided_ok):
-    """d_out of a backward entry; a row-strided slice is registered with scn_grad_stride when the entry can read it in place"""
+    """d_out of a backward entry; a row-strided slice is registered with scn_grad_stride when the entry can read it in place,
+    and a bf16 copy left by the kernel that produced a dense d_out (the BatchNorm backward behind this layer) is registered
+    with scn_grad_bf16 so that the entry skips its own cast pass"""
     if not strided_ok:
         return _cuda_f32(d_output_features, "grad")
     g, ld = _rows_f32(d_output_features, "grad")
     if ld:
         _lib.check(_lib.lib().scn_grad_stride(m._handle(), int(ld)))
+    elif _precision == _lib.BF16:
+        copy = held_bf16(d_output_features)
+        if copy is not None and g.data_ptr() == d_output_features.data_ptr():
+            _lib.check(_lib.lib().scn_grad_bf16(m._handle(), _ptr(g), _ptr(copy)))
     return g
 
 
@@ -522,17 +536,20 @@ def BatchNormalization_backwardFusion(m, input_features, saveMean, saveInvStd, w
 
 
 def BatchNormalization_backwardApply(input_features, d_masked, acc, saveMean, saveInvStd, weight, d_input_features, d_weight,
-                                     d_bias, d_input_add=None):
-    """(extension) second half of BatchNormalization_backward after a fused dgrad epilogue (scn_bn_bwd_apply)."""
+                                     d_bias, d_input_add=None, d_input_bf16=None):
+    """(extension) second half of BatchNormalization_backward after a fused dgrad epilogue (scn_bn_bwd_apply).
+    d_input_bf16: optional bfloat16 tensor that receives a copy of d_input_features (see _grad_operand)."""
     x, g = _cuda_f32(input_features, "input"), _cuda_f32(d_masked, "grad")
     ld_add = 0
     if d_input_add is not None:
         d_input_add, ld_add = _rows_f32(d_input_add, "d_input_add")      # may be a column slice of a joined gradient
     with _on(x.device):
         d_input_features.resize_(x.size(0), x.size(1))
+        if d_input_bf16 is not None:
+            d_input_bf16.resize_(x.size(0), x.size(1))
         _lib.check(_lib.lib().scn_bn_bwd_apply(_ptr(x), _ptr(g), _ptr(acc), _ptr(saveMean), _ptr(saveInvStd), _ptr(_opt(weight)),
-                                               _ptr(d_input_add), int(ld_add), _ptr(d_input_features), _ptr(_opt(d_weight)),
-                                               _ptr(_opt(d_bias)), x.size(0), x.size(1), _stream()))
+                                               _ptr(d_input_add), int(ld_add), _ptr(d_input_features), _ptr(d_input_bf16),
+                                               _ptr(_opt(d_weight)), _ptr(_opt(d_bias)), x.size(0), x.size(1), _stream()))
 
 
 # ---- 1x1 "NetworkInNetwork": the reference itself calls ATen's GEMM here (CUDA/NetworkInNetwork.cpp:9-50).

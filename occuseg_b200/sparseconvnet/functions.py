@@ -192,7 +192,12 @@ class BatchNormConvFunction(Function):
         gx = g.new_empty(0)
         g_gamma, g_beta = torch.zeros_like(bn_weight), torch.zeros_like(bn_bias)
         add = grad_alias if grad_alias is not None and grad_alias.numel() == x.numel() else None
-        SCN.BatchNormalization_backwardApply(x, d_masked, acc, save_mean, save_invstd, bn_weight, gx, g_gamma, g_beta, add)
+        # the gradient leaves with a bf16 copy attached: the convolution that produced x receives it as its d_out and reads the
+        # copy instead of casting (SCN._grad_operand); dropped silently if autograd adds another gradient to it on the way
+        gx16 = torch.empty(0, dtype=torch.bfloat16, device=x.device) if SCN.wants_bf16(x.size(1)) else None
+        SCN.BatchNormalization_backwardApply(x, d_masked, acc, save_mean, save_invstd, bn_weight, gx, g_gamma, g_beta, add, gx16)
+        if gx16 is not None:
+            SCN.attach_bf16(gx, gx16)
         del ctx.scn_meta
         return (gx, optionalTensorReturn(g_gamma), optionalTensorReturn(g_beta), None, None, None, None, None, gw,
                 optionalTensorReturn(gb), None, None, None, None, None, None,

@@ -598,3 +598,32 @@ def test_fused_batchnorm_conv_pair_equals_the_two_layers(kind):
     assert torch.equal(a[0], b[0]) and torch.equal(a[5], b[5]) and torch.equal(a[6], b[6])
     for i, name in ((1, "d_x"), (2, "d_gamma"), (3, "d_beta"), (4, "d_weight")):
         assert rel_err(a[i].cpu().numpy(), b[i].cpu().numpy()) < 1e-5, (kind, name)
+
+
+def test_bf16_gradient_copies_replace_the_cast_passes(monkeypatch):
+    """The BatchNorm backward of a fused BatchNorm -> convolution node leaves a bf16 copy of its d_x; the convolution that
+    receives that gradient as d_out reads the copy (scn_grad_bf16) instead of casting.  Same bits as the cast (both round to
+    nearest even), fewer cast launches."""
+    coords, feats = scenes.make_batch("small", (5, 6))
+
+    def step(use_copies):
+        if not use_copies:
+            monkeypatch.setattr(SCN, "held_bf16", lambda t: None)
+        torch.manual_seed(3)
+        net = scn.Sequential().add(scn.InputLayer(3, SIZE, mode=4)).add(scn.SubmanifoldConvolution(3, 3, 64, 3, False)) \
+            .add(scn.UNet(3, 2, [64, 128], True)).add(scn.BatchNormReLU(64)).add(scn.OutputLayer(3)).cuda()
+        _lib.profile(True)
+        out = net([torch.from_numpy(coords), cu(feats), None, 2])
+        out.square().mean().backward()
+        torch.cuda.synchronize()
+        prof = _lib.profile_read()
+        _lib.profile(False)
+        monkeypatch.undo()
+        return [p.grad.clone() for p in net.parameters()], prof["cast"]["launches"]
+
+    g1, casts1 = step(True)
+    g0, casts0 = step(False)
+    assert casts1 < casts0, (casts1, casts0)
+    # the weight gradients merge partial sums with floating-point atomics (run-to-run order), so equality is up to that noise
+    for a, b in zip(g1, g0):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
