@@ -131,8 +131,7 @@ struct Level {
   int n_pad = 0;             // row stride of the [V][n_pad] tables (multiple of 128)
   DevBuf<uint64_t> keys;     // [n] sorted unique voxel keys; row id == index
   // open-addressing hash: key -> row
-  DevBuf<uint64_t> hkeys;
-  DevBuf<int> hvals;
+  DevBuf<ulonglong2> htab;   // {key, row}: one 16-byte entry = one 32-byte sector per probe (keys and rows in separate arrays cost two)
   uint32_t hmask = 0;
   // submanifold 3x3x3 neighbour table (output-stationary form of the reference's 27 rule lists)
   DevBuf<int> nbr;           // [27][n_pad], -1 = absent

@@ -210,30 +210,29 @@ __device__ __forceinline__ uint32_t hash_key(uint64_t k) {
   return (uint32_t)k;
 }
 
-__global__ void k_hash_insert(const uint64_t *__restrict__ keys, int n, uint64_t *__restrict__ hkeys,
-                              int *__restrict__ hvals, uint32_t mask) {
+// An entry is {key, row} in 16 bytes: a probe is ONE 16-byte load (one 32-byte sector).  The neighbour query is bound by the
+// sectors its random probes pull from L2 (52 M probes at level 0), and separate key / row arrays cost two per hit.
+__global__ void k_hash_insert(const uint64_t *__restrict__ keys, int n, ulonglong2 *__restrict__ htab, uint32_t mask) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t k = keys[i];
   uint32_t slot = hash_key(k) & mask;
   while (true) {
-    unsigned long long prev = atomicCAS((unsigned long long *)&hkeys[slot], (unsigned long long)EMPTY_KEY,
-                                        (unsigned long long)k);
+    unsigned long long prev = atomicCAS(&htab[slot].x, (unsigned long long)EMPTY_KEY, (unsigned long long)k);
     if (prev == EMPTY_KEY) {  // keys are unique, so a slot is never claimed twice for the same key
-      hvals[slot] = i;
+      htab[slot].y = (unsigned long long)i;
       return;
     }
     slot = (slot + 1) & mask;
   }
 }
 
-__device__ __forceinline__ int hash_find(uint64_t k, const uint64_t *__restrict__ hkeys, const int *__restrict__ hvals,
-                                         uint32_t mask) {
+__device__ __forceinline__ int hash_find(uint64_t k, const ulonglong2 *__restrict__ htab, uint32_t mask) {
   uint32_t slot = hash_key(k) & mask;
   while (true) {
-    uint64_t cur = __ldg(&hkeys[slot]);
-    if (cur == k) return __ldg(&hvals[slot]);
-    if (cur == EMPTY_KEY) return -1;
+    const ulonglong2 e = __ldg(&htab[slot]);
+    if (e.x == k) return (int)e.y;
+    if (e.x == EMPTY_KEY) return -1;
     slot = (slot + 1) & mask;
   }
 }
@@ -265,8 +264,8 @@ __device__ __forceinline__ uint32_t pattern_of_key(uint32_t key) {
 // (CUDA/SubmanifoldRules_cuda.cu:63-73), NOT the dormant CPU-grid enumeration.  A neighbour exists only
 // inside the same sample (the reference keeps one hash per sample, Metadata.h:110-122).  Writes are
 // coalesced: consecutive threads -> consecutive rows of nbr[k][*].
-__global__ void k_neighbours(const uint64_t *__restrict__ keys, int n, int stride, const uint64_t *__restrict__ hkeys,
-                             const int *__restrict__ hvals, uint32_t mask, int *__restrict__ nbr,
+__global__ void k_neighbours(const uint64_t *__restrict__ keys, int n, int stride, const ulonglong2 *__restrict__ htab,
+                             uint32_t mask, int *__restrict__ nbr,
                              unsigned long long *__restrict__ n_rules, unsigned long long *__restrict__ row_key,
                              int sort_block, int dil) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -286,10 +285,15 @@ __global__ void k_neighbours(const uint64_t *__restrict__ keys, int n, int strid
           int r;
           if (t == 13) {
             r = i;
+          } else if (dil == 1 && dy == 0 && dz == 0) {
+            // the x neighbours of a row are its neighbours in the sorted key array, if they exist (x is the lowest key field
+            // and 65535 is not a coordinate, so key -+ 1 never reaches into another (y, z)): no probe
+            const int j = i + dx;
+            r = (j >= 0 && j < n && __ldg(&keys[j]) == k + (uint64_t)(long long)dx) ? j : -1;
           } else {
             int qx = x + dx * dil, qy = y + dy * dil, qz = z + dz * dil;
             bool inside = qx >= 0 && qy >= 0 && qz >= 0 && qx < COORD_LIMIT && qy < COORD_LIMIT && qz < COORD_LIMIT;
-            r = inside ? hash_find(make_key(b, qz, qy, qx), hkeys, hvals, mask) : -1;
+            r = inside ? hash_find(make_key(b, qz, qy, qx), htab, mask) : -1;
           }
           nbr[t * stride + i] = r;
           hits += (r >= 0);
@@ -305,48 +309,87 @@ __global__ void k_neighbours(const uint64_t *__restrict__ keys, int n, int strid
 }
 
 // ---- per-tap compaction of a [V][stride] table into padded (entry, column) lists ------------------------------
-struct IsRule {
-  __host__ __device__ int operator()(const int &t) const { return t >= 0 ? 1 : 0; }
-};
-// rank[i] = number of rules before flat position i.  One thread block: tap k owns rules rank[k*stride] ..
-// rank[(k+1)*stride]-1; its list starts at item_off[k] (PAIR_ITEM rules per item, every tap rounded up).
-__global__ void k_pair_offsets(const int *__restrict__ tbl, const int *__restrict__ rank, int V, int stride, int unit,
-                               int *__restrict__ item_off, int *__restrict__ rank_base) {
+// Ranks come from per-block counts: cnt[k][b] = rules of tap k in columns [b*BLK_ROWS, (b+1)*BLK_ROWS); an exclusive scan over
+// the V * n_blk counts (tap-major) gives base[k][b] = number of rules before that block, and the scatter kernel adds the rank
+// inside the block.  (Until round 2 a scan over all V * stride flags wrote a rank per table entry: 4 reads + 1 write of the
+// table's size instead of 2 reads.)  Tap k owns rules base[k][0] .. base[k+1][0]-1; its list starts at item_off[k] (`unit`
+// rules per item, every tap rounded up).
+constexpr int PB_THREADS = BLK_ROWS / 4;      // one int4 (4 columns) per thread
+static_assert(PB_THREADS % 32 == 0 && PB_THREADS <= 1024, "block geometry of the pair-list kernels");
+
+__device__ __forceinline__ int4 load_cols4(const int *__restrict__ tbl, int k, int stride, int col) {
+  return col < stride ? __ldg(reinterpret_cast<const int4 *>(tbl + (long long)k * stride + col)) : make_int4(-1, -1, -1, -1);
+}
+// exclusive prefix of `c` over the thread block (PB_THREADS threads); *total receives the block sum
+__device__ __forceinline__ int block_exclusive(int c, int *total) {
+  __shared__ int warp_sum[PB_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += v;
+  }
+  if (lane == 31) warp_sum[w] = inc;
+  __syncthreads();
+  int before = 0, all = 0;
+#pragma unroll
+  for (int j = 0; j < PB_THREADS / 32; ++j) {
+    const int v = warp_sum[j];
+    if (j < w) before += v;
+    all += v;
+  }
+  *total = all;
+  return before + inc - c;
+}
+// grid (n_blk, V)
+__global__ void __launch_bounds__(PB_THREADS) k_count_rules(const int *__restrict__ tbl, int stride, int n_blk,
+                                                            int *__restrict__ cnt) {
+  const int k = blockIdx.y, b = blockIdx.x;
+  const int4 t = load_cols4(tbl, k, stride, b * BLK_ROWS + 4 * threadIdx.x);
+  const int c = (t.x >= 0) + (t.y >= 0) + (t.z >= 0) + (t.w >= 0);
+  int total;
+  block_exclusive(c, &total);
+  if (threadIdx.x == 0) cnt[k * n_blk + b] = total;
+}
+// base = exclusive scan of cnt, V * n_blk + 1 entries (the last one = all rules)
+__global__ void k_pair_offsets(const int *__restrict__ base, int V, int n_blk, int unit, int *__restrict__ item_off,
+                               int *__restrict__ rank_base) {
   if (threadIdx.x != 0) return;
-  const long long last = (long long)V * stride - 1;
-  const int total = rank[last] + (tbl[last] >= 0 ? 1 : 0);
   int items = 0;
   for (int k = 0; k < V; ++k) {
-    const int b = rank[(long long)k * stride];
-    const int e = (k + 1 < V) ? rank[(long long)(k + 1) * stride] : total;
+    const int b = base[k * n_blk], e = base[(k + 1) * n_blk];
     item_off[k] = items;
     rank_base[k] = b;
     items += (e - b + unit - 1) / unit;
   }
   item_off[V] = items;
 }
-__global__ void k_block_items(const int *__restrict__ rank, int V, int stride, int n_blk, int blk_rows, int unit,
-                              const int *__restrict__ item_off, const int *__restrict__ rank_base,
-                              int *__restrict__ blk_item) {
+__global__ void k_block_items(const int *__restrict__ base, int V, int n_blk, int unit, const int *__restrict__ item_off,
+                              const int *__restrict__ rank_base, int *__restrict__ blk_item) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= V * (n_blk + 1)) return;
   const int k = i / (n_blk + 1), b = i - k * (n_blk + 1);
-  const long long col = (long long)b * blk_rows;
-  blk_item[i] = (b == n_blk || col >= stride) ? item_off[k + 1]
-                                              : item_off[k] + (rank[(long long)k * stride + col] - rank_base[k]) / unit;
+  blk_item[i] = b == n_blk ? item_off[k + 1] : item_off[k] + (base[k * n_blk + b] - rank_base[k]) / unit;
 }
-__global__ void k_scatter_pairs(const int *__restrict__ tbl, const int *__restrict__ rank, long long n_flat, int stride,
-                                int unit, const int *__restrict__ item_off, const int *__restrict__ rank_base,
-                                int *__restrict__ gi, int *__restrict__ si) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n_flat) return;
-  const int t = tbl[i];
-  if (t < 0) return;
-  const int k = (int)(i / stride);
-  const int col = (int)(i - (long long)k * stride);
-  const long long pos = (long long)item_off[k] * unit + (rank[i] - rank_base[k]);
-  gi[pos] = t;
-  si[pos] = col;
+// grid (n_blk, V)
+__global__ void __launch_bounds__(PB_THREADS) k_scatter_pairs(const int *__restrict__ tbl, const int *__restrict__ base,
+                                                              int stride, int n_blk, int unit,
+                                                              const int *__restrict__ item_off,
+                                                              const int *__restrict__ rank_base, int *__restrict__ gi,
+                                                              int *__restrict__ si) {
+  const int k = blockIdx.y, b = blockIdx.x;
+  const int col = b * BLK_ROWS + 4 * threadIdx.x;
+  const int4 t = load_cols4(tbl, k, stride, col);
+  const int c = (t.x >= 0) + (t.y >= 0) + (t.z >= 0) + (t.w >= 0);
+  int total;
+  const int pre = block_exclusive(c, &total);
+  if (!c) return;
+  long long pos = (long long)item_off[k] * unit + (base[k * n_blk + b] + pre - rank_base[k]);
+  if (t.x >= 0) { gi[pos] = t.x; si[pos] = col; ++pos; }
+  if (t.y >= 0) { gi[pos] = t.y; si[pos] = col + 1; ++pos; }
+  if (t.z >= 0) { gi[pos] = t.z; si[pos] = col + 2; ++pos; }
+  if (t.w >= 0) { gi[pos] = t.w; si[pos] = col + 3; ++pos; }
 }
 
 __global__ void k_fill_int(int *p, long long n, int v) {
@@ -414,8 +457,8 @@ void build_pair_list(PairList &out, const int *tbl, int V, int stride, long long
   if (out.item_off.p) return;
   out.unit = unit;
   const long long n_flat = (long long)V * stride;
-  // table read twice (rank scan + scatter, 4 B each) + the ranks (4 B written, 4 B read) + 8 B per rule written
-  ProfScope ps(PK_RULEBOOK, 16.0 * (double)n_flat + 8.0 * (double)n_rules, 0.0, s);
+  // table read twice (count + scatter, 4 B each) + 8 B per rule written
+  ProfScope ps(PK_RULEBOOK, 8.0 * (double)n_flat + 8.0 * (double)n_rules, 0.0, s);
   SCN_CHECK(n_flat > 0 && n_flat < (1ll << 31), "rule table too large for 32-bit ranks");
   out.n_items_ub = (n_rules + (long long)(unit - 1) * V) / unit + 1;
   out.gi.alloc((size_t)out.n_items_ub * unit, s);
@@ -423,27 +466,33 @@ void build_pair_list(PairList &out, const int *tbl, int V, int stride, long long
   out.item_off.alloc(V + 1, s);
   SCN_CUDA(cudaMemsetAsync(out.gi.p, pad_byte, sizeof(int) * out.gi.n, s));   // 0x7F -> PAIR_PAD, 0xFF -> -1
   SCN_CUDA(cudaMemsetAsync(out.si.p, pad_byte, sizeof(int) * out.si.n, s));
-  DevBuf<int> rank, rank_base;
-  rank.alloc((size_t)n_flat, s);
+  out.n_blk = (stride + BLK_ROWS - 1) / BLK_ROWS;
+  const int n_cnt = V * out.n_blk;
+  DevBuf<int> cnt, base, rank_base;
+  cnt.alloc((size_t)n_cnt + 1, s);
+  base.alloc((size_t)n_cnt + 1, s);
   rank_base.alloc(V, s);
-  cub::TransformInputIterator<int, IsRule, const int *> flags(tbl, IsRule());
+  SCN_CUDA(cudaMemsetAsync(cnt.p + n_cnt, 0, sizeof(int), s));
+  const dim3 grid(out.n_blk, V);
+  k_count_rules<<<grid, PB_THREADS, 0, s>>>(tbl, stride, out.n_blk, cnt.p);
+  SCN_LAUNCH_CHECK();
   size_t tb = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tb, flags, rank.p, (int)n_flat, s);
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt.p, base.p, n_cnt + 1, s);
   DevBuf<uint8_t> tmp;
   tmp.alloc(tb, s);
-  SCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags, rank.p, (int)n_flat, s));
+  SCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cnt.p, base.p, n_cnt + 1, s));
   count_launch(2);
-  k_pair_offsets<<<1, 32, 0, s>>>(tbl, rank.p, V, stride, unit, out.item_off.p, rank_base.p);
+  k_pair_offsets<<<1, 32, 0, s>>>(base.p, V, out.n_blk, unit, out.item_off.p, rank_base.p);
   SCN_LAUNCH_CHECK();
-  k_scatter_pairs<<<grid_for(n_flat, 256), 256, 0, s>>>(tbl, rank.p, n_flat, stride, unit, out.item_off.p, rank_base.p,
-                                                         out.gi.p, out.si.p);
+  k_scatter_pairs<<<grid, PB_THREADS, 0, s>>>(tbl, base.p, stride, out.n_blk, unit, out.item_off.p, rank_base.p, out.gi.p,
+                                              out.si.p);
   SCN_LAUNCH_CHECK();
-  out.n_blk = (stride + BLK_ROWS - 1) / BLK_ROWS;
   out.blk_item.alloc((size_t)V * (out.n_blk + 1), s);
-  k_block_items<<<grid_for((long long)V * (out.n_blk + 1), 256), 256, 0, s>>>(rank.p, V, stride, out.n_blk, BLK_ROWS, unit,
-                                                                             out.item_off.p, rank_base.p, out.blk_item.p);
+  k_block_items<<<grid_for((long long)V * (out.n_blk + 1), 256), 256, 0, s>>>(base.p, V, out.n_blk, unit, out.item_off.p,
+                                                                             rank_base.p, out.blk_item.p);
   SCN_LAUNCH_CHECK();
-  rank.release(s);
+  cnt.release(s);
+  base.release(s);
   rank_base.release(s);
   tmp.release(s);
 }
@@ -524,15 +573,14 @@ void build_input_level(Meta *m, const int64_t size[3], const int64_t *coords, bo
 }
 
 static void build_hash(Level *L, cudaStream_t s) {
-  if (L->hkeys.p) return;
+  if (L->htab.p) return;
   uint32_t cap = 1024;
   while (cap < 2u * (uint32_t)L->n) cap <<= 1;
   L->hmask = cap - 1;
-  L->hkeys.alloc(cap, s);
-  L->hvals.alloc(cap, s);
-  SCN_CUDA(cudaMemsetAsync(L->hkeys.p, 0xFF, sizeof(uint64_t) * cap, s));
+  L->htab.alloc(cap, s);
+  SCN_CUDA(cudaMemsetAsync(L->htab.p, 0xFF, sizeof(ulonglong2) * cap, s));
   if (L->n) {
-    k_hash_insert<<<grid_for(L->n, 256), 256, 0, s>>>(L->keys.p, L->n, L->hkeys.p, L->hvals.p, L->hmask);
+    k_hash_insert<<<grid_for(L->n, 256), 256, 0, s>>>(L->keys.p, L->n, L->htab.p, L->hmask);
     SCN_LAUNCH_CHECK();
   }
 }
@@ -624,7 +672,7 @@ void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
   if (L->nbr.p) return;
   Level *K = L->base ? L->base : L;       // the scale whose rows and hash this table is built on
   // algorithmic bytes: 27 key probes x 8 B + 12 B of coordinates + 27 x 4 B of table per row, + the hash insert
-  ProfScope ps(PK_RULEBOOK, (27.0 * 8 + 12 + 27.0 * 4 + (K->hkeys.p ? 0.0 : 8 + 12)) * (double)L->n, 0.0, s);
+  ProfScope ps(PK_RULEBOOK, (27.0 * 8 + 12 + 27.0 * 4 + (K->htab.p ? 0.0 : 8 + 12)) * (double)L->n, 0.0, s);
   build_hash(K, s);
   L->nbr.alloc((size_t)27 * L->n_pad, s);
   DevBuf<unsigned long long> cnt;
@@ -635,7 +683,7 @@ void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
       SCN_CUDA(cudaMemsetAsync(L->nbr.p + (size_t)k * L->n_pad + L->n, 0xFF, sizeof(int) * (size_t)(L->n_pad - L->n), s));
   if (L->n) {
     L->row_key.alloc((size_t)L->n, s);
-    k_neighbours<<<grid_for(L->n, 256), 256, 0, s>>>(K->keys.p, L->n, L->n_pad, K->hkeys.p, K->hvals.p, K->hmask,
+    k_neighbours<<<grid_for(L->n, 256), 256, 0, s>>>(K->keys.p, L->n, L->n_pad, K->htab.p, K->hmask,
                                                      L->nbr.p, cnt.p, L->row_key.p, sort_block(), L->dilation);
     SCN_LAUNCH_CHECK();
   }
