@@ -419,9 +419,15 @@ static std::atomic<int> g_depth_hint{0};
 
 static void prebuild_scales(Meta *m, cudaStream_t s) {
   const int depth = g_depth_hint.load();
+  // rule counts are not waited for one by one: each copy is resolved after the synchronisation of the NEXT coarse scale's row
+  // count (which the chain needs anyway), the last one by one final wait -- 7 host synchronisations per batch instead of 12
+  struct Resolve {
+    Meta *m; cudaStream_t s;
+    ~Resolve() { try { resolve_rule_counts(m, s, true); } catch (...) { m->pending_counts.clear(); } }
+  } resolve_at_exit{m, s};
   for (int i = 0; i + 1 <= depth; ++i) {
     Level *L = m->levels.back();
-    ensure_neighbour_table(m, L, s);
+    ensure_neighbour_table(m, L, s, true);
     if (i + 1 == depth) break;
     int64_t coarse[3];
     bool ok = L->n > 0;
@@ -431,6 +437,7 @@ static void prebuild_scales(Meta *m, cudaStream_t s) {
     }
     if (!ok) break;
     ensure_coarse_level(m, L, coarse, s);
+    resolve_rule_counts(m, s, false);        // ensure_coarse_level has just synchronised the stream
   }
 }
 

@@ -166,6 +166,7 @@ struct Level {
 
 struct Meta {
   int device = 0;
+  std::vector<std::pair<Level *, int>> pending_counts;   // (scale, slot) whose n_rules is still on its way
   cudaStream_t last_stream = nullptr;   // stream of the most recent entry that used this handle (scn_meta_destroy frees on it)
   int batch = 0;
   int mode = 0;
@@ -200,7 +201,10 @@ Level *find_level(Meta *m, const int64_t size[3]);
 // meta.cu
 void build_input_level(Meta *m, const int64_t size[3], const int64_t *coords, bool on_device, long long P, int batch,
                        int mode, cudaStream_t s);
-void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s);
+// defer = true (only while a whole chain of scales is built, prebuild_scales): the rule count is copied to pinned host memory
+// without waiting; resolve_rule_counts() reads it after the next synchronisation the chain performs anyway
+void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s, bool defer = false);
+void resolve_rule_counts(Meta *m, cudaStream_t s, bool synchronise);
 Level *dilated_level(Meta *m, Level *L, int rate, cudaStream_t s);    // rate 1 = L itself; table built on return
 void ensure_guided_tables(Meta *m, Level *L, cudaStream_t s);          // nbr_g / nbr_t of a scale that carries normals
 constexpr int SORT_BLOCK_DEFAULT = 262144;

@@ -667,8 +667,23 @@ void ensure_sorted_table(Level *L, cudaStream_t s) {
   L->row_key.release(s);
 }
 
-void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
-  (void)m;
+// Deferred rule counts: valid once the stream has been synchronised after the copies were enqueued.  The pinned slots belong
+// to the calling thread and live for the life of the process (cudaHostAlloc / cudaFreeHost synchronise the device: one pair
+// per handle cost more than the waits it saved); they are in use only inside one prebuild_scales call at a time.
+static unsigned long long *pinned_count_slots() {
+  static thread_local unsigned long long *slots = nullptr;
+  if (!slots) SCN_CUDA(cudaHostAlloc((void **)&slots, 16 * sizeof(unsigned long long), cudaHostAllocPortable));
+  return slots;
+}
+void resolve_rule_counts(Meta *m, cudaStream_t s, bool synchronise) {
+  if (m->pending_counts.empty()) return;
+  if (synchronise) SCN_CUDA(cudaStreamSynchronize(s));
+  const unsigned long long *slots = pinned_count_slots();
+  for (auto &pc : m->pending_counts) pc.first->n_rules = (long long)slots[pc.second];
+  m->pending_counts.clear();
+}
+
+void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s, bool defer) {
   if (L->nbr.p) return;
   Level *K = L->base ? L->base : L;       // the scale whose rows and hash this table is built on
   // algorithmic bytes: 27 key probes x 8 B + 12 B of coordinates + 27 x 4 B of table per row, + the hash insert
@@ -687,9 +702,18 @@ void ensure_neighbour_table(Meta *m, Level *L, cudaStream_t s) {
                                                      L->nbr.p, cnt.p, L->row_key.p, sort_block(), L->dilation);
     SCN_LAUNCH_CHECK();
   }
+  if (defer && m->pending_counts.size() < 16) {
+    // the count travels to pinned memory behind the kernel; the caller resolves it after its next synchronisation
+    const int slot = (int)m->pending_counts.size();
+    SCN_CUDA(cudaMemcpyAsync(pinned_count_slots() + slot, cnt.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    m->pending_counts.emplace_back(L, slot);
+    L->n_rules = 0;
+    cnt.release(s);
+    return;
+  }
   unsigned long long h = 0;
   SCN_CUDA(cudaMemcpyAsync(&h, cnt.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-  SCN_CUDA(cudaStreamSynchronize(s));   // once per scale per batch: the MAC count is part of the API
+  SCN_CUDA(cudaStreamSynchronize(s));   // the MAC count is part of the API
   L->n_rules = (long long)h;
   cnt.release(s);
 }
