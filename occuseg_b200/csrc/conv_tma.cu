@@ -72,7 +72,6 @@ static CUtensorMap make_map(const void *base, bool bf16, uint64_t cols, uint64_t
 
 // ------------------------------------------------------------------------------------------ device helpers
 constexpr int TM = 128;
-constexpr int KCH = 32;
 constexpr int A_STAGE = TM * 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -327,7 +326,6 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler
   const int n0 = blockIdx.y * p.TN;
   const int KC = p.c_in / p.kelems;
-  const int ipg = p.V * KC;                                   // items per tile group
   const int G = gridDim.x;
   const int acc_cols = p.MT * p.TN;
   // table rows (taps) present in tile group tg; every role derives the group's item list from it
