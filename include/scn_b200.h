@@ -63,6 +63,11 @@ int scn_pool_trim(int device, int64_t keep_bytes);
  * order of fp32 accumulation inside the BatchNorm statistics.  0 = natural row order.  Default 262144, or the value of the
  * SCN_TILE_SORT environment variable.  Applies to handles created afterwards.  Returns the previous setting. */
 int scn_tile_sort(int block_rows);
+/* Deterministic mode (default off, or the SCN_DETERMINISTIC environment variable): weight gradients and column statistics --
+ * everywhere partial results of row ranges / CTAs are otherwise merged with floating-point atomics (as the reference merges them,
+ * CUDA/Convolution.cu) -- are written one partial per range into scratch and added in range order, so that two runs on the same
+ * inputs give bit-identical outputs and gradients.  Costs a few per cent of extra traffic.  Returns the previous setting. */
+int scn_deterministic(int on);
 
 /* ---- InputLayer: replaces InputLayer_updateOutput's Metadata::inputLayer -> inputLayerRulesSimple
  * (CUDA/IOLayers.cpp:17-80, Metadata/Metadata.cpp:425-437, Metadata/IOLayersRules.h:136-202).

@@ -25,6 +25,7 @@ PROTOTYPES = {
     "scn_meta_destroy": (None, [_vp]),
     "scn_pool_trim": (C.c_int, [C.c_int, C.c_int64]),
     "scn_tile_sort": (C.c_int, [C.c_int]),
+    "scn_deterministic": (C.c_int, [C.c_int]),
     "scn_input_normals": (C.c_int, [_vp, _vp, C.c_int]),
     "scn_guided": (C.c_int, [_vp, _i64p]),
     "scn_subm_guided_table": (C.c_int, [_vp, _i64p, _vp, _vp, _vp]),
@@ -117,6 +118,12 @@ def trim_memory(device=None, keep_bytes=0):
 def tile_sort(block_rows):
     """Rows per pattern-sort block of the tensor-core tile order (0 = natural order); returns the previous setting."""
     return int(lib().scn_tile_sort(int(block_rows)))
+
+
+def deterministic(on):
+    """Deterministic mode of the library (scn_deterministic): reductions merged in a fixed order instead of with floating-point
+    atomics; returns the previous setting."""
+    return bool(lib().scn_deterministic(1 if on else 0))
 
 
 def launch_count():

@@ -25,7 +25,8 @@ template <int VEC, int MODE>
 __global__ void __launch_bounds__(RED_THREADS) k_bn_reduce(const float *__restrict__ x, const float *__restrict__ invstd,
                                                           const float *__restrict__ d, const float *__restrict__ mean,
                                                           const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                          long long n, int C, float leak, double *__restrict__ acc) {
+                                                          long long n, int C, float leak, double *__restrict__ acc,
+                                                          long long part_stride) {
   const int cv = C / VEC;
   const int row_lanes = blockDim.x / cv;
   const int cg = threadIdx.x % cv, rl = threadIdx.x / cv;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_bn_reduce(const float *__restri
     const int which = e / C, c = e - which * C;
     double t = 0.0;
     for (int i = 0; i < row_lanes; ++i) t += red[(which * row_lanes + i) * C + c];
-    atomicAdd(&acc[which * C + c], t);
+    atomicAdd(&acc[blockIdx.x * part_stride + which * C + c], t);
   }
 }
 
@@ -331,9 +332,20 @@ void bn_fwd(const float *in, float *out, uint16_t *out_bf16, const double *stats
     const bool r4 = v4 && C / 4 <= RED_THREADS;
     SCN_CHECK(r4 || C <= RED_THREADS, "BatchNorm: more than 256 channels need 16-byte aligned rows");
     const RedCfg rc = reduce_cfg(n, C, r4 ? 4 : 1);
-    if (r4) k_bn_reduce<4, 0><<<rc.grid, rc.threads, rc.smem, s>>>(in, nullptr, nullptr, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
-    else k_bn_reduce<1, 0><<<rc.grid, rc.threads, rc.smem, s>>>(in, nullptr, nullptr, nullptr, nullptr, nullptr, n, C, 0.f, acc.p);
+    DevBuf<double> part;              // deterministic mode: one zeroed slice per CTA, summed in CTA order
+    double *dst = acc.p;
+    long long ps = 0;
+    if (deterministic() && rc.grid > 1) {
+      part.alloc((size_t)rc.grid * 2 * C, s);
+      SCN_CUDA(cudaMemsetAsync(part.p, 0, sizeof(double) * part.n, s));
+      dst = part.p;
+      ps = 2ll * C;
+    }
+    if (r4) k_bn_reduce<4, 0><<<rc.grid, rc.threads, rc.smem, s>>>(in, nullptr, nullptr, nullptr, nullptr, nullptr, n, C, 0.f, dst, ps);
+    else k_bn_reduce<1, 0><<<rc.grid, rc.threads, rc.smem, s>>>(in, nullptr, nullptr, nullptr, nullptr, nullptr, n, C, 0.f, dst, ps);
     SCN_LAUNCH_CHECK();
+    if (part.p) sum_partials(part.p, rc.grid, 2ll * C, acc.p, s);
+    part.release(s);
   }
   k_bn_finalize_fwd<<<(C + 127) / 128, 128, 0, s>>>(acc_use, n, C, eps, momentum, train, save_mean, save_invstd,
                                                     running_mean, running_var);
@@ -362,9 +374,20 @@ void bn_bwd(const float *in, const float *out, const float *d_out, const float *
   const bool r4 = v4 && C / 4 <= RED_THREADS;
   SCN_CHECK(r4 || C <= RED_THREADS, "BatchNorm: more than 256 channels need 16-byte aligned rows");
   const RedCfg rc = reduce_cfg(n, C, r4 ? 4 : 1);
-  if (r4) k_bn_reduce<4, 1><<<rc.grid, rc.threads, rc.smem, s>>>(in, save_invstd, d_out, save_mean, gamma, beta, n, C, leakiness, acc.p);
-  else k_bn_reduce<1, 1><<<rc.grid, rc.threads, rc.smem, s>>>(in, save_invstd, d_out, save_mean, gamma, beta, n, C, leakiness, acc.p);
+  DevBuf<double> part;                // deterministic mode: see bn_fwd
+  double *dst = acc.p;
+  long long ps = 0;
+  if (deterministic() && rc.grid > 1) {
+    part.alloc((size_t)rc.grid * 2 * C, s);
+    SCN_CUDA(cudaMemsetAsync(part.p, 0, sizeof(double) * part.n, s));
+    dst = part.p;
+    ps = 2ll * C;
+  }
+  if (r4) k_bn_reduce<4, 1><<<rc.grid, rc.threads, rc.smem, s>>>(in, save_invstd, d_out, save_mean, gamma, beta, n, C, leakiness, dst, ps);
+  else k_bn_reduce<1, 1><<<rc.grid, rc.threads, rc.smem, s>>>(in, save_invstd, d_out, save_mean, gamma, beta, n, C, leakiness, dst, ps);
   SCN_LAUNCH_CHECK();
+  if (part.p) sum_partials(part.p, rc.grid, 2ll * C, acc.p, s);
+  part.release(s);
   k_bn_finalize_bwd<<<(C + 127) / 128, 128, 0, s>>>(acc.p, n, C, save_invstd, d_gamma, d_beta, coef.p, nullptr);
   SCN_LAUNCH_CHECK();
   size_t smem = sizeof(float) * 5 * C;

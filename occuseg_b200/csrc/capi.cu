@@ -393,6 +393,7 @@ scn_meta *scn_meta_create(int device) {
 }
 
 int scn_tile_sort(int block_rows) { return set_tile_sort(block_rows); }
+int scn_deterministic(int on) { return set_deterministic(on); }
 
 int scn_pool_trim(int device, int64_t keep_bytes) {
   SCN_TRY

@@ -208,6 +208,14 @@ void resolve_rule_counts(Meta *m, cudaStream_t s, bool synchronise);
 Level *dilated_level(Meta *m, Level *L, int rate, cudaStream_t s);    // rate 1 = L itself; table built on return
 void ensure_guided_tables(Meta *m, Level *L, cudaStream_t s);          // nbr_g / nbr_t of a scale that carries normals
 constexpr int SORT_BLOCK_DEFAULT = 262144;
+// Deterministic mode (scn_deterministic / SCN_DETERMINISTIC=1): every reduction whose partial results are otherwise merged with
+// floating-point atomics (weight gradients, column statistics) writes one partial per row range / CTA into scratch and
+// sum_partials adds them in range order -- run-to-run bit-identical results for a few per cent of extra traffic.
+bool deterministic();
+int set_deterministic(int on);   // returns the previous setting
+// out[e] = sum over p = 0 .. parts-1 (in that order) of partial[p * n + e]
+void sum_partials(const float *partial, int parts, long long n, float *out, cudaStream_t s);
+void sum_partials(const double *partial, int parts, long long n, double *out, cudaStream_t s);
 bool tile_sort_enabled();
 int set_tile_sort(int block);   // returns the previous setting
 void ensure_sorted_table(Level *L, cudaStream_t s);     // builds perm / nbr_sorted / tile_mask (no-op when already built)
@@ -298,6 +306,7 @@ struct WgradArgs {
   const int *gi = nullptr, *si = nullptr, *blk_item = nullptr;
   int n_blk = 0, blk_rows = 0;
   bool table_on_a = true;
+  long long part_stride = 0;       // deterministic mode: CTAs of row range r accumulate into dw + r * part_stride (zeroed scratch)
 };
 void wgrad_simt(const WgradArgs &a, cudaStream_t s);
 bool wgrad_small_supported(const WgradArgs &a);

@@ -13,6 +13,8 @@
 //    Convolution.cu:1331-1333,1372; no 27 blocking rule uploads, :793-798);
 //  * taps with no present neighbour in the tile are skipped.
 #include "common.cuh"
+#include <atomic>
+#include <cstdlib>
 
 namespace scn {
 
@@ -285,6 +287,57 @@ void transpose_weight(const float *src, float *dst, int V, int c_in, int c_out, 
   SCN_LAUNCH_CHECK();
 }
 
+static std::atomic<int> g_deterministic{[] {
+  const char *e = getenv("SCN_DETERMINISTIC");
+  return e ? (atoi(e) != 0 ? 1 : 0) : 0;
+}()};
+bool deterministic() { return g_deterministic.load(std::memory_order_relaxed) != 0; }
+int set_deterministic(int on) { return g_deterministic.exchange(on ? 1 : 0); }
+
+// Fixed summation tree: 16 part-lanes per element each add every 16th partial in ascending order, then the 16 lane sums are
+// added in lane order -- the same order on every run, without a 600-step dependent chain per element (the column statistics of a
+// convolution are 128 elements x 592 partials).
+constexpr int SP_LANES = 16;
+template <typename T>
+__global__ void __launch_bounds__(32 * SP_LANES) k_sum_partials(const T *__restrict__ partial, int parts, long long n,
+                                                               T *__restrict__ out) {
+  __shared__ T lane_sum[SP_LANES][33];
+  const long long e = blockIdx.x * 32ll + threadIdx.x;
+  T acc = T(0);
+  if (e < n)
+    for (int p = threadIdx.y; p < parts; p += SP_LANES) acc += partial[(long long)p * n + e];
+  lane_sum[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && e < n) {
+    T t = lane_sum[0][threadIdx.x];
+#pragma unroll
+    for (int y = 1; y < SP_LANES; ++y) t += lane_sum[y][threadIdx.x];
+    out[e] = t;
+  }
+}
+// many elements (weight gradients): one thread per element walks the partials in order; the threads supply the parallelism
+template <typename T>
+__global__ void k_sum_partials_wide(const T *__restrict__ partial, int parts, long long n, T *__restrict__ out) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    T acc = partial[e];
+    for (int p = 1; p < parts; ++p) acc += partial[(long long)p * n + e];
+    out[e] = acc;
+  }
+}
+template <typename T> static void sum_partials_t(const T *partial, int parts, long long n, T *out, cudaStream_t s) {
+  if (n == 0 || parts == 0) return;
+  if (n >= 16384) {        // (the choice depends on sizes only, so a given layer always takes the same tree)
+    long long g = (n + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    k_sum_partials_wide<T><<<(int)(g > cap ? cap : g), 256, 0, s>>>(partial, parts, n, out);
+  } else {
+    k_sum_partials<T><<<(unsigned)((n + 31) / 32), dim3(32, SP_LANES), 0, s>>>(partial, parts, n, out);
+  }
+  SCN_LAUNCH_CHECK();
+}
+void sum_partials(const float *partial, int parts, long long n, float *out, cudaStream_t s) { sum_partials_t(partial, parts, n, out, s); }
+void sum_partials(const double *partial, int parts, long long n, double *out, cudaStream_t s) { sum_partials_t(partial, parts, n, out, s); }
+
 // y += x
 __global__ void k_axpy(const float *__restrict__ x, float *__restrict__ y, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] += x[i];
@@ -434,7 +487,7 @@ __global__ void __launch_bounds__(NT) k_wgrad(WgradArgs a, int rows_per_cta, int
     __syncthreads();
   }
   if (!any_work) return;
-  float *dw = a.dw + (long long)tap * Ca * Cb;
+  float *dw = a.dw + blockIdx.x * a.part_stride + (long long)tap * Ca * Cb;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int ca = ca0 + ty * 4 + i;
@@ -447,8 +500,10 @@ __global__ void __launch_bounds__(NT) k_wgrad(WgradArgs a, int rows_per_cta, int
   }
 }
 
-void wgrad_simt(const WgradArgs &a, cudaStream_t s) {
-  SCN_CUDA(cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.V * a.c_a * a.c_b, s));
+void wgrad_simt(const WgradArgs &a_in, cudaStream_t s) {
+  WgradArgs a = a_in;
+  const size_t n_dw = (size_t)a.V * a.c_a * a.c_b;
+  SCN_CUDA(cudaMemsetAsync(a.dw, 0, sizeof(float) * n_dw, s));
   if (a.n_rows == 0) return;
   int tiles_a = (a.c_a + BM - 1) / BM, tiles_b = (a.c_b + BN - 1) / BN;
   // enough row chunks to fill the machine a few times over, but at least 256 rows each so the final
@@ -458,9 +513,18 @@ void wgrad_simt(const WgradArgs &a, cudaStream_t s) {
   rows_per_cta = ((rows_per_cta < 256 ? 256 : rows_per_cta) + BK - 1) / BK * BK;
   dim3 grid((a.n_rows + rows_per_cta - 1) / rows_per_cta, a.V, tiles_a * tiles_b);
   bool vec = (a.c_a % 4 == 0) && (a.c_b % 4 == 0) && ((uintptr_t)a.a % 16 == 0) && ((uintptr_t)a.b % 16 == 0);
+  DevBuf<float> part;
+  if (deterministic() && grid.x > 1) {      // one zeroed slice per row chunk: a single atomic per address, summed in chunk order below
+    part.alloc(n_dw * grid.x, s);
+    SCN_CUDA(cudaMemsetAsync(part.p, 0, sizeof(float) * n_dw * grid.x, s));
+    a.dw = part.p;
+    a.part_stride = (long long)n_dw;
+  }
   if (vec) k_wgrad<true><<<grid, NT, 0, s>>>(a, rows_per_cta, tiles_b);
   else k_wgrad<false><<<grid, NT, 0, s>>>(a, rows_per_cta, tiles_b);
   SCN_LAUNCH_CHECK();
+  if (part.p) sum_partials(part.p, (int)grid.x, (long long)n_dw, a_in.dw, s);
+  part.release(s);
 }
 
 // -----------------------------------------------------------------------------------------------------

@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(SW_THREADS) k_wgrad_small_cin(WgradArgs a, int
     const int k = q * SW_TAPS + kk;
     if (k >= a.V) break;
 #pragma unroll
-    for (int i = 0; i < CIN; ++i) atomicAdd(&a.dw[((long long)k * CIN + i) * a.c_b + n0 + co], acc[kk * CIN + i]);
+    for (int i = 0; i < CIN; ++i)
+      atomicAdd(&a.dw[blockIdx.x * a.part_stride + ((long long)k * CIN + i) * a.c_b + n0 + co], acc[kk * CIN + i]);
   }
 }
 
@@ -200,8 +201,10 @@ bool wgrad_small_supported(const WgradArgs &a) {
   return a.table_on_a && a.c_a >= 1 && a.c_a <= 4 && a.V <= 32;
 }
 
-void wgrad_small(const WgradArgs &a, cudaStream_t s) {
-  SCN_CUDA(cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.V * a.c_a * a.c_b, s));
+void wgrad_small(const WgradArgs &a_in, cudaStream_t s) {
+  WgradArgs a = a_in;
+  const size_t n_dw = (size_t)a.V * a.c_a * a.c_b;
+  SCN_CUDA(cudaMemsetAsync(a.dw, 0, sizeof(float) * n_dw, s));
   if (a.n_rows == 0) return;
   const int tiles = (a.c_b + SC_TILE - 1) / SC_TILE;
   long long ctas = (long long)sm_count() * 4 / tiles;
@@ -210,6 +213,13 @@ void wgrad_small(const WgradArgs &a, cudaStream_t s) {
   rows = (rows + SW_ROWS - 1) / SW_ROWS * SW_ROWS;
   if (rows < 8 * SW_ROWS) rows = 8 * SW_ROWS;
   dim3 grid((unsigned)((a.n_rows + rows - 1) / rows), tiles);
+  DevBuf<float> part;
+  if (deterministic() && grid.x > 1) {      // see wgrad_simt
+    part.alloc(n_dw * grid.x, s);
+    SCN_CUDA(cudaMemsetAsync(part.p, 0, sizeof(float) * n_dw * grid.x, s));
+    a.dw = part.p;
+    a.part_stride = (long long)n_dw;
+  }
   switch (a.c_a) {
     case 1: k_wgrad_small_cin<1><<<grid, SW_THREADS, 0, s>>>(a, (int)rows); break;
     case 2: k_wgrad_small_cin<2><<<grid, SW_THREADS, 0, s>>>(a, (int)rows); break;
@@ -217,6 +227,8 @@ void wgrad_small(const WgradArgs &a, cudaStream_t s) {
     default: k_wgrad_small_cin<4><<<grid, SW_THREADS, 0, s>>>(a, (int)rows); break;
   }
   SCN_LAUNCH_CHECK();
+  if (part.p) sum_partials(part.p, (int)grid.x, (long long)n_dw, a_in.dw, s);
+  part.release(s);
 }
 
 }  // namespace scn

@@ -275,6 +275,7 @@ struct ConvParams {
   const float *bias;
   const float *residual;       // optional [n_rows, c_out] fp32 added to the result (residual shortcut fused into the epilogue)
   double *stats;               // optional [2][c_out]: column sums and sums of squares of the result (for the BatchNorm that follows)
+  long long stats_stride;      // deterministic mode: epilogue warp q of CTA x adds into stats + (4x + q) * stats_stride (zeroed scratch)
   // optional fused inference BatchNorm + (leaky) ReLU of the layer that follows: out = leaky(scale[c] * acc + shift[c]),
   // plus an optional bf16 copy of that result for the next tensor-core convolution
   const float *ep_scale, *ep_shift;
@@ -724,8 +725,9 @@ __global__ void __launch_bounds__(CONV_MAX_THREADS, 1) k_conv_tma(const __grid_c
       __syncwarp();
       for (int c = lane; c < p.TN; c += 32) {
         if (((c >> 4) % EPI_SPLIT) != half) continue;          // the chunks this warp accumulated
-        atomicAdd(p.stats + n0 + c, (double)my_stat[c]);
-        atomicAdd(p.stats + p.c_out + n0 + c, (double)my_stat[256 + c]);
+        double *st = p.stats + (long long)(blockIdx.x * 4 + quarter) * p.stats_stride;
+        atomicAdd(st + n0 + c, (double)my_stat[c]);
+        atomicAdd(st + p.c_out + n0 + c, (double)my_stat[256 + c]);
       }
     }
     TRC(if (p.trace && lane == 0 && quarter == 0 && half == 0) {
@@ -766,6 +768,7 @@ constexpr int WG_THREADS = 288;   // warp 0: TMEM + MMA; warps 1-4: producers; w
 
 struct WgParams {
   float *dw;
+  long long part_stride;       // deterministic mode: CTAs of row range r accumulate into dw + r * part_stride (zeroed scratch)
   const int *gi, *si, *blk_item;
   int V, Cg, Cs, transpose_out, n_blk, blk_per_range;
   int N, m_tiles, stages, nprod, stage_bytes, tmem_cols;
@@ -922,11 +925,11 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tma(const __grid_constant_
         tmem_ld32(acc + mt * p.N + c0, v);
         if (cg < p.Cg) {
           if (!p.transpose_out) {
-            float *dst = p.dw + ((long long)tap * p.Cg + cg) * p.Cs + n0 + c0;
+            float *dst = p.dw + blockIdx.y * p.part_stride + ((long long)tap * p.Cg + cg) * p.Cs + n0 + c0;
 #pragma unroll
             for (int q = 0; q < 32; q += 4) red_add_v4(dst + q, v[q], v[q + 1], v[q + 2], v[q + 3]);
           } else {
-            float *dst = p.dw + ((long long)tap * p.Cs + n0 + c0) * p.Cg + cg;
+            float *dst = p.dw + blockIdx.y * p.part_stride + ((long long)tap * p.Cs + n0 + c0) * p.Cg + cg;
 #pragma unroll
             for (int q = 0; q < 32; ++q) atomicAdd(dst + (long long)q * p.Cg, v[q]);
           }
@@ -971,6 +974,7 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   SCN_CHECK(!a.bnb_x || a.stats, "conv_tma: the fused BatchNorm backward needs the statistics buffer");
   SCN_CHECK(!(a.bnb_x && a.residual), "conv_tma: residual and fused BatchNorm backward are mutually exclusive");
   p.stats = a.stats;
+  p.stats_stride = 0;
   if (a.stats) SCN_CUDA(cudaMemsetAsync(a.stats, 0, sizeof(double) * 2 * (size_t)a.c_out, s));
   p.in = a.in; p.bias = a.bias; p.out = a.out; p.tbl = a.tbl; p.tbl_stride = a.tbl_stride; p.n_rows = a.n_rows;
   p.V = a.V; p.c_in = a.c_in; p.c_out = a.c_out; p.mirror = a.mirror ? 1 : 0;
@@ -1020,6 +1024,14 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
   if (gx < 1) gx = 1;
   if (gx > p.n_groups) gx = p.n_groups;
   dim3 grid(gx, n_tiles_n);
+  DevBuf<double> stats_part;
+  if (a.stats && deterministic()) {      // one zeroed [2][c_out] slice per (CTA, epilogue warp), summed in that order after the launch
+    static_assert(EPI_WARPS == 4, "deterministic statistics: one slice per TMEM quarter");
+    stats_part.alloc((size_t)gx * 4 * 2 * a.c_out, s);
+    SCN_CUDA(cudaMemsetAsync(stats_part.p, 0, sizeof(double) * stats_part.n, s));
+    p.stats = stats_part.p;
+    p.stats_stride = 2ll * a.c_out;
+  }
   static const int trace = env_int("SCN_TRACE", 0);
   p.trace = nullptr;
 #ifndef SCN_TRACE_BUILD
@@ -1032,6 +1044,8 @@ void conv_tma(const ConvArgs &a, cudaStream_t s) {
 #endif
   k_conv_tma<<<grid, 32 + 32 * p.nprod * p.ni + 32 * EPI_WARPS, smem, s>>>(mx, mw, p);
   SCN_LAUNCH_CHECK();
+  if (stats_part.p) sum_partials(stats_part.p, gx * 4, 2ll * a.c_out, a.stats, s);
+  stats_part.release(s);
   if (p.trace) {
     unsigned long long h[64];
     SCN_CUDA(cudaStreamSynchronize(s));
@@ -1117,8 +1131,19 @@ void wgrad_tma(const WgradArgs &a, cudaStream_t s) {
   static SmemAttrCache smem_attr;
   smem_attr.ensure(k_wgrad_tma, smem);
   dim3 grid(a.V, ranges, p.Cs / p.N);
+  DevBuf<float> part;
+  const size_t n_dw = (size_t)a.V * a.c_a * a.c_b;
+  p.part_stride = 0;
+  if (deterministic() && ranges > 1) {     // one zeroed slice per row range: a single addend per address, summed in range order below
+    part.alloc(n_dw * ranges, s);
+    SCN_CUDA(cudaMemsetAsync(part.p, 0, sizeof(float) * n_dw * ranges, s));
+    p.dw = part.p;
+    p.part_stride = (long long)n_dw;
+  }
   k_wgrad_tma<<<grid, WG_THREADS, smem, s>>>(mg, ms, p);
   SCN_LAUNCH_CHECK();
+  if (part.p) sum_partials(part.p, ranges, (long long)n_dw, a.dw, s);
+  part.release(s);
 }
 
 }  // namespace scn

@@ -23,6 +23,12 @@ _PRECISIONS = {"fp32": _lib.FP32, "tf32": _lib.TF32, "bf16": _lib.BF16}
 _precision = _PRECISIONS[os.environ.get("SCN_B200_PRECISION", "fp32").lower()]
 
 
+def set_deterministic(on=True):
+    """Run-to-run bit-identical results: weight gradients and column statistics are summed in a fixed order instead of with
+    floating-point atomics (off by default, as in the reference; also SCN_DETERMINISTIC=1).  Returns the previous setting."""
+    return _lib.deterministic(on)
+
+
 def set_precision(name):
     """'fp32' (default) = exact FMA path everywhere; 'tf32' / 'bf16' = tcgen05 tiles (tf32 operands / bf16 copies of
     the operands, fp32 accumulate and fp32 results) where the channel counts allow, exact fp32 elsewhere."""

@@ -3,7 +3,7 @@
     import occuseg_b200.sparseconvnet as scn          # or occuseg_b200.install_as_sparseconvnet()
 """
 from . import SCN
-from .SCN import set_precision, get_precision
+from .SCN import set_precision, get_precision, set_deterministic
 from .architectures import UNet
 from .functions import counters
 from .layers import (AddTable, BatchNormalization, BatchNormLeakyReLU, BatchNormReLU, ConcatTable, Convolution,

@@ -445,3 +445,33 @@ def test_device_side_augmentation_and_coordinates():
     t = scn.InputLayer(3, SIZE, mode=4)([c0, torch.ones(len(c0), 3, device="cuda"), None, 1])
     vox = rb.voxelize(c0.cpu().numpy(), 1)
     assert np.array_equal(t.metadata.getSpatialLocations(lt(SIZE)).numpy(), vox["locs"])
+
+
+# ------------------------------------------------------------------------------------------- deterministic mode
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_deterministic_mode_is_bit_reproducible(precision):
+    """scn.set_deterministic(True): two training steps of a residual UNet from the same state give bit-identical outputs and
+    gradients (weight gradients, column statistics and BatchNorm reductions summed in a fixed order instead of with atomics),
+    and the same values as the default mode up to the rounding of the merge order."""
+    coords, feats = scenes.make_batch("small", (7, 8))
+
+    def step():
+        scn.set_precision(precision)
+        net = _net([64, 128, 192], seed=21).cuda()
+        out = net([torch.from_numpy(coords), cu(feats), None, 2])
+        out.square().mean().backward()
+        torch.cuda.synchronize()
+        return out.detach().clone(), [p.grad.detach().clone() for p in net.parameters()]
+
+    prev = scn.set_deterministic(True)
+    try:
+        o1, g1 = step()
+        o2, g2 = step()
+    finally:
+        scn.set_deterministic(prev)
+    assert torch.equal(o1, o2)
+    assert all(torch.equal(a, b) for a, b in zip(g1, g2))
+    o0, g0 = step()                                  # default mode: same numbers up to summation order
+    assert rel_err(o0.cpu().numpy(), o1.cpu().numpy()) < 1e-4
+    for a, b in zip(g0, g1):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < (1e-3 if precision == "fp32" else 2e-2)
