@@ -11,7 +11,7 @@ opt = torch.optim.Adam(net.parameters(), lr=1e-3, fused=True)
 coords, feats = scenes.make_batch("S250k", tuple(range(8)))
 c, f = torch.from_numpy(coords).cuda(), torch.from_numpy(feats).cuda()
 def step():
-    out = net([c, f, None, 8]); out.square().mean().backward(); opt.step(); opt.zero_grad(set_to_none=False)
+    out = net([c, f, None, 8]); out.square().mean().backward(); opt.step(); opt.zero_grad(set_to_none=True)
 for _ in range(3): step()
 torch.cuda.synchronize()
 t0 = time.perf_counter()

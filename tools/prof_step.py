@@ -15,6 +15,6 @@ for _ in range(steps):
     out = net([c, f, None, 8])
     out.square().mean().backward()
     opt.step()
-    opt.zero_grad(set_to_none=False)
+    opt.zero_grad(set_to_none=True)
 torch.cuda.synchronize()
 print("done")
