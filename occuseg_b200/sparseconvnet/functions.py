@@ -39,7 +39,7 @@ class SubmanifoldConvolutionFunction(Function):
     @staticmethod
     def backward(ctx, grad_out, _grad_stats=None):
         x, spatial_size, weight, bias, filter_size = ctx.saved_tensors
-        gw, gb = torch.zeros_like(weight), torch.zeros_like(bias)
+        gw, gb = torch.empty_like(weight), torch.zeros_like(bias)      # d_weight is overwritten by the entry (it zeroes it itself)
         # the layer behind the InputLayer has no use for d_input (point features are data): skip that product
         gx = grad_out.new_empty(0) if ctx.needs_input_grad[0] else None
         SCN.bf16_operand_again(ctx.scn_meta, x, ctx.x16)
@@ -66,7 +66,7 @@ class _StridedFunction(Function):
     @classmethod
     def _backward(cls, ctx, grad_out):
         x, in_size, weight, bias, out_size, filter_size, filter_stride = ctx.saved_tensors
-        gx, gw, gb = grad_out.new_empty(0), torch.zeros_like(weight), torch.zeros_like(bias)
+        gx, gw, gb = grad_out.new_empty(0), torch.empty_like(weight), torch.zeros_like(bias)
         SCN.bf16_operand_again(ctx.scn_meta, x, ctx.x16)
         cls.bwd(in_size, out_size, filter_size, filter_stride, ctx.scn_meta, x, gx, grad_out.contiguous(), weight, gw, gb)
         del ctx.scn_meta, ctx.x16
@@ -122,7 +122,9 @@ class BatchNormalizationFunction(Function):
     def backward(ctx, grad_out, _grad_out16=None, grad_alias=None):
         x, weight, bias, running_mean, running_var, save_mean, save_invstd = ctx.saved_tensors
         assert ctx.train, "BatchNormalization backward is only defined in training mode (as in the reference)"
-        gx, gw, gb = grad_out.new_empty(0), torch.zeros_like(weight), torch.zeros_like(bias)
+        # d_gamma / d_beta are written for every channel by the entry (unless there are no rows at all)
+        fresh = torch.empty_like if x.size(0) else torch.zeros_like
+        gx, gw, gb = grad_out.new_empty(0), fresh(weight), fresh(bias)
         add = grad_alias.contiguous() if grad_alias is not None and grad_alias.numel() == x.numel() else None
         SCN.BatchNormalization_backward(x, gx, None, grad_out.contiguous(), save_mean, save_invstd, running_mean,
                                         running_var, weight, bias, gw, gb, ctx.leakiness, add)
@@ -182,7 +184,7 @@ class BatchNormConvFunction(Function):
         g = grad_out          # may be a column slice of a JoinTable's gradient: read in place (SCN._grad_operand)
         acc = torch.empty((2, x.size(1)), dtype=torch.float64, device=x.device)      # zeroed by the convolution entry
         d_masked = g.new_empty(0)
-        gw, gb = torch.zeros_like(conv_weight), torch.zeros_like(conv_bias)
+        gw, gb = torch.empty_like(conv_weight), torch.zeros_like(conv_bias)
         SCN.BatchNormalization_backwardFusion(m, x, save_mean, save_invstd, bn_weight, bn_bias, ctx.leakiness, acc)
         bwd = BatchNormConvFunction.KINDS[kind][1]
         if kind == "subm":
@@ -190,7 +192,8 @@ class BatchNormConvFunction(Function):
         else:
             bwd(in_size, out_size, filter_size, filter_stride, m, None, d_masked, g, conv_weight, gw, gb, input_bf16=y16)
         gx = g.new_empty(0)
-        g_gamma, g_beta = torch.zeros_like(bn_weight), torch.zeros_like(bn_bias)
+        fresh = torch.empty_like if x.size(0) else torch.zeros_like      # written for every channel by the entry
+        g_gamma, g_beta = fresh(bn_weight), fresh(bn_bias)
         add = grad_alias if grad_alias is not None and grad_alias.numel() == x.numel() else None
         # the gradient leaves with a bf16 copy attached: the convolution that produced x receives it as its d_out and reads the
         # copy instead of casting (SCN._grad_operand); dropped silently if autograd adds another gradient to it on the way
