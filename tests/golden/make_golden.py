@@ -95,7 +95,81 @@ def make(name, preset, seeds, cin, cout, seed):
     print(name, "N", N, "Nc", Nc, "rules", len(sf), os.path.getsize(out) // 1024, "KiB")
 
 
+def make_guided(name, preset, seeds, c, seed):
+    """Normal-guided rules (OccuSeg's use_normal): the lists are oracle/rulebook.py's restatement, checked here against the
+    reference's compiled builders (remap_rules_with_normal on GPU-ordered lists, the CPU normal-guided builder, the normal-guided
+    2/2 builder) before they are written; y / dx / dw and the strided results are outputs of the reference's CPU arithmetic on
+    those lists -- run SINGLE-THREADED: the reference's rule_index_add_ (CPU/Convolution.cpp:21-33) is an OpenMP loop without
+    atomics that relies on a target row appearing at most once per list, which guided lists do not guarantee for d_input (an
+    input row can feed two outputs of different orientation classes through the same permuted tap); with several threads its
+    d_input loses updates."""
+    assert os.environ.get("OMP_NUM_THREADS") == "1", "generate the guided fixture with OMP_NUM_THREADS=1 (see the docstring)"
+    assert reference.available() and rr.available(), "oracle/_ref not built"
+    rng = np.random.default_rng(seed)
+    coords, _ = scenes.make_batch(preset, seeds)
+    coords = np.concatenate([coords, coords[:37]], 0)
+    coords = coords[np.argsort(coords[:, 3], kind="stable")]
+    B = len(seeds)
+    pn = rng.standard_normal((len(coords), 3)).astype(np.float32)
+    pn /= np.linalg.norm(pn, axis=1, keepdims=True)
+    pn[::19] = 0
+    pn[3::29] = np.float32([[0.5, 0.0, 0.5]])
+    vox = rb.voxelize(coords, B)
+    locs = vox["locs"]
+    N = len(locs)
+    vn = rb.voxel_normals(pn, vox)
+    ori = rb.oriented_filter(vn)
+    guided = rb.guided_submanifold_rules(rb.submanifold_rules(locs, B), vn)
+    clocs, strided, cn = rb.guided_strided_rules(locs, vn, B)
+    Nc = len(clocs)
+    # pin against the reference-compiled builders (rows matched through coordinates)
+    sc = rr.Scene(coords, B, 4)
+    row_of = {tuple(l): i for i, l in enumerate(locs.tolist())}
+    mine_of_ref = np.array([row_of[tuple(l)] for l in sc.locs.tolist()])
+    mine = rr.relation_of_lists(guided, locs)
+    assert np.array_equal(sc.submanifold(3, normals=vn[mine_of_ref]), mine)
+    assert np.array_equal(sc.submanifold(1, normals=vn[mine_of_ref]), mine)
+    rel, rcl, rcn = sc.strided(normals=vn[mine_of_ref])
+    crow = {tuple(l): i for i, l in enumerate(clocs.tolist())}
+    order = np.array([crow[tuple(l)] for l in rcl.tolist()])
+    assert np.allclose(rcn, cn[order], rtol=0, atol=1e-6)
+    a = np.sort(np.abs(cn), 1)
+    tie = (a[:, 2] - a[:, 1]) < 1e-5                 # class unspecified in the reference itself (hash-map summation order)
+    key = lambda r: r[np.lexsort(r[:, 1:].T[::-1])]
+    ra, rm = key(rel), key(rr.relation_of_lists(strided, locs, clocs))
+    assert np.array_equal(ra[:, 1:], rm[:, 1:])
+    crows = np.array([crow[tuple(l)] for l in ra[:, 4:8].tolist()])
+    assert np.array_equal(ra[~tie[crows], 0], rm[~tie[crows], 0])
+    R = reference.Ref()
+    R.load_submanifold(4096, guided, N)
+    R.load_strided(4096, 2048, strided, N, Nc)
+    x = rng.standard_normal((N, c)).astype(np.float32)
+    w = (rng.standard_normal((27, c, c)) * (2.0 / c / 27) ** 0.5).astype(np.float32)
+    g = rng.standard_normal((N, c)).astype(np.float32)
+    y, _ = R.subm_forward(4096, x, w)
+    dx, dw = R.subm_backward(4096, x, g, w)
+    w8 = (rng.standard_normal((8, c, c)) * (2.0 / c / 8) ** 0.5).astype(np.float32)
+    gc = rng.standard_normal((Nc, c)).astype(np.float32)
+    yc, _ = R.conv_forward(4096, 2048, x, w8)
+    dxc, dw8 = R.conv_backward(4096, 2048, x, gc, w8)
+    gf, go = pack(rb.canonical(guided))
+    tf, to = pack(rb.canonical(strided))
+    out = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(
+        out, coords=coords.astype(np.int32), batch=np.int64(B), point_normals=pn, locs=locs.astype(np.int32),
+        voxel_normals=vn, ori=ori, guided_flat=gf, guided_off=go, coarse_locs=clocs.astype(np.int32), coarse_normals=cn,
+        strided_flat=tf, strided_off=to, coarse_ties=tie, x=x, w=w, g=g, y=y, dx=dx, dw=dw, w8=w8, gc=gc, yc=yc, dxc=dxc, dw8=dw8)
+    print(name, "N", N, "Nc", Nc, "ties", int(tie.sum()), os.path.getsize(out) // 1024, "KiB")
+
+
 if __name__ == "__main__":
+    if os.environ.get("OMP_NUM_THREADS") != "1":          # the guided fixture needs the serial reference arithmetic
+        os.environ["OMP_NUM_THREADS"] = "1"
+        os.execv(sys.executable, [sys.executable] + sys.argv)
+    if "--guided-only" in sys.argv:
+        make_guided("guided_b2_c16", (0.30, 0.24, 0.20, 1), (9, 10), 16, seed=14)
+        sys.exit(0)
     make("room_b2_c16", (0.36, 0.30, 0.24, 1), (3, 4), 16, 16, seed=11)
     make("room_b1_c3_8", (0.30, 0.24, 0.20, 1), (5,), 3, 8, seed=12)
     make("room_b3_c32_64", (0.30, 0.24, 0.20, 1), (6, 7, 8), 32, 64, seed=13)
+    make_guided("guided_b2_c16", (0.30, 0.24, 0.20, 1), (9, 10), 16, seed=14)

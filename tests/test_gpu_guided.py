@@ -192,3 +192,37 @@ def test_guided_network_step_runs_through_the_public_api(precision):
         out0, grads0 = step("fp32")
         l2 = lambda a, b: np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
         assert l2(out, out0) < 5e-2
+
+
+def test_guided_golden_fixture():
+    """The committed fixture (reference-checked lists, reference CPU arithmetic): CUDA normals / classes / guided tables / guided
+    2/2 rules bit-exact, fp32 products within 1e-5 of the reference outputs."""
+    from conftest import load_golden, unpack
+    g = load_golden("guided_b2_c16")
+    B = int(g["batch"])
+    coords = g["coords"].astype(np.int64)
+    m = _guided_meta(coords, g["point_normals"], B, SIZE)
+    N = len(g["locs"])
+    assert np.array_equal(m.getSpatialLocations(lt(SIZE)).numpy(), g["locs"])
+    assert np.array_equal(m.normalsOf(lt(SIZE)).numpy(), g["voxel_normals"])
+    tbl, ori = m.submanifoldGuidedTable(lt(SIZE))
+    assert np.array_equal(ori.numpy(), g["ori"])
+    assert np.array_equal(tbl.numpy(), _table(unpack(g["guided_flat"], g["guided_off"]), N))
+    parent, off, nc = m.stridedTable(lt(SIZE), lt(SIZE // 2))
+    assert nc == len(g["coarse_locs"]) and np.array_equal(m.normalsOf(lt(SIZE // 2)).numpy(), g["coarse_normals"])
+    got = _strided_lists(parent.numpy(), off.numpy())
+    assert all(np.array_equal(a, b) for a, b in zip(rb.canonical(got), unpack(g["strided_flat"], g["strided_off"])))
+    scn.set_precision("fp32")
+    c = g["x"].shape[1]
+    conv = scn.SubmanifoldConvolution(3, c, c, 3, False).cuda()
+    down = scn.Convolution(3, c, c, 2, 2, False).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(cu(g["w"]))
+        down.weight.copy_(cu(g["w8"]))
+    for layer, gout, ky, kdx, kdw in ((conv, g["g"], "y", "dx", "dw"), (down, g["gc"], "yc", "dxc", "dw8")):
+        xin = cu(g["x"]).requires_grad_(True)
+        y = layer(scn.SparseConvNetTensor(xin, m, lt(SIZE))).features
+        y.backward(cu(gout))
+        assert rel_err(y.detach().cpu().numpy(), g[ky]) < FP32_TOL
+        assert rel_err(xin.grad.cpu().numpy(), g[kdx]) < FP32_TOL
+        assert rel_err(layer.weight.grad.cpu().numpy(), g[kdw]) < FP32_TOL

@@ -4,7 +4,7 @@ and the edge cases the domain has (duplicates, single voxels, empty samples, sam
 import numpy as np
 import pytest
 
-from conftest import rel_err, unpack
+from conftest import load_golden, rel_err, unpack
 from oracle import arith, rulebook as rb
 
 
@@ -288,3 +288,29 @@ def test_normal_guided_restatement_pinned_to_reference_builders():
             coarse_row = np.array([crow[tuple(l)] for l in ra[:, 4:8].tolist()])
             assert np.array_equal(ra[~tie[coarse_row], 0], rm[~tie[coarse_row], 0])
             assert tie.sum() < 0.1 * len(cn)     # integer point normals make exact ties common (5 %)
+
+
+def test_normal_guided_golden_fixture():
+    """tests/golden/guided_b2_c16.npz (lists checked against the reference's compiled builders when it was written, floats =
+    outputs of the reference's CPU arithmetic on those lists): the restatement reproduces the integer part bit for bit, the
+    numpy port of the arithmetic the floating-point part within 1e-5 -- on a box without the reference tree too."""
+    g = load_golden("guided_b2_c16")
+    B = int(g["batch"])
+    coords = g["coords"].astype(np.int64)
+    vox = rb.voxelize(coords, B)
+    assert np.array_equal(vox["locs"], g["locs"])
+    vn = rb.voxel_normals(g["point_normals"], vox)
+    assert np.array_equal(vn, g["voxel_normals"]) and np.array_equal(rb.oriented_filter(vn), g["ori"])
+    guided = rb.guided_submanifold_rules(rb.submanifold_rules(vox["locs"], B), vn)
+    want = unpack(g["guided_flat"], g["guided_off"])
+    assert all(np.array_equal(a, b) for a, b in zip(rb.canonical(guided), want))
+    cl, strided, cn = rb.guided_strided_rules(vox["locs"], vn, B)
+    assert np.array_equal(cl, g["coarse_locs"]) and np.array_equal(cn, g["coarse_normals"])
+    assert all(np.array_equal(a, b) for a, b in zip(rb.canonical(strided), unpack(g["strided_flat"], g["strided_off"])))
+    N, Nc = len(vox["locs"]), len(cl)
+    y, _ = arith.rule_conv_forward(g["x"], g["w"], guided, N)
+    dx, dw = arith.rule_conv_backward(g["x"], g["g"], g["w"], guided)
+    assert rel_err(y, g["y"]) < 1e-5 and rel_err(dx, g["dx"]) < 1e-5 and rel_err(dw, g["dw"]) < 1e-5
+    yc, _ = arith.rule_conv_forward(g["x"], g["w8"], strided, Nc)
+    dxc, dw8 = arith.rule_conv_backward(g["x"], g["gc"], g["w8"], strided)
+    assert rel_err(yc, g["yc"]) < 1e-5 and rel_err(dxc, g["dxc"]) < 1e-5 and rel_err(dw8, g["dw8"]) < 1e-5
