@@ -314,3 +314,25 @@ def test_normal_guided_golden_fixture():
     yc, _ = arith.rule_conv_forward(g["x"], g["w8"], strided, Nc)
     dxc, dw8 = arith.rule_conv_backward(g["x"], g["gc"], g["w8"], strided)
     assert rel_err(yc, g["yc"]) < 1e-5 and rel_err(dxc, g["dxc"]) < 1e-5 and rel_err(dw8, g["dw8"]) < 1e-5
+
+
+def test_tile_order_key_puts_rare_taps_on_top():
+    """The design claim behind the sort key of the tile order (occuseg_b200/csrc/meta.cu: tap_key_bit), re-derived on the CPU
+    with tools/sim_tile_order.py: sorting the rows of a scene by a key whose most significant bits are the rarely present taps
+    (corners, then edges) and whose least significant bits are the frequent ones (faces) leaves fewer non-empty (tile group,
+    tap) pairs -- pipeline items of the convolution kernel -- than the plain tap order, and both beat the natural row order."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import sim_tile_order as sim
+    from occuseg_b200 import scenes
+    coords, _ = scenes.make_batch("S100k", (0,))
+    locs = rb.voxelize(coords, 1)["locs"]
+    pat = sim.patterns_of(locs, 1)
+
+    def cls(t):
+        return (t // 9 != 1) + ((t // 3) % 3 != 1) + (t % 3 != 1)        # 0 centre, 1 face, 2 edge, 3 corner
+    shipped = sorted(range(27), key=lambda t: ({0: 0, 3: 1, 2: 2, 1: 3}[cls(t)], t))     # most significant first
+    items = {name: sim.cost(pat if order is None else sim.sorted_by(pat, sim.permute_bits(pat, order), 262144))["items"]
+             for name, order in (("natural", None), ("tap order", list(range(26, -1, -1))), ("shipped", shipped))}
+    assert items["shipped"] < 0.95 * items["tap order"] < 0.95 * items["natural"], items
